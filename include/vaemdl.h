@@ -1,0 +1,189 @@
+/*
+ * vaemdl.h -- C ABI of libvaemdl_b200.so: the B200 (sm_100a) observation-model
+ * kernels that stand in for the hot path of nbip/vae-mdl.
+ *
+ * The reference has NO native / FFI boundary for this path (it is a TensorFlow
+ * op graph built by five Python classes and two loss functions); every entry
+ * point below cites the reference code (file:line, relative to the reference
+ * root) whose computation it replaces.  The reference-side binding a maintainer
+ * would add (a ctypes stub inside utils/mdl.py etc.) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - Plain C: raw pointers + sizes, no torch / C++ types.
+ *   - Every *device* entry point is an asynchronous enqueue on `stream`
+ *     (a cudaStream_t passed as void*); nothing is allocated inside; all
+ *     buffers are caller-owned DEVICE memory unless the name ends in _host.
+ *   - Returns 0 on success, a negative VAEMDL_E* code for argument errors, or a
+ *     positive cudaError_t.  Never throws, never aborts.  Re-entrant.
+ *   - Tensors are dense row-major float32 unless stated.
+ *   - "image" n = one (importance-sample, batch) element of the flattened
+ *     leading dims (s-major, b-minor: n = s*B + b, utils/mdl_openai_iwae.py:38-46).
+ *     Image n is scored against x[n % x_batch]; x_batch = B for x [B,H,W,3],
+ *     1 for the broadcast x [H,W,3] of models/model05.py:173.
+ *   - MoDL parameter row per pixel (utils/mdl.py:98-108, utils/mdl_openai.py:90-94):
+ *       [ logit(M) | muR(M) sR(M) kR(M) | muG(M) sG(M) kG(M) | muB(M) sB(M) kB(M) ]
+ */
+#ifndef VAEMDL_H_
+#define VAEMDL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAEMDL_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VAEMDL_API __attribute__((visibility("default")))
+#else
+#define VAEMDL_API
+#endif
+
+/* error codes (negative; positive values are cudaError_t) */
+#define VAEMDL_OK 0
+#define VAEMDL_EINVAL (-1)      /* bad argument (null pointer, non-positive size, unknown enum) */
+#define VAEMDL_EALIGN (-2)      /* parameter / gradient pointer not 16-byte aligned */
+#define VAEMDL_EUNSUPPORTED (-3) /* n_mix outside [1, VAEMDL_MAX_MIX] */
+#define VAEMDL_EWORKSPACE (-4)  /* workspace too small */
+
+#define VAEMDL_MAX_MIX 64
+
+/* dtype of the observed image x */
+#define VAEMDL_X_F32 0 /* float32 */
+#define VAEMDL_X_U8 1  /* raw uint8 bytes k; the kernel forms k/255.f exactly as utils/data.py:15-16 */
+
+/* value range of x */
+#define VAEMDL_RANGE_UNIT 0 /* x in [0,1]; kernel applies x*2-1 (utils/mdl.py:65, utils/mdl_openai_iwae.py:35) */
+#define VAEMDL_RANGE_SYM 1  /* x already in [-1,1] (utils/mdl_openai.py:31-32); only valid with VAEMDL_X_F32 */
+
+/* which edge test selects the x=0 / x=255 branches */
+#define VAEMDL_EDGE_MDL 0    /* x <= -1 , x >= 1        (utils/mdl.py:200-205)        */
+#define VAEMDL_EDGE_OPENAI 1 /* x < -0.999 , x > 0.999  (utils/mdl_openai.py:139,:142) */
+
+/* sampler variants */
+#define VAEMDL_SAMPLE_OPENAI 0 /* select mixture first, one logistic draw per sub-pixel (utils/mdl_openai.py:160-193); u_log [n,H,W,3] */
+#define VAEMDL_SAMPLE_MDL 1    /* a draw for every mixture, then select (utils/mdl.py:209-252); u_log [n,H,W,3,M] */
+
+VAEMDL_API int vaemdl_version(void);
+VAEMDL_API const char* vaemdl_strerror(int code);
+
+/* ------------------------------------------------------------------------ *
+ * Mixture of discretized logistics -- log-likelihood
+ * replaces: MixtureDiscretizedLogistic._log_prob            utils/mdl.py:56-207
+ *           discretized_mix_logistic_loss(sum_all=False)    utils/mdl_openai.py:83-157
+ *           MixtureDiscretizedLogisticOpenaiIWAE._log_prob  utils/mdl_openai_iwae.py:33-67
+ *           + the caller's reduce_sum over [-1,-2,-3]       models/loss.py:32
+ *
+ * params   [n_img, H, W, 10*M]
+ * x        [x_batch, H, W, 3]  (float32 or uint8, see x_dtype / x_range)
+ * lp_pixel [n_img, H, W]   nullable -- per-pixel log-prob (what log_prob() returns, minus the trailing 1)
+ * ll_image [n_img]         nullable -- sum over H,W of lp_pixel (deterministic summation order when H*W % 32 == 0)
+ * workspace: at least vaemdl_modl_workspace_bytes(n_img, H, W) bytes (only read/written when ll_image != NULL)
+ * ------------------------------------------------------------------------ */
+VAEMDL_API size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W);
+
+VAEMDL_API int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    float* lp_pixel, float* ll_image,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Mixture of discretized logistics -- gradient w.r.t. params
+ * replaces: tf.GradientTape over the ops above              models/model05.py:141-145
+ * The upstream gradient on lp_pixel[n,h,w] is
+ *     (g_image ? g_image[n] : 0) + (g_pixel ? g_pixel[n,h,w] : 0)
+ * g_image [n_img] nullable, g_pixel [n_img,H,W] nullable (at least one non-null)
+ * dparams [n_img, H, W, 10*M]  (fully overwritten)
+ * The log-scale gradient is masked with (raw_log_scale >= -7) (tf.maximum, utils/mdl.py:109).
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    const float* g_image, const float* g_pixel,
+                    float* dparams, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Plain discretized logistic
+ * replaces: DiscretizedLogistic.log_prob   utils/discretized_logistic.py:35-78
+ *           + reduce_sum over [-1,-2,-3]   models/loss.py:32, models/model06.py:45
+ *
+ * loc, logscale: element e = (n, i) with i < D = H*W*C lives at  ptr[(n*D + i)/C*ld + (n*D+i)%C]
+ *                i.e. a [.., C] tensor with channel-row stride `ld` floats
+ *                (ld = C for separate tensors; ld = 2*C with logscale = loc + C for the
+ *                 un-split [..,6] conv output of models/model03.py:88-91).
+ * x  [x_batch, D] float32 or uint8 (uint8 => x = k/255.f); used as is (no rescale, :37).
+ * lp_elem [n_img, D] nullable ; ll_image [n_img] nullable.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API size_t vaemdl_dlogistic_workspace_bytes(long long n_img, long long D);
+
+VAEMDL_API int vaemdl_dlogistic_fwd(const float* loc, const float* logscale, int C, int ld,
+                         const void* x, int x_dtype, long long n_img, int x_batch, long long D,
+                         float low, float high, float levels,
+                         float* lp_elem, float* ll_image,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* dloc / dlogscale use the same (C, ld_out) addressing as loc / logscale. */
+VAEMDL_API int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int C, int ld,
+                         const void* x, int x_dtype, long long n_img, int x_batch, long long D,
+                         float low, float high, float levels,
+                         const float* g_image, const float* g_elem,
+                         float* dloc, float* dlogscale, int ld_out, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * IWAE log-mean-exp over the importance-sample axis
+ * replaces: logmeanexp(log_w, axis=0)   utils/utils.py:9-11
+ *           iwae_loss tail              models/loss.py:34-43 ; models/model06.py:47-55
+ * log_w [S, B] ; out_b [B]
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_logmeanexp_fwd(const float* log_w, int S, long long B, float* out_b, void* stream);
+/* dlog_w[s,b] = g_out[b] * softmax_s(log_w[:,b])  (gradient of utils/utils.py:9-11; no stop_gradient there) */
+VAEMDL_API int vaemdl_logmeanexp_bwd(const float* log_w, const float* g_out, int S, long long B, float* dlog_w, void* stream);
+
+/* Fused IWAE tail: log_w = ll + (extra ? extra : 0); lme_b = logmeanexp_s; elbo = mean_b lme_b;
+ * g_ll[s,b] = d(-elbo)/d ll[s,b] = -softmax_s(log_w)[s,b] / B.       (models/loss.py:34-37)
+ * ll [S,B]; extra [S,B] nullable (= beta*(lpz-lqzx)); outputs nullable: log_w [S,B], lme_b [B], elbo [1], g_ll [S,B].
+ * One CTA-wide deterministic reduction; single launch. */
+VAEMDL_API int vaemdl_iwae_tail(const float* ll, const float* extra, int S, long long B,
+                     float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Samplers (explicit uniform noise; float64 internal arithmetic)
+ * replaces: sample_from_discretized_mix_logistic   utils/mdl_openai.py:160-193 (explicit-noise lines :167, :185-186)
+ *           MixtureDiscretizedLogistic._sample_n   utils/mdl.py:209-252
+ *           DiscretizedLogistic.sample             utils/discretized_logistic.py:80-85
+ * params [n_img,H,W,10M], re-used for n_rep consecutive blocks of noise (the reference tiles the parameter tensor n
+ *        times instead: utils/mdl_openai.py:39-45, utils/mdl_openai_iwae.py:78-84; tfd sample(n));
+ * u_mix [n_rep,n_img,H,W,M]; u_log [n_rep,n_img,H,W,3] (OPENAI) or [n_rep,n_img,H,W,3,M] (MDL); uniforms in (0,1)
+ * outputs carry the leading [n_rep, n_img]:
+ * x_out  [..,H,W,3] float32 nullable; out_range: VAEMDL_RANGE_SYM -> [-1,1], VAEMDL_RANGE_UNIT -> x*0.5+0.5
+ * x_q    [..,H,W,3] uint8 nullable: rint(255*clip(x01,0,1))  (new-build definition, the reference never quantises)
+ * idx    [..,H,W]   uint8 nullable: selected mixture
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_sample(const float* params, const float* u_mix, const float* u_log, int variant, int out_range,
+                       long long n_rep, long long n_img, int H, int W, int M,
+                       float* x_out, uint8_t* x_q, uint8_t* idx, void* stream);
+
+VAEMDL_API int vaemdl_dlogistic_sample(const float* loc, const float* logscale, int C, int ld, const float* u,
+                            long long n_elem, float low, float high, float* x_out, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Host-buffer step: the whole IWAE observation-model step through HOST memory.
+ * params_host [S,B,H,W,10M] (pinned recommended), x_host uint8 [B,H,W,3],
+ * extra_host [S,B] nullable, outputs: dparams_host [S,B,H,W,10M] nullable (forward only if NULL),
+ * ll_host [S,B], lme_host [B], elbo_host [1].
+ * Splits B into chunks, pipelines H2D copy / fwd / IWAE tail / bwd / D2H copy over internal
+ * streams and device staging buffers (allocated on first use, cached per device, freed by
+ * vaemdl_host_release).  Synchronous: returns when all outputs are in host memory.
+ * replaces: one train_step's loss+grad on the observation model, models/model05.py:139-148.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_t* x_host, const float* extra_host,
+                               int S, int B, int H, int W, int M,
+                               float* dparams_host, float* ll_host, float* lme_host, float* elbo_host,
+                               int chunk_b /*0 = auto*/);
+VAEMDL_API void vaemdl_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEMDL_H_ */

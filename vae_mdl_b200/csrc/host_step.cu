@@ -1,0 +1,177 @@
+// host_step.cu -- the IWAE observation-model step with HOST buffers (pipelined H2D / kernels / D2H).
+//
+// Replaces the loss + gradient of one train_step on the observation model (models/model05.py:139-148) for a caller
+// whose decoder output lives in host memory.  The batch is cut into chunks of images; every importance sample of a
+// chunk's images travels together, so the log-mean-exp over samples and its gradient stay chunk-local
+// (models/loss.py:34-37 reduces over s for a fixed b).  Chunks rotate over kSlots device staging slots, each with
+// its own stream: the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vaemdl {
+
+constexpr int kSlots = 3;
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  float* params = nullptr;
+  float* grads = nullptr;
+  float* ll = nullptr;     // [S, cb]
+  float* extra = nullptr;  // [S, cb]
+  float* g_ll = nullptr;   // [S, cb]
+  float* lme = nullptr;    // [cb]
+  void* ws = nullptr;
+  size_t params_bytes = 0, grads_bytes = 0, small_elems = 0, lme_elems = 0, ws_bytes = 0;
+};
+
+struct HostCtx {
+  int device = -1;
+  Slot slots[kSlots];
+  uint8_t* x = nullptr;
+  size_t x_bytes = 0;
+  cudaEvent_t x_ready = nullptr;
+};
+
+static std::mutex g_mu;
+static std::vector<HostCtx*> g_ctxs;
+
+template <typename T>
+static cudaError_t grow(T*& p, size_t& have, size_t want) {
+  if (have >= want) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr;
+  have = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want);
+  if (e == cudaSuccess) have = want;
+  return e;
+}
+
+static HostCtx* get_ctx() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (HostCtx* c : g_ctxs)
+    if (c->device == dev) return c;
+  HostCtx* c = new HostCtx();
+  c->device = dev;
+  for (auto& s : c->slots) cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming);
+  g_ctxs.push_back(c);
+  return c;
+}
+
+}  // namespace vaemdl
+
+using namespace vaemdl;
+
+#define VAEMDL_TRY(expr)                       \
+  do {                                         \
+    cudaError_t e__ = (expr);                  \
+    if (e__ != cudaSuccess) return cuda_rc(e__); \
+  } while (0)
+
+extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_t* x_host, const float* extra_host, int S,
+                                          int B, int H, int W, int M, float* dparams_host, float* ll_host,
+                                          float* lme_host, float* elbo_host, int chunk_b) {
+  if (!params_host || !x_host || !ll_host || !lme_host || !elbo_host) return VAEMDL_EINVAL;
+  if (S <= 0 || B <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
+  if (M < 1 || M > VAEMDL_MAX_MIX) return VAEMDL_EUNSUPPORTED;
+  std::lock_guard<std::mutex> lock(g_mu);
+  HostCtx* c = get_ctx();
+  const size_t HW = static_cast<size_t>(H) * W;
+  const size_t img_bytes = HW * 10 * M * sizeof(float);  // one (s,b) image of parameters
+  if (chunk_b <= 0) {
+    const size_t target = 16u << 20;  // ~16 MB of parameters per chunk
+    chunk_b = static_cast<int>(target / (img_bytes * S));
+    if (chunk_b < 1) chunk_b = 1;
+  }
+  if (chunk_b > B) chunk_b = B;
+  const size_t chunk_param_bytes = img_bytes * S * chunk_b;
+
+  VAEMDL_TRY(grow(c->x, c->x_bytes, static_cast<size_t>(B) * HW * 3));
+  for (auto& s : c->slots) {
+    VAEMDL_TRY(grow(s.params, s.params_bytes, chunk_param_bytes));
+    if (dparams_host) VAEMDL_TRY(grow(s.grads, s.grads_bytes, chunk_param_bytes));
+    const size_t small = static_cast<size_t>(S) * chunk_b * sizeof(float);
+    if (s.small_elems < small) {
+      if (s.ll) cudaFree(s.ll);
+      if (s.extra) cudaFree(s.extra);
+      if (s.g_ll) cudaFree(s.g_ll);
+      s.ll = s.extra = s.g_ll = nullptr;
+      s.small_elems = 0;
+      VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.ll), small));
+      VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.extra), small));
+      VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.g_ll), small));
+      s.small_elems = small;
+    }
+    VAEMDL_TRY(grow(s.lme, s.lme_elems, static_cast<size_t>(chunk_b) * sizeof(float)));
+    VAEMDL_TRY(grow(s.ws, s.ws_bytes, vaemdl_modl_workspace_bytes(static_cast<long long>(S) * chunk_b, H, W)));
+  }
+
+  // the observed images: one small copy, every slot stream waits for it
+  VAEMDL_TRY(cudaMemcpyAsync(c->x, x_host, static_cast<size_t>(B) * HW * 3, cudaMemcpyHostToDevice, c->slots[0].stream));
+  VAEMDL_TRY(cudaEventRecord(c->x_ready, c->slots[0].stream));
+  for (int k = 1; k < kSlots; ++k) VAEMDL_TRY(cudaStreamWaitEvent(c->slots[k].stream, c->x_ready, 0));
+
+  const size_t host_pitch = img_bytes * B;  // bytes between consecutive s in the host tensors
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk_b, ++ci) {
+    Slot& s = c->slots[ci % kSlots];
+    const int cb = (B - b0) < chunk_b ? (B - b0) : chunk_b;
+    const size_t width = img_bytes * cb;
+    const long long n_img = static_cast<long long>(S) * cb;
+    // [S, B, ...] host  ->  [S, cb, ...] device: S rows of `width` bytes
+    VAEMDL_TRY(cudaMemcpy2DAsync(s.params, width, reinterpret_cast<const char*>(params_host) + img_bytes * b0, host_pitch,
+                                 width, S, cudaMemcpyHostToDevice, s.stream));
+    if (extra_host)
+      VAEMDL_TRY(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), extra_host + b0, static_cast<size_t>(B) * sizeof(float),
+                                   cb * sizeof(float), S, cudaMemcpyHostToDevice, s.stream));
+    int rc = vaemdl_modl_fwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
+                             VAEMDL_EDGE_MDL, n_img, cb, H, W, M, nullptr, s.ll, s.ws, s.ws_bytes, s.stream);
+    if (rc) return rc;
+    rc = iwae_tail_norm(s.ll, extra_host ? s.extra : nullptr, S, cb, static_cast<float>(B), nullptr, s.lme,
+                        dparams_host ? s.g_ll : nullptr, s.stream);
+    if (rc) return rc;
+    VAEMDL_TRY(cudaMemcpy2DAsync(ll_host + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
+                                 cb * sizeof(float), S, cudaMemcpyDeviceToHost, s.stream));
+    VAEMDL_TRY(cudaMemcpyAsync(lme_host + b0, s.lme, cb * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (dparams_host) {
+      rc = vaemdl_modl_bwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
+                           VAEMDL_EDGE_MDL, n_img, cb, H, W, M, s.g_ll, nullptr, s.grads, s.stream);
+      if (rc) return rc;
+      VAEMDL_TRY(cudaMemcpy2DAsync(reinterpret_cast<char*>(dparams_host) + img_bytes * b0, host_pitch, s.grads, width,
+                                   width, S, cudaMemcpyDeviceToHost, s.stream));
+    }
+  }
+  for (auto& s : c->slots) VAEMDL_TRY(cudaStreamSynchronize(s.stream));
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b) acc += static_cast<double>(lme_host[b]);  // models/loss.py:37 (mean over the batch)
+  elbo_host[0] = static_cast<float>(acc / B);
+  return VAEMDL_OK;
+}
+
+extern "C" void vaemdl_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (HostCtx* c : g_ctxs) {
+    cudaSetDevice(c->device);
+    for (auto& s : c->slots) {
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      cudaFree(s.params);
+      cudaFree(s.grads);
+      cudaFree(s.ll);
+      cudaFree(s.extra);
+      cudaFree(s.g_ll);
+      cudaFree(s.lme);
+      cudaFree(s.ws);
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(c->x);
+    if (c->x_ready) cudaEventDestroy(c->x_ready);
+    delete c;
+  }
+  g_ctxs.clear();
+  cudaSetDevice(cur);
+}

@@ -1,0 +1,670 @@
+// modl_kernels.cu -- mixture-of-discretized-logistics log-likelihood (forward) and parameter gradient (backward).
+//
+// Replaces utils/mdl.py:56-207, utils/mdl_openai.py:83-157, utils/mdl_openai_iwae.py:33-67 and the autodiff of
+// models/model05.py:141-145 (see include/vaemdl.h).
+//
+// Data movement.  The parameter tensor is a flat stream of rows (one 40*M-byte row per pixel-sample).  Every warp
+// runs its own pipeline: a 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) brings a tile of PPT rows into the warp's
+// shared-memory slot and signals an mbarrier; each lane then pulls its own row (or its MC-mixture chunk of the row)
+// into registers with conflict-free 128/64-bit shared loads, the slot is re-armed for the warp's next tile right
+// away, and the arithmetic runs out of registers while the next tile streams in.  The backward kernel stages its
+// gradient rows in a second slot and writes them back with a bulk store.  There is no CTA-wide synchronisation.
+//
+// Work split.  M = MC * LPP: LPP lanes share a pixel, each owning MC mixtures (M=5: 5x1, M=10: 10x1, M=20: 10x2,
+// M=30: 10x3).  Any other M runs on a plain one-thread-per-pixel kernel (correct, not tuned).
+#include <type_traits>
+
+#include "modl_math.cuh"
+
+namespace vaemdl {
+
+constexpr float kDx = 1.0f / 255.0f;     // half bin width in [-1,1] units   (utils/mdl.py:47-50)
+constexpr float kWidth = 2.0f / 255.0f;  // bin width                         (utils/mdl.py:47)
+constexpr float kTinySum = 1e-30f;       // below this the linear-domain mixture sum is re-done in the log domain
+
+struct ModlArgs {
+  const float* params;
+  const void* x;
+  float* lp_pixel;       // nullable
+  float* partial;        // [num_tiles][2] tile partial sums (nullable)
+  float* ll_atomic;      // [n_img] pre-zeroed, used instead of `partial` when H*W < pixels-per-tile
+  const float* g_image;  // nullable
+  const float* g_pixel;  // nullable
+  float* dparams;
+  long long n_px;  // n_img * H * W
+  long long num_tiles;
+  int HW;
+  int x_batch;
+  int x_u8;
+  int x_unit;       // apply x*2-1
+  int edge_openai;  // < -0.999 / > 0.999 instead of <= -1 / >= 1
+  int M;
+};
+
+struct Pixel {
+  float x[3];
+  bool left[3], right[3];
+};
+
+// pixel `pix` of image n (image n is scored against x[n % x_batch], include/vaemdl.h)
+__device__ __forceinline__ void load_pixel(const ModlArgs& a, long long n, int pix, Pixel& px) {
+  const long long xb = a.x_batch == 1 ? 0 : (n < a.x_batch ? n : n % a.x_batch);
+  const long long xo = (xb * a.HW + pix) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v;
+    if (a.x_u8) {
+      v = __fdiv_rn(static_cast<float>(static_cast<const uint8_t*>(a.x)[xo + c]), 255.0f);  // utils/data.py:15-16
+    } else {
+      v = static_cast<const float*>(a.x)[xo + c];
+    }
+    if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);  // utils/mdl.py:65
+    px.x[c] = v;
+    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
+    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+  }
+}
+
+// ---- rare fallback: one mixture's  logit + sum_c log f_c  in the log domain, straight from global memory -------
+__device__ __noinline__ float modl_logt(const float* __restrict__ row, int M, int m, const Pixel& px) {
+  const float k0 = tanhf(row[M + 2 * M + m]);
+  const float k1 = tanhf(row[M + 3 * M + 2 * M + m]);
+  const float k2 = tanhf(row[M + 6 * M + 2 * M + m]);
+  float t = row[m];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float loc = row[M + c * 3 * M + m];
+    if (c == 1) loc = loc + k0 * px.x[0];
+    if (c == 2) loc = loc + k1 * px.x[0] + k2 * px.x[1];
+    const float ls = fmaxf(row[M + c * 3 * M + M + m], -7.0f);
+    t += subpix_logf(px.x[c], px.left[c], px.right[c], loc, ls, kDx, kWidth);
+  }
+  return t;
+}
+// log sum_m exp(logit_m + sum_c log f)  and  log sum_m exp(logit_m)
+__device__ __noinline__ void modl_pixel_logdomain(const float* __restrict__ row, int M, const Pixel& px, float& lse_t,
+                                                  float& lse_l) {
+  float mt = -INFINITY, ml = -INFINITY;
+  for (int m = 0; m < M; ++m) {
+    mt = fmaxf(mt, modl_logt(row, M, m, px));
+    ml = fmaxf(ml, row[m]);
+  }
+  float st = 0.f, sl = 0.f;
+  for (int m = 0; m < M; ++m) {
+    st += expf(modl_logt(row, M, m, px) - mt);
+    sl += expf(row[m] - ml);
+  }
+  lse_t = mt + logf(st);
+  lse_l = ml + logf(sl);
+}
+
+// ---- group (LPP lanes of one pixel) all-reduce with a fixed summation order --------------------------------------
+template <int LPP>
+__device__ __forceinline__ float group_sum(float v, int lane) {
+  if constexpr (LPP == 1) {
+    return v;
+  } else {
+    const int base = lane - (lane % LPP);
+    float s = __shfl_sync(kFull, v, base);
+#pragma unroll
+    for (int j = 1; j < LPP; ++j) s += __shfl_sync(kFull, v, (base + j) & 31);
+    return s;
+  }
+}
+template <int LPP>
+__device__ __forceinline__ float group_max(float v, int lane) {
+  if constexpr (LPP == 1) {
+    return v;
+  } else {
+    const int base = lane - (lane % LPP);
+    float s = __shfl_sync(kFull, v, base);
+#pragma unroll
+    for (int j = 1; j < LPP; ++j) s = fmaxf(s, __shfl_sync(kFull, v, (base + j) & 31));
+    return s;
+  }
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---- chunk <-> shared memory -------------------------------------------------------------------------------------
+// v[j*MC + i] = row[j*M + sub*MC + i],  j = 0..9 (0: logits, 1..9: muR sR kR muG sG kG muB sB kB)
+template <int MC, int LPP>
+__device__ __forceinline__ void chunk_load(float (&v)[10 * MC], const float* __restrict__ rowp, int sub) {
+  constexpr int M = MC * LPP;
+  if constexpr (LPP == 1) {
+    if constexpr ((10 * M) % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < (10 * M) / 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(rowp)[q];
+        v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < (10 * M) / 2; ++q) {
+        const float2 t = reinterpret_cast<const float2*>(rowp)[q];
+        v[2 * q] = t.x, v[2 * q + 1] = t.y;
+      }
+    }
+  } else {
+    static_assert(MC % 2 == 0, "multi-lane chunks use 64-bit shared accesses");
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float2* src = reinterpret_cast<const float2*>(rowp + j * M + sub * MC);
+#pragma unroll
+      for (int q = 0; q < MC / 2; ++q) {
+        const float2 t = src[q];
+        v[j * MC + 2 * q] = t.x, v[j * MC + 2 * q + 1] = t.y;
+      }
+    }
+  }
+}
+template <int MC, int LPP>
+__device__ __forceinline__ void chunk_store(const float (&v)[10 * MC], float* __restrict__ rowp, int sub) {
+  constexpr int M = MC * LPP;
+  if constexpr (LPP == 1) {
+    if constexpr ((10 * M) % 4 == 0) {
+#pragma unroll
+      for (int q = 0; q < (10 * M) / 4; ++q)
+        reinterpret_cast<float4*>(rowp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < (10 * M) / 2; ++q) reinterpret_cast<float2*>(rowp)[q] = make_float2(v[2 * q], v[2 * q + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      float2* dst = reinterpret_cast<float2*>(rowp + j * M + sub * MC);
+#pragma unroll
+      for (int q = 0; q < MC / 2; ++q) dst[q] = make_float2(v[j * MC + 2 * q], v[j * MC + 2 * q + 1]);
+    }
+  }
+}
+
+// ---- one mixture component ------------------------------------------------------------------------------------------
+// forward: returns P = prod_c f_c (linear domain)
+__device__ __forceinline__ float mix_fwd(const Pixel& px, const float mu[3], const float s[3], const float kap[3]) {
+  float k0, k1, k2;
+  tanh3(kap[0], kap[1], kap[2], k0, k1, k2);  // utils/mdl.py:110
+  const float loc0 = mu[0];
+  const float loc1 = fmaf(k0, px.x[0], mu[1]);                       // utils/mdl.py:140
+  const float loc2 = fmaf(k2, px.x[1], fmaf(k1, px.x[0], mu[2]));    // utils/mdl.py:141-145
+  SubF f0, f1, f2;
+  subpix<false>(px.x[0], px.left[0], px.right[0], loc0, fmaxf(s[0], -7.0f), kDx, kWidth, f0);
+  subpix<false>(px.x[1], px.left[1], px.right[1], loc1, fmaxf(s[1], -7.0f), kDx, kWidth, f1);
+  subpix<false>(px.x[2], px.left[2], px.right[2], loc2, fmaxf(s[2], -7.0f), kDx, kWidth, f2);
+  return (f0.num * f1.num * f2.num) * rcpa(f0.den * f1.den * f2.den);
+}
+
+// backward: returns P and the nine d log P / d(param) values u = {dmuR dsR dkR dmuG dsG dkG dmuB dsB dkB}
+__device__ __forceinline__ float mix_bwd(const Pixel& px, const float mu[3], const float s[3], const float kap[3],
+                                         float u[9]) {
+  float k[3];
+  tanh3(kap[0], kap[1], kap[2], k[0], k[1], k[2]);
+  float loc[3];
+  loc[0] = mu[0];
+  loc[1] = fmaf(k[0], px.x[0], mu[1]);
+  loc[2] = fmaf(k[2], px.x[1], fmaf(k[1], px.x[0], mu[2]));
+  SubB f[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) subpix<true>(px.x[c], px.left[c], px.right[c], loc[c], fmaxf(s[c], -7.0f), kDx, kWidth, f[c]);
+  const float d01 = f[0].den * f[1].den;
+  const float R = rcpa(d01 * f[2].den);
+  float rd[3];
+  rd[0] = f[1].den * f[2].den * R;
+  rd[1] = f[0].den * f[2].den * R;
+  rd[2] = d01 * R;
+  float dloc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float Dm = f[c].nm * rd[c];
+    dloc[c] = -f[c].inv * Dm;
+    float dls = (f[c].dir - f[c].c0) - fmaf(f[c].mid, Dm, f[c].nh * rd[c]);
+    if (!(s[c] >= -7.0f)) dls = 0.0f;  // tf.maximum(logscale, -7) routes the gradient to logscale iff logscale >= -7
+    u[3 * c + 0] = dloc[c];
+    u[3 * c + 1] = dls;
+  }
+  // coefficients: loc_g = mu_g + k0 x_r ; loc_b = mu_b + k1 x_r + k2 x_g ; d tanh = 1 - tanh^2
+  u[2] = dloc[1] * px.x[0] * fmaf(-k[0], k[0], 1.0f);
+  u[5] = dloc[2] * px.x[0] * fmaf(-k[1], k[1], 1.0f);
+  u[8] = dloc[2] * px.x[1] * fmaf(-k[2], k[2], 1.0f);
+  return (f[0].num * f[1].num * f[2].num) * R;
+}
+
+// ---- the tiled kernel -------------------------------------------------------------------------------------------------
+template <int MC, int LPP>
+struct Tile {
+  static constexpr int M = MC * LPP;
+  static constexpr int PPT = 32 / LPP;  // pixels per warp tile
+  static constexpr int ROWF = 10 * M;
+  static constexpr int TILE_F = PPT * ROWF;
+  static constexpr int TILE_B = TILE_F * 4;
+  static_assert(TILE_B % 16 == 0, "bulk copies need 16-byte multiples");
+};
+
+template <int MC, int LPP, bool BWD, int STAGES>
+__global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlArgs a) {
+  using T = Tile<MC, LPP>;
+  constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F;
+  constexpr int SLOTS = STAGES + (BWD ? 1 : 0);  // BWD: last slot stages the gradient tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * SLOTS * TILE_F;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * SLOTS * T::TILE_B) + warp * STAGES;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
+  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const int p = (lane / LPP) < PPT ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
+  const int sub = lane % LPP;
+  const bool lane_used = (lane / LPP) < PPT;
+
+  auto tile_rows = [&](long long t) -> int {
+    const long long rem = a.n_px - t * PPT;
+    return rem < PPT ? static_cast<int>(rem) : PPT;
+  };
+  // bring tile t into stage slot s (bulk copy when the byte count allows it, plain loads for a ragged tail tile)
+  auto issue = [&](long long t, int s) {
+    const int rows = tile_rows(t);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+    const float* src = a.params + t * TILE_F;
+    float* dst = slots + s * TILE_F;
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        bulk_g2s(dst, src, bytes, &bars[s]);
+      }
+    } else {
+      for (int i = lane; i < rows * ROWF; i += 32) dst[i] = src[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
+    }
+  };
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < STAGES; ++s) {
+    const long long t = gw + s * total_warps;
+    if (t < a.num_tiles) issue(t, s);
+  }
+
+  // (image, pixel-in-image) of this lane's pixel-sample, advanced incrementally: one 64-bit division per kernel
+  const long long step_px = total_warps * PPT;
+  const long long step_n = step_px / a.HW;
+  const int step_pix = static_cast<int>(step_px - step_n * a.HW);
+  long long n_own = (gw * PPT + p) / a.HW;
+  int pix_own = static_cast<int>((gw * PPT + p) - n_own * a.HW);
+
+  long long it = 0;
+  for (long long t = gw; t < a.num_tiles; t += total_warps, ++it) {
+    const int s = static_cast<int>(it % STAGES);
+    const uint32_t parity = static_cast<uint32_t>((it / STAGES) & 1);
+    const int rows = tile_rows(t);
+    const int pp = p < rows ? p : 0;
+    const bool active = lane_used && (p < rows);
+    const long long i = t * PPT + pp;  // this lane's pixel-sample
+    // lanes past a ragged last tile shadow the tile's first pixel
+    const long long n_first = __shfl_sync(kFull, n_own, 0);
+    const int pix_first = __shfl_sync(kFull, pix_own, 0);
+    const long long n = p < rows ? n_own : n_first;
+    const int pix = p < rows ? pix_own : pix_first;
+    n_own += step_n;
+    pix_own += step_pix;
+    if (pix_own >= a.HW) {
+      pix_own -= a.HW;
+      ++n_own;
+    }
+
+    // the pixel itself (L2-resident, tiny) -- issued before the wait so its latency hides behind the tile copy
+    Pixel px;
+    load_pixel(a, n, pix, px);
+    float g = 0.0f;
+    if constexpr (BWD) {
+      if (a.g_image) g += a.g_image[n];
+      if (a.g_pixel) g += a.g_pixel[i];
+    }
+
+    mbar_wait(&bars[s], parity);
+    float v[10 * MC];
+    chunk_load<MC, LPP>(v, slots + s * TILE_F + pp * ROWF, sub);
+    __syncwarp();
+    {
+      const long long tn = t + STAGES * total_warps;
+      if (tn < a.num_tiles) issue(tn, s);
+    }
+
+    // mixture weights: W_m = exp(logit_m - max logit)
+    float lmax = v[0];
+#pragma unroll
+    for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, v[m]);
+    lmax = group_max<LPP>(lmax, lane);
+
+    float sumW = 0.0f, sumWP = 0.0f;
+    float w[BWD ? MC : 1], wp[BWD ? MC : 1];
+#pragma unroll
+    for (int m = 0; m < MC; ++m) {
+      const float mu[3] = {v[1 * MC + m], v[4 * MC + m], v[7 * MC + m]};
+      const float sc[3] = {v[2 * MC + m], v[5 * MC + m], v[8 * MC + m]};
+      const float kp[3] = {v[3 * MC + m], v[6 * MC + m], v[9 * MC + m]};
+      const float W = ex2a((v[m] - lmax) * kLog2e);
+      float P;
+      if constexpr (BWD) {
+        float u[9];
+        P = mix_bwd(px, mu, sc, kp, u);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[(1 + j) * MC + m] = u[j];
+        w[m] = W;
+        wp[m] = W * P;
+      } else {
+        P = mix_fwd(px, mu, sc, kp);
+      }
+      sumW += W;
+      sumWP = fmaf(W, P, sumWP);
+    }
+    const float S = group_sum<LPP>(sumWP, lane);
+    const float SW = group_sum<LPP>(sumW, lane);
+    const bool tiny = !(S > kTinySum);  // also catches NaN
+    const float* grow = a.params + i * ROWF;
+
+    if constexpr (!BWD) {
+      float lp = (lg2a(S) - lg2a(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
+      if (tiny) {
+        float lt, ll;
+        modl_pixel_logdomain(grow, M, px, lt, ll);
+        lp = lt - ll;
+      }
+      const bool owner = active && sub == 0;
+      if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
+      const float val = owner ? lp : 0.0f;
+      if (a.partial) {
+        const float s0 = warp_sum(n == n_first ? val : 0.0f);
+        const float s1 = warp_sum(n == n_first ? 0.0f : val);
+        if (lane == 0) {
+          a.partial[2 * t] = s0;
+          a.partial[2 * t + 1] = s1;
+        }
+      } else if (a.ll_atomic) {
+        if (owner) atomicAdd(a.ll_atomic + n, val);
+      }
+    } else {
+      const float rS = rcpa(S), rSW = rcpa(SW);
+      float lt = 0.f, ll = 0.f;
+      if (tiny) modl_pixel_logdomain(grow, M, px, lt, ll);
+#pragma unroll
+      for (int m = 0; m < MC; ++m) {
+        float r = wp[m] * rS;       // posterior responsibility of the component
+        float pi = w[m] * rSW;      // softmax(logits)
+        if (tiny) {
+          r = expf(modl_logt(grow, M, sub * MC + m, px) - lt);
+          pi = expf(grow[sub * MC + m] - ll);
+        }
+        const float gr = g * r;
+        v[m] = g * (r - pi);
+#pragma unroll
+        for (int j = 1; j < 10; ++j) v[j * MC + m] *= gr;
+      }
+      // stage the gradient tile and hand it to the TMA engine
+      float* ob = slots + STAGES * TILE_F;
+      if (lane == 0) bulk_wait_read<0>();  // previous tile's store has finished reading the slot
+      __syncwarp();
+      if (active) chunk_store<MC, LPP>(v, ob + pp * ROWF, sub);
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+      float* dst = a.dparams + t * TILE_F;
+      if ((bytes & 15u) == 0) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(dst, ob, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = ob[q];
+        __syncwarp();
+      }
+    }
+  }
+  if constexpr (BWD) {
+    if (lane == 0) bulk_wait_all<0>();
+  }
+}
+
+// ---- per-image sums from the tile partials (fixed order => bitwise reproducible) ---------------------------------------
+__global__ void modl_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ll_image, long long n_img,
+                                            int HW, int PPT) {
+  const long long n = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= n_img) return;
+  const long long first = n * HW, last = first + HW - 1;
+  const long long t_lo = first / PPT, t_hi = last / PPT;
+  float acc = 0.0f;
+  for (long long t = t_lo + lane; t <= t_hi; t += 32) {
+    const long long n0 = (t * PPT) / HW;
+    acc += (n0 == n) ? partial[2 * t] : partial[2 * t + 1];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ll_image[n] = acc;
+}
+
+// ---- any-M kernel: one thread per pixel-sample, parameters straight from global memory (correct, not tuned) --------------
+template <bool BWD>
+__global__ void __launch_bounds__(128) modl_generic_kernel(const ModlArgs a) {
+  const int M = a.M;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n_iter = (a.n_px + stride - 1) / stride;  // every lane runs the same trip count (warp votes inside)
+  for (long long itn = 0; itn < n_iter; ++itn) {
+    const long long i_raw = itn * stride + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool active = i_raw < a.n_px;
+    const long long i = active ? i_raw : 0;
+    Pixel px;
+    const long long n = i / a.HW;
+    load_pixel(a, n, static_cast<int>(i - n * a.HW), px);
+    const float* row = a.params + i * 10 * M;
+    float lmax = row[0];
+    for (int m = 1; m < M; ++m) lmax = fmaxf(lmax, row[m]);
+    float sumW = 0.f, sumWP = 0.f;
+    for (int m = 0; m < M; ++m) {
+      const float mu[3] = {row[M + m], row[4 * M + m], row[7 * M + m]};
+      const float sc[3] = {row[2 * M + m], row[5 * M + m], row[8 * M + m]};
+      const float kp[3] = {row[3 * M + m], row[6 * M + m], row[9 * M + m]};
+      const float W = ex2a((row[m] - lmax) * kLog2e);
+      sumW += W;
+      sumWP = fmaf(W, mix_fwd(px, mu, sc, kp), sumWP);
+    }
+    const bool tiny = !(sumWP > kTinySum);
+    float lt = 0.f, ll = 0.f;
+    if (tiny) modl_pixel_logdomain(row, M, px, lt, ll);
+    if constexpr (!BWD) {
+      const float lp = tiny ? (lt - ll) : (lg2a(sumWP) - lg2a(sumW)) * kLn2;
+      if (active) {
+        if (a.lp_pixel) a.lp_pixel[i] = lp;
+        if (a.ll_atomic) atomicAdd(a.ll_atomic + n, lp);
+      }
+    } else {
+      float g = 0.f;
+      if (a.g_image) g += a.g_image[n];
+      if (a.g_pixel) g += a.g_pixel[i];
+      const float rS = rcpa(sumWP), rSW = rcpa(sumW);
+      float* orow = a.dparams + i * 10 * M;
+      for (int m = 0; m < M; ++m) {
+        const float mu[3] = {row[M + m], row[4 * M + m], row[7 * M + m]};
+        const float sc[3] = {row[2 * M + m], row[5 * M + m], row[8 * M + m]};
+        const float kp[3] = {row[3 * M + m], row[6 * M + m], row[9 * M + m]};
+        const float W = ex2a((row[m] - lmax) * kLog2e);
+        float u[9];
+        const float P = mix_bwd(px, mu, sc, kp, u);
+        float r = W * P * rS, pi = W * rSW;
+        if (tiny) {
+          r = expf(modl_logt(row, M, m, px) - lt);
+          pi = expf(row[m] - ll);
+        }
+        if (active) {
+          orow[m] = g * (r - pi);
+          const float gr = g * r;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) orow[(1 + j) * M + m] = gr * u[j];
+        }
+      }
+    }
+  }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------------------------
+struct LaunchCfg {
+  int warps;
+};
+
+template <int MC, int LPP, bool BWD, int STAGES>
+static int launch_tiled(ModlArgs a, int warps, cudaStream_t st) {
+  using T = Tile<MC, LPP>;
+  constexpr int SLOTS = STAGES + (BWD ? 1 : 0);
+  a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
+  const DeviceInfo& di = device_info();
+  auto smem_for = [&](int w) { return static_cast<size_t>(w) * SLOTS * T::TILE_B + static_cast<size_t>(w) * STAGES * 8; };
+  while (warps > 1 && smem_for(warps) > static_cast<size_t>(di.max_smem_optin)) --warps;
+  const size_t smem = smem_for(warps);
+  auto kern = modl_tile_kernel<MC, LPP, BWD, STAGES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return cuda_rc(e);
+  int ctas_per_sm = static_cast<int>(static_cast<size_t>(di.max_smem_optin) / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
+  return cuda_rc(cudaGetLastError());
+}
+
+template <bool BWD>
+static int launch_modl(ModlArgs a, cudaStream_t st) {
+  switch (a.M) {
+    case 5:
+      return launch_tiled<5, 1, BWD, BWD ? 1 : 2>(a, 8, st);
+    case 10:
+      return launch_tiled<10, 1, BWD, BWD ? 1 : 2>(a, 8, st);
+    case 20:
+      return launch_tiled<10, 2, BWD, BWD ? 1 : 2>(a, 8, st);
+    case 30:
+      return launch_tiled<10, 3, BWD, BWD ? 1 : 2>(a, 8, st);
+    default: {
+      const DeviceInfo& di = device_info();
+      long long blocks = (a.n_px + 127) / 128;
+      const long long cap = static_cast<long long>(di.sm_count) * 8;
+      if (blocks > cap) blocks = cap;
+      modl_generic_kernel<BWD><<<static_cast<unsigned>(blocks), 128, 0, st>>>(a);
+      return cuda_rc(cudaGetLastError());
+    }
+  }
+}
+
+static int tile_ppt(int M) {
+  switch (M) {
+    case 5:
+    case 10:
+      return 32;
+    case 20:
+      return 16;
+    case 30:
+      return 10;
+    default:
+      return 0;  // generic kernel: atomics
+  }
+}
+
+static int check_common(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
+                        int x_batch, int H, int W, int M) {
+  if (!params || !x) return VAEMDL_EINVAL;
+  if (n_img <= 0 || x_batch <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
+  if (x_dtype != VAEMDL_X_F32 && x_dtype != VAEMDL_X_U8) return VAEMDL_EINVAL;
+  if (x_range != VAEMDL_RANGE_UNIT && x_range != VAEMDL_RANGE_SYM) return VAEMDL_EINVAL;
+  if (x_dtype == VAEMDL_X_U8 && x_range != VAEMDL_RANGE_UNIT) return VAEMDL_EINVAL;
+  if (edge_mode != VAEMDL_EDGE_MDL && edge_mode != VAEMDL_EDGE_OPENAI) return VAEMDL_EINVAL;
+  if (M < 1 || M > VAEMDL_MAX_MIX) return VAEMDL_EUNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(params) & 15u) return VAEMDL_EALIGN;
+  return VAEMDL_OK;
+}
+
+}  // namespace vaemdl
+
+using namespace vaemdl;
+
+extern "C" size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W) {
+  if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+  // two floats per tile at the smallest tile size (10 pixels) -- an upper bound for every M
+  const long long n_px = n_img * H * W;
+  return static_cast<size_t>((n_px + 9) / 10) * 2 * sizeof(float) + 256;
+}
+
+extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                               long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
+  if (rc) return rc;
+  if (!lp_pixel && !ll_image) return VAEMDL_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ModlArgs a{};
+  a.params = params;
+  a.x = x;
+  a.lp_pixel = lp_pixel;
+  a.HW = H * W;
+  a.n_px = n_img * a.HW;
+  a.x_batch = x_batch;
+  a.x_u8 = x_dtype == VAEMDL_X_U8;
+  a.x_unit = x_range == VAEMDL_RANGE_UNIT;
+  a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
+  a.M = M;
+  const int ppt = tile_ppt(M);
+  const bool use_partials = ll_image && ppt > 0 && a.HW >= ppt;
+  if (ll_image) {
+    if (use_partials) {
+      if (!workspace || workspace_bytes < vaemdl_modl_workspace_bytes(n_img, H, W)) return VAEMDL_EWORKSPACE;
+      a.partial = static_cast<float*>(workspace);
+    } else {
+      cudaError_t e = cudaMemsetAsync(ll_image, 0, sizeof(float) * n_img, st);
+      if (e != cudaSuccess) return cuda_rc(e);
+      a.ll_atomic = ll_image;
+    }
+  }
+  rc = launch_modl<false>(a, st);
+  if (rc) return rc;
+  if (use_partials) {
+    const long long threads = n_img * 32;
+    const int block = 256;
+    const long long grid = (threads + block - 1) / block;
+    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(a.partial, ll_image, n_img, a.HW, ppt);
+    return cuda_rc(cudaGetLastError());
+  }
+  return VAEMDL_OK;
+}
+
+extern "C" int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                               long long n_img, int x_batch, int H, int W, int M, const float* g_image,
+                               const float* g_pixel, float* dparams, void* stream) {
+  int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
+  if (rc) return rc;
+  if (!dparams || (!g_image && !g_pixel)) return VAEMDL_EINVAL;
+  if (reinterpret_cast<uintptr_t>(dparams) & 15u) return VAEMDL_EALIGN;
+  ModlArgs a{};
+  a.params = params;
+  a.x = x;
+  a.g_image = g_image;
+  a.g_pixel = g_pixel;
+  a.dparams = dparams;
+  a.HW = H * W;
+  a.n_px = n_img * a.HW;
+  a.x_batch = x_batch;
+  a.x_u8 = x_dtype == VAEMDL_X_U8;
+  a.x_unit = x_range == VAEMDL_RANGE_UNIT;
+  a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
+  a.M = M;
+  return launch_modl<true>(a, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,317 @@
+"""Tensor-level entry points: shape handling + ``torch.autograd.Function`` wrappers around the C ABI.
+
+Everything here enqueues hand-written sm_100a kernels from ``libvaemdl_b200.so`` on the current CUDA
+stream; PyTorch only owns the buffers.  CPU tensors are rejected (``_abi.require_cuda``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _abi
+from ._abi import check, dense_f32, lib, ptr, stream_ptr
+
+__all__ = [
+    "modl_log_prob",
+    "modl_log_likelihood",
+    "dlogistic_log_prob",
+    "dlogistic_log_likelihood",
+    "logmeanexp",
+    "iwae_tail",
+    "modl_sample",
+    "dlogistic_sample",
+]
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
+def _prep_x(x: torch.Tensor, img_shape: Tuple[int, ...], what: str):
+    """Returns (x dense, x_dtype enum, x_batch).  x: [x_batch, *img_shape] or [*img_shape]; uint8 or float."""
+    _abi.require_cuda(x, what)
+    nd = len(img_shape)
+    if tuple(x.shape[-nd:]) != tuple(img_shape):
+        raise ValueError(f"{what}: trailing dims {tuple(x.shape[-nd:])} do not match the parameter image shape {img_shape}")
+    lead = x.shape[:-nd]
+    x_batch = int(math.prod(lead)) if len(lead) else 1
+    if x.dtype == torch.uint8:
+        return x.contiguous(), _abi.X_U8, x_batch
+    return dense_f32(x, what), _abi.X_F32, x_batch
+
+
+def _check_batch(n_img: int, x_batch: int, what: str):
+    if n_img % x_batch:
+        raise ValueError(f"{what}: {n_img} parameter images cannot be scored against {x_batch} observed images "
+                         "(the leading dims of the parameters must end with the batch dim of x)")
+
+
+class _ModlFn(torch.autograd.Function):
+    """Forward: per-pixel log-prob and/or per-image log-likelihood.  Backward: one fused kernel."""
+
+    @staticmethod
+    def forward(ctx, params, x, x_range, edge_mode, want_pixel, want_image):
+        p = dense_f32(params, "parameters")
+        H, W, C10 = p.shape[-3], p.shape[-2], p.shape[-1]
+        M = C10 // 10
+        if C10 != 10 * M or M < 1:
+            raise ValueError(f"last parameter dim must be 10*n_mix, got {C10}")
+        lead = tuple(p.shape[:-3])
+        n_img = int(math.prod(lead)) if lead else 1
+        xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
+        _check_batch(n_img, x_batch, "log_prob")
+        L = lib()
+        lp = torch.empty(lead + (H, W), device=p.device, dtype=torch.float32) if want_pixel else None
+        ll = torch.empty(lead, device=p.device, dtype=torch.float32) if want_image else None
+        ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W) if want_image else 0
+        ws = torch.empty(ws_bytes, device=p.device, dtype=torch.uint8) if ws_bytes else None
+        with torch.cuda.device(p.device):
+            check(L.vaemdl_modl_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                                    ptr(lp), ptr(ll), ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_fwd")
+        ctx.save_for_backward(p, xd)
+        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M)
+        outs = tuple(t for t in (lp, ll) if t is not None)
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        p, xd = ctx.saved_tensors
+        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M = ctx.meta
+        g_pixel = g_image = None
+        for g in grads:
+            if g is None:
+                continue
+            if g.dim() == p.dim() - 1:  # [..., H, W]
+                g_pixel = dense_f32(g, "grad(lp_pixel)")
+            else:
+                g_image = dense_f32(g, "grad(ll_image)")
+        if g_pixel is None and g_image is None:
+            return None, None, None, None, None, None
+        dp = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                                        ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+        return dp, None, None, None, None, None
+
+
+def modl_log_prob(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
+                  edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
+    """Per-pixel MoDL log-prob ``[..., H, W]`` (utils/mdl.py:56-92 without the trailing ``expand_dims``)."""
+    return _ModlFn.apply(params, x, x_range, edge_mode, True, False)
+
+
+def modl_log_likelihood(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
+                        edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
+    """Per-image MoDL log-likelihood ``[...]`` = ``reduce_sum(log_prob(x), [-1,-2,-3])`` (models/loss.py:32),
+    computed without ever writing the per-pixel tensor."""
+    return _ModlFn.apply(params, x, x_range, edge_mode, False, True)
+
+
+# --------------------------------------------------------------------------------------------------
+# plain discretized logistic
+# --------------------------------------------------------------------------------------------------
+def _dl_layout(loc: torch.Tensor, logscale: torch.Tensor):
+    """Detects the un-split ``[..., 2C]`` conv output (models/model03.py:88-91): ``loc`` and ``logscale`` are the two
+    halves of one contiguous tensor.  Returns (loc, logscale, C, ld) with both tensors addressable as
+    ``base[(e // C) * ld + e % C]``."""
+    C = loc.shape[-1]
+    if (loc.dtype == torch.float32 and logscale.dtype == torch.float32 and loc.shape == logscale.shape and loc.dim() >= 1
+            and loc.stride() == logscale.stride() and loc.stride(-1) == 1
+            and logscale.data_ptr() == loc.data_ptr() + 4 * C and loc.data_ptr() % 16 == 0):
+        # candidate split view: check all leading strides describe a dense [..., 2C] parent
+        expect = 2 * C
+        okay = True
+        for size, stride in zip(reversed(loc.shape[:-1]), reversed(loc.stride()[:-1])):
+            if size != 1 and stride != expect:
+                okay = False
+                break
+            expect *= size
+        if okay:
+            return loc, logscale, C, 2 * C
+    return dense_f32(loc, "loc"), dense_f32(logscale, "logscale"), C, C
+
+
+class _DlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, logscale, x, low, high, levels, n_event_dims, want_elem, want_image):
+        if loc.shape != logscale.shape:
+            loc, logscale = torch.broadcast_tensors(loc, logscale)
+        _abi.require_cuda(loc, "loc")
+        locd, lsd, C, ld = _dl_layout(loc, logscale)
+        shape = tuple(loc.shape)
+        ev = shape[len(shape) - n_event_dims:]
+        lead = shape[:len(shape) - n_event_dims]
+        D = int(math.prod(ev))
+        n_img = int(math.prod(lead)) if lead else 1
+        xd, x_dtype, x_batch = _prep_x(x, ev, "x")
+        _check_batch(n_img, x_batch, "log_prob")
+        L = lib()
+        lp = torch.empty(shape, device=loc.device, dtype=torch.float32) if want_elem else None
+        ll = torch.empty(lead, device=loc.device, dtype=torch.float32) if want_image else None
+        ws_bytes = L.vaemdl_dlogistic_workspace_bytes(n_img, D) if want_image else 0
+        ws = torch.empty(ws_bytes, device=loc.device, dtype=torch.uint8) if ws_bytes else None
+        with torch.cuda.device(loc.device):
+            check(L.vaemdl_dlogistic_fwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D,
+                                         float(low), float(high), float(levels), ptr(lp), ptr(ll), ptr(ws), ws_bytes,
+                                         stream_ptr(loc.device)), "vaemdl_dlogistic_fwd")
+        ctx.save_for_backward(locd, lsd, xd)
+        ctx.meta = (C, ld, x_dtype, n_img, x_batch, D, float(low), float(high), float(levels), shape)
+        outs = tuple(t for t in (lp, ll) if t is not None)
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        locd, lsd, xd = ctx.saved_tensors
+        C, ld, x_dtype, n_img, x_batch, D, low, high, levels, shape = ctx.meta
+        g_elem = g_image = None
+        for g in grads:
+            if g is None:
+                continue
+            if tuple(g.shape) == shape:
+                g_elem = dense_f32(g, "grad(lp_elem)")
+            else:
+                g_image = dense_f32(g, "grad(ll_image)")
+        if g_elem is None and g_image is None:
+            return (None,) * 9
+        # gradients of the two halves of an un-split [..,2C] tensor are written into one [..,2C] buffer
+        if ld == 2 * C:
+            both = torch.empty(shape[:-1] + (2 * C,), device=locd.device, dtype=torch.float32)
+            dloc, dls, ld_out = both[..., :C], both[..., C:], 2 * C
+            p_loc, p_ls = both.data_ptr(), both.data_ptr() + 4 * C
+        else:
+            dloc = torch.empty(shape, device=locd.device, dtype=torch.float32)
+            dls = torch.empty(shape, device=locd.device, dtype=torch.float32)
+            ld_out = C
+            p_loc, p_ls = dloc.data_ptr(), dls.data_ptr()
+        import ctypes
+        with torch.cuda.device(locd.device):
+            check(lib().vaemdl_dlogistic_bwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D, low, high,
+                                             levels, ptr(g_image), ptr(g_elem), ctypes.c_void_p(p_loc),
+                                             ctypes.c_void_p(p_ls), ld_out, stream_ptr(locd.device)),
+                  "vaemdl_dlogistic_bwd")
+        return dloc, dls, None, None, None, None, None, None, None
+
+
+def dlogistic_log_prob(loc, logscale, x, low=-1.0, high=1.0, levels=256.0) -> torch.Tensor:
+    """Element-wise plain discretized-logistic log-prob (utils/discretized_logistic.py:35-78)."""
+    n_event = min(3, loc.dim())
+    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event, True, False)
+
+
+def dlogistic_log_likelihood(loc, logscale, x, low=-1.0, high=1.0, levels=256.0, n_event_dims: int = 3) -> torch.Tensor:
+    """``reduce_sum(log_prob(x), last n_event_dims axes)`` (models/loss.py:32) without the element-wise tensor."""
+    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event_dims, False, True)
+
+
+# --------------------------------------------------------------------------------------------------
+# log-mean-exp / IWAE tail
+# --------------------------------------------------------------------------------------------------
+class _LmeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_w2d):
+        S, B = log_w2d.shape
+        out = torch.empty(B, device=log_w2d.device, dtype=torch.float32)
+        with torch.cuda.device(log_w2d.device):
+            check(lib().vaemdl_logmeanexp_fwd(ptr(log_w2d), S, B, ptr(out), stream_ptr(log_w2d.device)),
+                  "vaemdl_logmeanexp_fwd")
+        ctx.save_for_backward(log_w2d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (log_w2d,) = ctx.saved_tensors
+        S, B = log_w2d.shape
+        g = dense_f32(g, "grad")
+        d = torch.empty_like(log_w2d)
+        with torch.cuda.device(log_w2d.device):
+            check(lib().vaemdl_logmeanexp_bwd(ptr(log_w2d), ptr(g), S, B, ptr(d), stream_ptr(log_w2d.device)),
+                  "vaemdl_logmeanexp_bwd")
+        return d
+
+
+def logmeanexp(log_w: torch.Tensor, axis: int) -> torch.Tensor:
+    """``log(mean(exp(log_w), axis))`` computed stably (utils/utils.py:9-11), differentiable."""
+    _abi.require_cuda(log_w, "log_w")
+    axis = axis % log_w.dim()
+    moved = log_w.movedim(axis, 0)
+    rest = tuple(moved.shape[1:])
+    flat = dense_f32(moved.reshape(moved.shape[0], -1), "log_w")
+    return _LmeFn.apply(flat).reshape(rest)
+
+
+def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None):
+    """Fused IWAE tail on ``ll [S,B]`` (+ ``extra [S,B]``): returns ``(log_w, lme_b, elbo, g_ll)`` where
+    ``g_ll = d(-elbo)/d ll`` (models/loss.py:34-37).  Not recorded by autograd -- use ``logmeanexp`` for that."""
+    ll = dense_f32(ll, "ll")
+    S, B = ll.shape
+    ex = dense_f32(extra, "extra") if extra is not None else None
+    log_w = torch.empty_like(ll)
+    lme_b = torch.empty(B, device=ll.device, dtype=torch.float32)
+    elbo = torch.empty(1, device=ll.device, dtype=torch.float32)
+    g_ll = torch.empty_like(ll)
+    with torch.cuda.device(ll.device):
+        check(lib().vaemdl_iwae_tail(ptr(ll), ptr(ex), S, B, ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll),
+                                     stream_ptr(ll.device)), "vaemdl_iwae_tail")
+    return log_w, lme_b, elbo, g_ll
+
+
+# --------------------------------------------------------------------------------------------------
+# samplers
+# --------------------------------------------------------------------------------------------------
+def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, variant: int = _abi.SAMPLE_OPENAI,
+                out_range: int = _abi.RANGE_SYM, want_quantised: bool = False, want_index: bool = False):
+    """Explicit-noise MoDL sampler.  ``params [..., H, W, 10M]``; the noise may carry extra leading dims ``[n..., ...]``
+    (``u_mix [n..., ..., H, W, M]``): the parameters are then re-used for every ``n`` without being tiled.
+    Returns ``x [n..., ..., H, W, 3]`` float32 (+ uint8 quantised values, + uint8 mixture indices)."""
+    p = dense_f32(params, "parameters")
+    H, W, C10 = p.shape[-3:]
+    M = C10 // 10
+    lead = tuple(p.shape[:-3])
+    n_img = int(math.prod(lead)) if lead else 1
+    um = dense_f32(u_mix, "u_mix")
+    ul = dense_f32(u_log, "u_log")
+    per_rep = n_img * H * W * M
+    if um.shape[-1] != M or um.numel() % per_rep:
+        raise ValueError("u_mix must have shape [n..., ..., H, W, n_mix]")
+    n_rep = um.numel() // per_rep
+    out_lead = tuple(um.shape[:-3])
+    if int(math.prod(out_lead)) != n_rep * n_img:
+        raise ValueError("u_mix leading dims must be [n...] + parameters.shape[:-3]")
+    want = n_rep * n_img * H * W * 3 * (M if variant == _abi.SAMPLE_MDL else 1)
+    if ul.numel() != want:
+        raise ValueError("u_log must have shape [n..., ..., H, W, 3] (openai) or [n..., ..., H, W, 3, n_mix] (mdl)")
+    x = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.float32)
+    xq = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.uint8) if want_quantised else None
+    idx = torch.empty(out_lead + (H, W), device=p.device, dtype=torch.uint8) if want_index else None
+    with torch.cuda.device(p.device):
+        check(lib().vaemdl_modl_sample(ptr(p), ptr(um), ptr(ul), variant, out_range, n_rep, n_img, H, W, M, ptr(x),
+                                       ptr(xq), ptr(idx), stream_ptr(p.device)), "vaemdl_modl_sample")
+    outs = [x]
+    if want_quantised:
+        outs.append(xq)
+    if want_index:
+        outs.append(idx)
+    return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def dlogistic_sample(loc: torch.Tensor, logscale: torch.Tensor, u: torch.Tensor, low=-1.0, high=1.0) -> torch.Tensor:
+    """``clip(loc + exp(logscale) * (log u - log(1-u)), low, high)`` (utils/discretized_logistic.py:80-85)."""
+    if loc.shape != logscale.shape:
+        loc, logscale = torch.broadcast_tensors(loc, logscale)
+    _abi.require_cuda(loc, "loc")
+    locd, lsd, C, ld = _dl_layout(loc, logscale)
+    n_param = loc.numel()
+    ud = dense_f32(u, "u")
+    if ud.numel() % n_param:
+        raise ValueError("u must have shape [n..., *loc.shape]")
+    out = torch.empty(ud.shape, device=loc.device, dtype=torch.float32)
+    reps = ud.numel() // n_param
+    with torch.cuda.device(loc.device):
+        for r in range(reps):  # leading sample dims re-use the same parameters
+            import ctypes
+            off = r * n_param * 4
+            check(lib().vaemdl_dlogistic_sample(ptr(locd), ptr(lsd), C, ld, ctypes.c_void_p(ud.data_ptr() + off), n_param,
+                                                float(low), float(high), ctypes.c_void_p(out.data_ptr() + off),
+                                                stream_ptr(loc.device)), "vaemdl_dlogistic_sample")
+    return out

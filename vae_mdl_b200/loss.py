@@ -1,0 +1,117 @@
+"""Mirror of models/loss.py (``iwae_loss`` :26-55, ``elbo_loss`` :58-70) and of model06's ``loss_fn``
+(models/model06.py:38-72), plus the fused observation-model step used by the benchmark.
+
+Like the reference (models/loss.py:13-23) importing this module gives every ``torch.distributions.Distribution`` a
+settable ``axes`` property, so ``pz`` / ``qzx`` can be plain ``torch.distributions.Normal`` objects.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributions as td
+
+from . import functional as F
+from .utils import logmeanexp
+
+__all__ = ["iwae_loss", "elbo_loss", "loss_fn", "modl_iwae_step"]
+
+
+def _get_axes(self):
+    return self._axes
+
+
+def _set_axes(self, axes):
+    self._axes = axes
+
+
+td.Distribution.axes = property(_get_axes, _set_axes)  # models/loss.py:13-23
+
+
+def _axes(d):
+    return tuple(d.axes)
+
+
+def _lpxz(pxz, x):
+    """``reduce_sum(pxz.log_prob(x), axis=pxz.axes)`` (models/loss.py:32).  The observation models of this package
+    compute the per-image sum inside the kernel when the axes are the image axes."""
+    axes = [a for a in pxz.axes]
+    if hasattr(pxz, "log_likelihood") and sorted(axes) == [-3, -2, -1]:
+        return pxz.log_likelihood(x)
+    return torch.sum(pxz.log_prob(x), dim=tuple(axes))
+
+
+def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
+    """models/loss.py:26-55; returns ``(-iwae_elbo, metrics)`` with the reference's metric keys."""
+    lpz = torch.sum(pz.log_prob(z), dim=_axes(pz))                      # :28
+    lqzx = torch.sum(qzx.log_prob(z), dim=_axes(qzx))                   # :30
+    lpxz = _lpxz(pxz, x)                                                # :32
+    log_w = lpxz + beta * (lpz - lqzx)                                  # :34
+    iwae_elbo = torch.mean(logmeanexp(log_w, axis=0), dim=-1)           # :37
+    n_dims = float(math.prod(x.shape[1:]))                              # :42 (reference semantics kept)
+    bpd = -iwae_elbo / (math.log(2.0) * n_dims)                         # :43
+    kl = -torch.mean(lpz - lqzx, dim=0)                                 # :46
+    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz, "lqzx": lqzx, "lpz": lpz, "kl": kl}
+
+
+def elbo_loss(x, z, pz, qzx, pxz):
+    """models/loss.py:58-70."""
+    lpz = torch.sum(pz.log_prob(z), dim=_axes(pz))
+    lqzx = torch.sum(qzx.log_prob(z), dim=_axes(qzx))
+    lpxz = _lpxz(pxz, x)
+    log_w = lpxz + (lpz - lqzx)
+    elbo = torch.mean(torch.mean(log_w, dim=0), dim=-1)
+    return -elbo, {"loss": -elbo, "lpxz": lpxz}
+
+
+def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
+    """model06's loss (models/model06.py:38-72); arguments are ``DistributionTuple``s except ``pz``."""
+    lqz2z1 = torch.sum(qz2z1.dist.log_prob(qz2z1.z), dim=tuple(qz2z1.axes))
+    lqz1x = torch.sum(qz1x.dist.log_prob(qz1x.z), dim=tuple(qz1x.axes))
+    lpz2 = torch.sum(pz.log_prob(qz2z1.z), dim=_axes(pz))
+    lpz1z2 = torch.sum(pz1z2.dist.log_prob(qz1x.z), dim=tuple(qz1x.axes))
+    dist = pxz1.dist
+    if hasattr(dist, "log_likelihood") and sorted(pxz1.axes) == [-3, -2, -1]:
+        lpxz = dist.log_likelihood(x)
+    else:
+        lpxz = torch.sum(dist.log_prob(x), dim=tuple(pxz1.axes))
+    log_w = lpxz + (lpz2 - lqz2z1) + (lpz1z2 - lqz1x)                    # :47
+    iwae_elbo = torch.mean(logmeanexp(log_w, axis=0), dim=-1)           # :50
+    n_dims = float(math.prod(x.shape[-len(pxz1.axes):]))                # :54
+    bpd = -iwae_elbo / (math.log(2.0) * n_dims)
+    kl1 = -torch.mean(lpz1z2 - lqz1x, dim=0)
+    kl2 = -torch.mean(lpz2 - lqz2z1, dim=0)
+    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz, "lqz1x": lqz1x, "lqz2z1": lqz2z1,
+                        "lpz2": lpz2, "lpz1z2": lpz1z2, "kl1": kl1, "kl2": kl2}
+
+
+def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True):
+    """The whole observation-model side of one IWAE step in 3 (+1) kernel launches, no autograd graph:
+    per-image MoDL log-likelihood -> fused IWAE tail (log-mean-exp, elbo, softmax weights) -> MoDL gradient.
+
+    ``params [S,B,H,W,10M]``, ``x [B,H,W,3]`` (uint8 or float in [0,1]), ``extra = beta*(lpz-lqzx) [S,B]`` or None.
+    Returns ``(loss=-elbo [1], lpxz [S,B], dparams or None)`` -- the same numbers ``iwae_loss`` + ``backward`` give.
+    """
+    with torch.no_grad():
+        lpxz = F.modl_log_likelihood(params, x)
+        S = lpxz.shape[0]
+        _, _, elbo, g_ll = F.iwae_tail(lpxz.reshape(S, -1), None if extra is None else extra.reshape(S, -1))
+        dparams = None
+        if need_grad:
+            dparams = F._ModlFn.backward(_Ctx(params, x), g_ll.reshape(lpxz.shape))[0]
+    return -elbo, lpxz, dparams
+
+
+class _Ctx:
+    """Minimal stand-in for an autograd context so ``modl_iwae_step`` can call the backward kernel directly."""
+
+    def __init__(self, params, x):
+        from . import _abi
+        from .functional import _prep_x
+        p = _abi.dense_f32(params, "parameters")
+        H, W, C10 = p.shape[-3:]
+        lead = tuple(p.shape[:-3])
+        n_img = int(math.prod(lead)) if lead else 1
+        xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
+        self.saved_tensors = (p, xd)
+        self.meta = (x_dtype, _abi.RANGE_UNIT, _abi.EDGE_MDL, n_img, x_batch, H, W, C10 // 10)
