@@ -79,14 +79,18 @@ VAEMDL_API const char* vaemdl_strerror(int code);
  * params   [n_img, H, W, 10*M]
  * x        [x_batch, H, W, 3]  (float32 or uint8, see x_dtype / x_range)
  * lp_pixel [n_img, H, W]   nullable -- per-pixel log-prob (what log_prob() returns, minus the trailing 1)
- * ll_image [n_img]         nullable -- sum over H,W of lp_pixel (deterministic summation order when H*W % 32 == 0)
- * workspace: at least vaemdl_modl_workspace_bytes(n_img, H, W) bytes (only read/written when ll_image != NULL)
+ * ll_image [n_img]         nullable -- sum over H,W of lp_pixel
+ * ll_image_f64 [n_img]     nullable -- the same sum in float64.  The per-pixel values are float32, but they are
+ *                          accumulated in float64 (fixed order for M in {5,10,20,30} and H*W >= 32, float64 atomics
+ *                          otherwise): |ll| ~ 2e4 nats has a float32 ulp of 2e-3, which would go straight into the
+ *                          softmax over importance samples of the IWAE gradient.  Feed this to vaemdl_iwae_tail.
+ * workspace: 8-byte aligned, at least vaemdl_modl_workspace_bytes(n_img, H, W) bytes (used when a sum is requested)
  * ------------------------------------------------------------------------ */
 VAEMDL_API size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W);
 
 VAEMDL_API int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
                     long long n_img, int x_batch, int H, int W, int M,
-                    float* lp_pixel, float* ll_image,
+                    float* lp_pixel, float* ll_image, double* ll_image_f64,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ *
@@ -113,14 +117,14 @@ VAEMDL_API int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, 
  *                (ld = C for separate tensors; ld = 2*C with logscale = loc + C for the
  *                 un-split [..,6] conv output of models/model03.py:88-91).
  * x  [x_batch, D] float32 or uint8 (uint8 => x = k/255.f); used as is (no rescale, :37).
- * lp_elem [n_img, D] nullable ; ll_image [n_img] nullable.
+ * lp_elem [n_img, D] nullable ; ll_image [n_img] nullable ; ll_image_f64 [n_img] nullable (float64 accumulation).
  * ------------------------------------------------------------------------ */
 VAEMDL_API size_t vaemdl_dlogistic_workspace_bytes(long long n_img, long long D);
 
 VAEMDL_API int vaemdl_dlogistic_fwd(const float* loc, const float* logscale, int C, int ld,
                          const void* x, int x_dtype, long long n_img, int x_batch, long long D,
                          float low, float high, float levels,
-                         float* lp_elem, float* ll_image,
+                         float* lp_elem, float* ll_image, double* ll_image_f64,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* dloc / dlogscale use the same (C, ld_out) addressing as loc / logscale. */
@@ -137,14 +141,17 @@ VAEMDL_API int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int
  * log_w [S, B] ; out_b [B]
  * ------------------------------------------------------------------------ */
 VAEMDL_API int vaemdl_logmeanexp_fwd(const float* log_w, int S, long long B, float* out_b, void* stream);
+VAEMDL_API int vaemdl_logmeanexp_fwd_f64(const double* log_w, int S, long long B, float* out_b, void* stream);
 /* dlog_w[s,b] = g_out[b] * softmax_s(log_w[:,b])  (gradient of utils/utils.py:9-11; no stop_gradient there) */
 VAEMDL_API int vaemdl_logmeanexp_bwd(const float* log_w, const float* g_out, int S, long long B, float* dlog_w, void* stream);
+VAEMDL_API int vaemdl_logmeanexp_bwd_f64(const double* log_w, const float* g_out, int S, long long B, float* dlog_w, void* stream);
 
 /* Fused IWAE tail: log_w = ll + (extra ? extra : 0); lme_b = logmeanexp_s; elbo = mean_b lme_b;
  * g_ll[s,b] = d(-elbo)/d ll[s,b] = -softmax_s(log_w)[s,b] / B.       (models/loss.py:34-37)
- * ll [S,B]; extra [S,B] nullable (= beta*(lpz-lqzx)); outputs nullable: log_w [S,B], lme_b [B], elbo [1], g_ll [S,B].
- * One CTA-wide deterministic reduction; single launch. */
-VAEMDL_API int vaemdl_iwae_tail(const float* ll, const float* extra, int S, long long B,
+ * ll [S,B] float32 or ll_f64 [S,B] float64 (exactly one may be NULL; ll_f64 wins when both are given);
+ * extra [S,B] nullable (= beta*(lpz-lqzx)); outputs nullable: log_w [S,B], lme_b [B], elbo [1], g_ll [S,B].
+ * Fixed summation order (bitwise reproducible). */
+VAEMDL_API int vaemdl_iwae_tail(const float* ll, const double* ll_f64, const float* extra, int S, long long B,
                      float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
 
 /* ------------------------------------------------------------------------ *

@@ -41,7 +41,13 @@ def modl_case(S, B, H, W, M, kind="randn", xdtype="u8"):
     ll = F.modl_log_likelihood(pd, xd)
     lp = F.modl_log_prob(pd, xd)
     loss, lpxz, dp = V.modl_iwae_step(pd, xd, ex.float().to(dev))
+    # kernel-only gradient: identical upstream weights on both sides
+    gw = torch.randn(S, B, generator=g)
+    p64b = p.double().requires_grad_(True)
+    (O.modl_log_prob(p64b, x64).sum((-1, -2, -3)) * gw.double()).sum().backward()
+    dpk = F.modl_backward(pd, xd, g_image=gw.to(dev))
     out = {
+        "gradk_rel": relerr(dpk, p64b.grad),
         "ll_maxrel": ((ll.cpu().double() - ll64.detach()).abs() / ll64.detach().abs()).max().item(),
         "lp_maxabs": (lp.cpu().double() - lp64.detach()[..., 0]).abs().max().item(),
         "lpsum_vs_ll": (lp.sum((-1, -2)) - ll).abs().max().item(),
@@ -147,7 +153,7 @@ for name, (S, B, H, W, M) in {"cfg1": (5, 64, 32, 32, 10), "cfg1p": (5, 128, 32,
     wsb = L.vaemdl_modl_workspace_bytes(n_img, H, W)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev); ll = torch.empty(S, B, device=dev)
     st = _abi.stream_ptr(dev)
-    f = lambda: L.vaemdl_modl_fwd(p.data_ptr(), xu.data_ptr(), 1, 0, 0, n_img, B, H, W, M, None, ll.data_ptr(), ws.data_ptr(), wsb, st)
+    f = lambda: L.vaemdl_modl_fwd(p.data_ptr(), xu.data_ptr(), 1, 0, 0, n_img, B, H, W, M, None, ll.data_ptr(), None, ws.data_ptr(), wsb, st)
     b = lambda: L.vaemdl_modl_bwd(p.data_ptr(), xu.data_ptr(), 1, 0, 0, n_img, B, H, W, M, gimg.data_ptr(), None, dp.data_ptr(), st)
     tf = timeit(f); tb = timeit(b)
     npx = S * B * H * W

@@ -31,17 +31,20 @@ PROTOTYPES = {
     "vaemdl_strerror": (c_char_p, [c_int]),
     "vaemdl_modl_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "vaemdl_modl_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
-                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "vaemdl_dlogistic_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_longlong,
-                                     c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_dlogistic_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_longlong,
                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vaemdl_logmeanexp_fwd": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_logmeanexp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
-    "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_logmeanexp_fwd_f64": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+    "vaemdl_logmeanexp_bwd_f64": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+    "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
     "vaemdl_modl_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_sample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_longlong, c_float, c_float,

@@ -124,7 +124,7 @@ struct DeviceInfo {
 const DeviceInfo& device_info();  // cached per current device (api_misc.cu)
 
 // iwae.cu: fused IWAE tail with an explicit batch normaliser
-int iwae_tail_norm(const float* ll, const float* extra, int S, long long B, float b_norm, float* log_w, float* lme_b,
-                   float* g_ll, cudaStream_t st);
+int iwae_tail_norm(const float* ll, const double* ll64, const float* extra, int S, long long B, float b_norm,
+                   float* log_w, float* lme_b, float* g_ll, cudaStream_t st);
 
 }  // namespace vaemdl

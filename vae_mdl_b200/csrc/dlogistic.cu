@@ -17,8 +17,8 @@ struct DlArgs {
   const float* logscale;
   const void* x;
   float* lp_elem;
-  float* partial;
-  float* ll_atomic;
+  double* partial;    // [n_tiles][2] float64
+  double* ll_atomic;  // [n_img] float64 accumulators
   const float* g_image;
   const float* g_elem;
   float* dloc;
@@ -93,7 +93,7 @@ __device__ __forceinline__ DlOut dl_elem(float x, float loc, float ls, const DlA
   return o;
 }
 
-__device__ __forceinline__ float dl_warp_sum(float v) {
+__device__ __forceinline__ double dl_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
@@ -154,33 +154,41 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
       const float val = active ? acc : 0.0f;
       if (a.partial) {
         const long long n_first = __shfl_sync(kFull, n, 0);
-        const float s0 = dl_warp_sum(n == n_first ? val : 0.0f);
-        const float s1 = dl_warp_sum(n == n_first ? 0.0f : val);
+        const double s0 = dl_warp_sum(n == n_first ? static_cast<double>(val) : 0.0);
+        const double s1 = dl_warp_sum(n == n_first ? 0.0 : static_cast<double>(val));
         if (lane == 0) {
           a.partial[2 * t] = s0;
           a.partial[2 * t + 1] = s1;
         }
       } else if (a.ll_atomic && active) {
-        atomicAdd(a.ll_atomic + n, val);
+        atomicAdd(a.ll_atomic + n, static_cast<double>(val));
       }
     }
   }
 }
 
-__global__ void dl_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ll_image, long long n_img,
-                                          long long rows_per_img) {
+__global__ void dl_cast_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+
+__global__ void dl_reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ ll_image,
+                                          double* __restrict__ ll_image_f64, long long n_img, long long rows_per_img) {
   const long long n = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= n_img) return;
   const long long first = n * rows_per_img, last = first + rows_per_img - 1;
   const long long t_lo = first / 32, t_hi = last / 32;
-  float acc = 0.0f;
+  double acc = 0.0;
   for (long long t = t_lo + lane; t <= t_hi; t += 32) {
     const long long n0 = (t * 32) / rows_per_img;
     acc += (n0 == n) ? partial[2 * t] : partial[2 * t + 1];
   }
   acc = dl_warp_sum(acc);
-  if (lane == 0) ll_image[n] = acc;
+  if (lane == 0) {
+    if (ll_image) ll_image[n] = static_cast<float>(acc);
+    if (ll_image_f64) ll_image_f64[n] = acc;
+  }
 }
 
 // sampler: clip(loc + exp(ls) * (log u - log(1-u)), low, high) in float64   (utils/discretized_logistic.py:80-85)
@@ -246,37 +254,46 @@ using namespace vaemdl;
 
 extern "C" size_t vaemdl_dlogistic_workspace_bytes(long long n_img, long long D) {
   if (n_img <= 0 || D <= 0) return 0;
-  return static_cast<size_t>((n_img * D + 31) / 32) * 2 * sizeof(float) + 256;
+  const size_t bytes = static_cast<size_t>((n_img * D + 31) / 32) * 2 * sizeof(double);
+  const size_t acc = static_cast<size_t>(n_img) * sizeof(double);
+  return (bytes > acc ? bytes : acc) + 256;
 }
 
 extern "C" int vaemdl_dlogistic_fwd(const float* loc, const float* logscale, int C, int ld, const void* x, int x_dtype,
                                     long long n_img, int x_batch, long long D, float low, float high, float levels,
-                                    float* lp_elem, float* ll_image, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+                                    float* lp_elem, float* ll_image, double* ll_image_f64, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
   DlArgs a{};
   int cpt = 1;
   int rc = dl_fill(a, loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, cpt);
   if (rc) return rc;
-  if (!lp_elem && !ll_image) return VAEMDL_EINVAL;
+  const bool want_ll = ll_image || ll_image_f64;
+  if (!lp_elem && !want_ll) return VAEMDL_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   a.lp_elem = lp_elem;
-  const bool use_partials = ll_image && a.rows_per_img >= 32;
-  if (ll_image) {
+  const bool use_partials = want_ll && a.rows_per_img >= 32;
+  if (want_ll) {
+    if (!workspace || workspace_bytes < vaemdl_dlogistic_workspace_bytes(n_img, D)) return VAEMDL_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
     if (use_partials) {
-      if (!workspace || workspace_bytes < vaemdl_dlogistic_workspace_bytes(n_img, D)) return VAEMDL_EWORKSPACE;
-      a.partial = static_cast<float*>(workspace);
+      a.partial = static_cast<double*>(workspace);
     } else {
-      cudaError_t e = cudaMemsetAsync(ll_image, 0, sizeof(float) * n_img, st);
+      a.ll_atomic = ll_image_f64 ? ll_image_f64 : static_cast<double*>(workspace);
+      cudaError_t e = cudaMemsetAsync(a.ll_atomic, 0, sizeof(double) * n_img, st);
       if (e != cudaSuccess) return cuda_rc(e);
-      a.ll_atomic = ll_image;
     }
   }
   rc = dl_launch<false>(a, cpt, st);
   if (rc) return rc;
   if (use_partials) {
     const long long threads = n_img * 32;
-    dl_reduce_partials_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(a.partial, ll_image, n_img,
+    dl_reduce_partials_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(a.partial, ll_image,
+                                                                                           ll_image_f64, n_img,
                                                                                            a.rows_per_img);
+    return cuda_rc(cudaGetLastError());
+  }
+  if (want_ll && ll_image) {
+    dl_cast_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
     return cuda_rc(cudaGetLastError());
   }
   return VAEMDL_OK;

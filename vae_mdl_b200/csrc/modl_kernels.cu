@@ -26,8 +26,8 @@ struct ModlArgs {
   const float* params;
   const void* x;
   float* lp_pixel;       // nullable
-  float* partial;        // [num_tiles][2] tile partial sums (nullable)
-  float* ll_atomic;      // [n_img] pre-zeroed, used instead of `partial` when H*W < pixels-per-tile
+  double* partial;       // [num_tiles][2] tile partial sums in float64 (nullable)
+  double* ll_atomic;     // [n_img] pre-zeroed float64 accumulators, used instead of `partial` when tiles would span >2 images
   const float* g_image;  // nullable
   const float* g_pixel;  // nullable
   float* dparams;
@@ -127,6 +127,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+// log2 with the exponent split off: lg2.approx is only accurate to 2^-22 RELATIVE outside (0.5, 2); on the mantissa
+// its error is 2^-22 absolute, which keeps the per-pixel log-prob good to ~2e-7 instead of ~5e-6.
+__device__ __forceinline__ float lg2_split(float v) {
+  const int bits = __float_as_int(v);
+  const int e = (bits >> 23) - 127;
+  const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+  return static_cast<float>(e) + lg2a(m);
 }
 
 // ---- chunk <-> shared memory -------------------------------------------------------------------------------------
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
     const float* grow = a.params + i * ROWF;
 
     if constexpr (!BWD) {
-      float lp = (lg2a(S) - lg2a(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
+      float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
       if (tiny) {
         float lt, ll;
         modl_pixel_logdomain(grow, M, px, lt, ll);
@@ -385,14 +398,15 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
       if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
       const float val = owner ? lp : 0.0f;
       if (a.partial) {
-        const float s0 = warp_sum(n == n_first ? val : 0.0f);
-        const float s1 = warp_sum(n == n_first ? 0.0f : val);
+        // float64 from here on: the per-image sums (~ -2e4 nats) feed a softmax over importance samples
+        const double s0 = warp_sum(n == n_first ? static_cast<double>(val) : 0.0);
+        const double s1 = warp_sum(n == n_first ? 0.0 : static_cast<double>(val));
         if (lane == 0) {
           a.partial[2 * t] = s0;
           a.partial[2 * t + 1] = s1;
         }
       } else if (a.ll_atomic) {
-        if (owner) atomicAdd(a.ll_atomic + n, val);
+        if (owner) atomicAdd(a.ll_atomic + n, static_cast<double>(val));
       }
     } else {
       const float rS = rcpa(S), rSW = rcpa(SW);
@@ -438,20 +452,28 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
 }
 
 // ---- per-image sums from the tile partials (fixed order => bitwise reproducible) ---------------------------------------
-__global__ void modl_reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ll_image, long long n_img,
-                                            int HW, int PPT) {
+__global__ void modl_reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ ll_image,
+                                            double* __restrict__ ll_image_f64, long long n_img, int HW, int PPT) {
   const long long n = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= n_img) return;
   const long long first = n * HW, last = first + HW - 1;
   const long long t_lo = first / PPT, t_hi = last / PPT;
-  float acc = 0.0f;
+  double acc = 0.0;
   for (long long t = t_lo + lane; t <= t_hi; t += 32) {
     const long long n0 = (t * PPT) / HW;
     acc += (n0 == n) ? partial[2 * t] : partial[2 * t + 1];
   }
   acc = warp_sum(acc);
-  if (lane == 0) ll_image[n] = acc;
+  if (lane == 0) {
+    if (ll_image) ll_image[n] = static_cast<float>(acc);
+    if (ll_image_f64) ll_image_f64[n] = acc;
+  }
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
 }
 
 // ---- any-M kernel: one thread per pixel-sample, parameters straight from global memory (correct, not tuned) --------------
@@ -483,10 +505,10 @@ __global__ void __launch_bounds__(128) modl_generic_kernel(const ModlArgs a) {
     float lt = 0.f, ll = 0.f;
     if (tiny) modl_pixel_logdomain(row, M, px, lt, ll);
     if constexpr (!BWD) {
-      const float lp = tiny ? (lt - ll) : (lg2a(sumWP) - lg2a(sumW)) * kLn2;
+      const float lp = tiny ? (lt - ll) : (lg2_split(sumWP) - lg2_split(sumW)) * kLn2;
       if (active) {
         if (a.lp_pixel) a.lp_pixel[i] = lp;
-        if (a.ll_atomic) atomicAdd(a.ll_atomic + n, lp);
+        if (a.ll_atomic) atomicAdd(a.ll_atomic + n, static_cast<double>(lp));
       }
     } else {
       float g = 0.f;
@@ -599,18 +621,21 @@ using namespace vaemdl;
 
 extern "C" size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W) {
   if (n_img <= 0 || H <= 0 || W <= 0) return 0;
-  // two floats per tile at the smallest tile size (10 pixels) -- an upper bound for every M
+  // two float64 per tile at the smallest tile size (10 pixels) -- an upper bound for every M
   const long long n_px = n_img * H * W;
-  return static_cast<size_t>((n_px + 9) / 10) * 2 * sizeof(float) + 256;
+  size_t bytes = static_cast<size_t>((n_px + 9) / 10) * 2 * sizeof(double);
+  const size_t acc = static_cast<size_t>(n_img) * sizeof(double);  // atomic path: one float64 accumulator per image
+  return (bytes > acc ? bytes : acc) + 256;
 }
 
 extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
                                long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               double* ll_image_f64, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
-  if (!lp_pixel && !ll_image) return VAEMDL_EINVAL;
+  if (!lp_pixel && !ll_image && !ll_image_f64) return VAEMDL_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool want_ll = ll_image || ll_image_f64;
   ModlArgs a{};
   a.params = params;
   a.x = x;
@@ -623,15 +648,16 @@ extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, 
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
   const int ppt = tile_ppt(M);
-  const bool use_partials = ll_image && ppt > 0 && a.HW >= ppt;
-  if (ll_image) {
+  const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
+  if (want_ll) {
+    if (!workspace || workspace_bytes < vaemdl_modl_workspace_bytes(n_img, H, W)) return VAEMDL_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
     if (use_partials) {
-      if (!workspace || workspace_bytes < vaemdl_modl_workspace_bytes(n_img, H, W)) return VAEMDL_EWORKSPACE;
-      a.partial = static_cast<float*>(workspace);
+      a.partial = static_cast<double*>(workspace);
     } else {
-      cudaError_t e = cudaMemsetAsync(ll_image, 0, sizeof(float) * n_img, st);
+      a.ll_atomic = ll_image_f64 ? ll_image_f64 : static_cast<double*>(workspace);
+      cudaError_t e = cudaMemsetAsync(a.ll_atomic, 0, sizeof(double) * n_img, st);
       if (e != cudaSuccess) return cuda_rc(e);
-      a.ll_atomic = ll_image;
     }
   }
   rc = launch_modl<false>(a, st);
@@ -640,7 +666,12 @@ extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, 
     const long long threads = n_img * 32;
     const int block = 256;
     const long long grid = (threads + block - 1) / block;
-    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(a.partial, ll_image, n_img, a.HW, ppt);
+    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(a.partial, ll_image, ll_image_f64, n_img,
+                                                                               a.HW, ppt);
+    return cuda_rc(cudaGetLastError());
+  }
+  if (want_ll && ll_image) {
+    cast_f64_f32_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
     return cuda_rc(cudaGetLastError());
   }
   return VAEMDL_OK;

@@ -39,9 +39,9 @@ class DiscretizedLogistic:
         """Element-wise, shape of ``loc`` (:35-78); x is used as given (no rescale)."""
         return F.dlogistic_log_prob(self.loc, self.logscale, x, self.low, self.high, self.levels)
 
-    def log_likelihood(self, x, n_event_dims=3):
+    def log_likelihood(self, x, n_event_dims=3, dtype=torch.float32):
         """``reduce_sum(log_prob(x), last n_event_dims axes)`` without the element-wise tensor (models/loss.py:32)."""
-        return F.dlogistic_log_likelihood(self.loc, self.logscale, x, self.low, self.high, self.levels, n_event_dims)
+        return F.dlogistic_log_likelihood(self.loc, self.logscale, x, self.low, self.high, self.levels, n_event_dims, dtype)
 
     def sample(self, n_samples=[], u=None, generator=None):
         """:80-85; ``n_samples=[]`` -> shape of ``loc``; ``n`` or ``[n]`` -> leading ``[n]``."""

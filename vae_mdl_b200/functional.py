@@ -16,6 +16,7 @@ from ._abi import check, dense_f32, lib, ptr, stream_ptr
 __all__ = [
     "modl_log_prob",
     "modl_log_likelihood",
+    "modl_backward",
     "dlogistic_log_prob",
     "dlogistic_log_likelihood",
     "logmeanexp",
@@ -48,10 +49,11 @@ def _check_batch(n_img: int, x_batch: int, what: str):
 
 
 class _ModlFn(torch.autograd.Function):
-    """Forward: per-pixel log-prob and/or per-image log-likelihood.  Backward: one fused kernel."""
+    """Forward: per-pixel log-prob or per-image log-likelihood (float32 or float64 sums).  Backward: one fused kernel."""
 
     @staticmethod
-    def forward(ctx, params, x, x_range, edge_mode, want_pixel, want_image):
+    def forward(ctx, params, x, x_range, edge_mode, mode):
+        # mode: "pixel" -> [..., H, W] ; "image" -> [...] float32 ; "image64" -> [...] float64
         p = dense_f32(params, "parameters")
         H, W, C10 = p.shape[-3], p.shape[-2], p.shape[-1]
         M = C10 // 10
@@ -62,50 +64,71 @@ class _ModlFn(torch.autograd.Function):
         xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
         _check_batch(n_img, x_batch, "log_prob")
         L = lib()
-        lp = torch.empty(lead + (H, W), device=p.device, dtype=torch.float32) if want_pixel else None
-        ll = torch.empty(lead, device=p.device, dtype=torch.float32) if want_image else None
-        ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W) if want_image else 0
-        ws = torch.empty(ws_bytes, device=p.device, dtype=torch.uint8) if ws_bytes else None
+        lp = ll = ll64 = ws = None
+        ws_bytes = 0
+        if mode == "pixel":
+            lp = torch.empty(lead + (H, W), device=p.device, dtype=torch.float32)
+        else:
+            if mode == "image64":
+                ll64 = torch.empty(lead, device=p.device, dtype=torch.float64)
+            else:
+                ll = torch.empty(lead, device=p.device, dtype=torch.float32)
+            ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W)
+            ws = torch.empty((ws_bytes + 7) // 8, device=p.device, dtype=torch.float64)
         with torch.cuda.device(p.device):
             check(L.vaemdl_modl_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
-                                    ptr(lp), ptr(ll), ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_fwd")
+                                    ptr(lp), ptr(ll), ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)),
+                  "vaemdl_modl_fwd")
         ctx.save_for_backward(p, xd)
-        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M)
-        outs = tuple(t for t in (lp, ll) if t is not None)
-        return outs if len(outs) > 1 else outs[0]
+        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode)
+        return lp if mode == "pixel" else (ll64 if mode == "image64" else ll)
 
     @staticmethod
-    def backward(ctx, *grads):
+    def backward(ctx, g):
         p, xd = ctx.saved_tensors
-        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M = ctx.meta
-        g_pixel = g_image = None
-        for g in grads:
-            if g is None:
-                continue
-            if g.dim() == p.dim() - 1:  # [..., H, W]
-                g_pixel = dense_f32(g, "grad(lp_pixel)")
-            else:
-                g_image = dense_f32(g, "grad(ll_image)")
-        if g_pixel is None and g_image is None:
-            return None, None, None, None, None, None
+        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode = ctx.meta
+        if g is None:
+            return None, None, None, None, None
+        g = dense_f32(g, "upstream gradient")
+        g_pixel, g_image = (g, None) if mode == "pixel" else (None, g)
         dp = torch.empty_like(p)
         with torch.cuda.device(p.device):
             check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
                                         ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
-        return dp, None, None, None, None, None
+        return dp, None, None, None, None
+
+
+def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch.Tensor] = None,
+                  g_pixel: Optional[torch.Tensor] = None, x_range: int = _abi.RANGE_UNIT,
+                  edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
+    """The gradient kernel on its own: d/dparams of sum(g_image * ll_image) + sum(g_pixel * lp_pixel)."""
+    p = dense_f32(params, "parameters")
+    H, W, C10 = p.shape[-3:]
+    lead = tuple(p.shape[:-3])
+    n_img = int(math.prod(lead)) if lead else 1
+    xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
+    _check_batch(n_img, x_batch, "backward")
+    gi = dense_f32(g_image, "g_image") if g_image is not None else None
+    gp = dense_f32(g_pixel, "g_pixel") if g_pixel is not None else None
+    dp = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
+                                    ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+    return dp
 
 
 def modl_log_prob(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
                   edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
     """Per-pixel MoDL log-prob ``[..., H, W]`` (utils/mdl.py:56-92 without the trailing ``expand_dims``)."""
-    return _ModlFn.apply(params, x, x_range, edge_mode, True, False)
+    return _ModlFn.apply(params, x, x_range, edge_mode, "pixel")
 
 
 def modl_log_likelihood(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
-                        edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
+                        edge_mode: int = _abi.EDGE_MDL, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """Per-image MoDL log-likelihood ``[...]`` = ``reduce_sum(log_prob(x), [-1,-2,-3])`` (models/loss.py:32),
-    computed without ever writing the per-pixel tensor."""
-    return _ModlFn.apply(params, x, x_range, edge_mode, False, True)
+    computed without ever writing the per-pixel tensor.  ``dtype=torch.float64`` returns the float64-accumulated sums
+    (same float32 per-pixel values; no float32 rounding of the ~-2e4 totals)."""
+    return _ModlFn.apply(params, x, x_range, edge_mode, "image64" if dtype == torch.float64 else "image")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -134,7 +157,7 @@ def _dl_layout(loc: torch.Tensor, logscale: torch.Tensor):
 
 class _DlFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, loc, logscale, x, low, high, levels, n_event_dims, want_elem, want_image):
+    def forward(ctx, loc, logscale, x, low, high, levels, n_event_dims, mode):
         if loc.shape != logscale.shape:
             loc, logscale = torch.broadcast_tensors(loc, logscale)
         _abi.require_cuda(loc, "loc")
@@ -147,33 +170,33 @@ class _DlFn(torch.autograd.Function):
         xd, x_dtype, x_batch = _prep_x(x, ev, "x")
         _check_batch(n_img, x_batch, "log_prob")
         L = lib()
-        lp = torch.empty(shape, device=loc.device, dtype=torch.float32) if want_elem else None
-        ll = torch.empty(lead, device=loc.device, dtype=torch.float32) if want_image else None
-        ws_bytes = L.vaemdl_dlogistic_workspace_bytes(n_img, D) if want_image else 0
-        ws = torch.empty(ws_bytes, device=loc.device, dtype=torch.uint8) if ws_bytes else None
+        lp = ll = ll64 = ws = None
+        ws_bytes = 0
+        if mode == "elem":
+            lp = torch.empty(shape, device=loc.device, dtype=torch.float32)
+        else:
+            if mode == "image64":
+                ll64 = torch.empty(lead, device=loc.device, dtype=torch.float64)
+            else:
+                ll = torch.empty(lead, device=loc.device, dtype=torch.float32)
+            ws_bytes = L.vaemdl_dlogistic_workspace_bytes(n_img, D)
+            ws = torch.empty((ws_bytes + 7) // 8, device=loc.device, dtype=torch.float64)
         with torch.cuda.device(loc.device):
             check(L.vaemdl_dlogistic_fwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D,
-                                         float(low), float(high), float(levels), ptr(lp), ptr(ll), ptr(ws), ws_bytes,
-                                         stream_ptr(loc.device)), "vaemdl_dlogistic_fwd")
+                                         float(low), float(high), float(levels), ptr(lp), ptr(ll), ptr(ll64), ptr(ws),
+                                         ws_bytes, stream_ptr(loc.device)), "vaemdl_dlogistic_fwd")
         ctx.save_for_backward(locd, lsd, xd)
-        ctx.meta = (C, ld, x_dtype, n_img, x_batch, D, float(low), float(high), float(levels), shape)
-        outs = tuple(t for t in (lp, ll) if t is not None)
-        return outs if len(outs) > 1 else outs[0]
+        ctx.meta = (C, ld, x_dtype, n_img, x_batch, D, float(low), float(high), float(levels), shape, mode)
+        return lp if mode == "elem" else (ll64 if mode == "image64" else ll)
 
     @staticmethod
-    def backward(ctx, *grads):
+    def backward(ctx, g):
         locd, lsd, xd = ctx.saved_tensors
-        C, ld, x_dtype, n_img, x_batch, D, low, high, levels, shape = ctx.meta
-        g_elem = g_image = None
-        for g in grads:
-            if g is None:
-                continue
-            if tuple(g.shape) == shape:
-                g_elem = dense_f32(g, "grad(lp_elem)")
-            else:
-                g_image = dense_f32(g, "grad(ll_image)")
-        if g_elem is None and g_image is None:
-            return (None,) * 9
+        C, ld, x_dtype, n_img, x_batch, D, low, high, levels, shape, mode = ctx.meta
+        if g is None:
+            return (None,) * 8
+        g = dense_f32(g, "upstream gradient")
+        g_elem, g_image = (g, None) if mode == "elem" else (None, g)
         # gradients of the two halves of an un-split [..,2C] tensor are written into one [..,2C] buffer
         if ld == 2 * C:
             both = torch.empty(shape[:-1] + (2 * C,), device=locd.device, dtype=torch.float32)
@@ -190,18 +213,19 @@ class _DlFn(torch.autograd.Function):
                                              levels, ptr(g_image), ptr(g_elem), ctypes.c_void_p(p_loc),
                                              ctypes.c_void_p(p_ls), ld_out, stream_ptr(locd.device)),
                   "vaemdl_dlogistic_bwd")
-        return dloc, dls, None, None, None, None, None, None, None
+        return dloc, dls, None, None, None, None, None, None
 
 
 def dlogistic_log_prob(loc, logscale, x, low=-1.0, high=1.0, levels=256.0) -> torch.Tensor:
     """Element-wise plain discretized-logistic log-prob (utils/discretized_logistic.py:35-78)."""
     n_event = min(3, loc.dim())
-    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event, True, False)
+    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event, "elem")
 
 
-def dlogistic_log_likelihood(loc, logscale, x, low=-1.0, high=1.0, levels=256.0, n_event_dims: int = 3) -> torch.Tensor:
+def dlogistic_log_likelihood(loc, logscale, x, low=-1.0, high=1.0, levels=256.0, n_event_dims: int = 3,
+                             dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``reduce_sum(log_prob(x), last n_event_dims axes)`` (models/loss.py:32) without the element-wise tensor."""
-    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event_dims, False, True)
+    return _DlFn.apply(loc, logscale, x, low, high, levels, n_event_dims, "image64" if dtype == torch.float64 else "image")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -212,9 +236,10 @@ class _LmeFn(torch.autograd.Function):
     def forward(ctx, log_w2d):
         S, B = log_w2d.shape
         out = torch.empty(B, device=log_w2d.device, dtype=torch.float32)
+        L = lib()
+        fn = L.vaemdl_logmeanexp_fwd_f64 if log_w2d.dtype == torch.float64 else L.vaemdl_logmeanexp_fwd
         with torch.cuda.device(log_w2d.device):
-            check(lib().vaemdl_logmeanexp_fwd(ptr(log_w2d), S, B, ptr(out), stream_ptr(log_w2d.device)),
-                  "vaemdl_logmeanexp_fwd")
+            check(fn(ptr(log_w2d), S, B, ptr(out), stream_ptr(log_w2d.device)), "vaemdl_logmeanexp_fwd")
         ctx.save_for_backward(log_w2d)
         return out
 
@@ -223,36 +248,46 @@ class _LmeFn(torch.autograd.Function):
         (log_w2d,) = ctx.saved_tensors
         S, B = log_w2d.shape
         g = dense_f32(g, "grad")
-        d = torch.empty_like(log_w2d)
+        d = torch.empty(log_w2d.shape, device=log_w2d.device, dtype=torch.float32)
+        L = lib()
+        fn = L.vaemdl_logmeanexp_bwd_f64 if log_w2d.dtype == torch.float64 else L.vaemdl_logmeanexp_bwd
         with torch.cuda.device(log_w2d.device):
-            check(lib().vaemdl_logmeanexp_bwd(ptr(log_w2d), ptr(g), S, B, ptr(d), stream_ptr(log_w2d.device)),
-                  "vaemdl_logmeanexp_bwd")
-        return d
+            check(fn(ptr(log_w2d), ptr(g), S, B, ptr(d), stream_ptr(log_w2d.device)), "vaemdl_logmeanexp_bwd")
+        return d.to(log_w2d.dtype)
+
+
+def _dense_f32_or_f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype == torch.float64:
+        _abi.require_cuda(t, name)
+        return t.contiguous()
+    return dense_f32(t, name)
 
 
 def logmeanexp(log_w: torch.Tensor, axis: int) -> torch.Tensor:
-    """``log(mean(exp(log_w), axis))`` computed stably (utils/utils.py:9-11), differentiable."""
+    """``log(mean(exp(log_w), axis))`` computed stably (utils/utils.py:9-11), differentiable.  float64 input is
+    reduced with float64 differences; the result is float32 either way."""
     _abi.require_cuda(log_w, "log_w")
     axis = axis % log_w.dim()
     moved = log_w.movedim(axis, 0)
     rest = tuple(moved.shape[1:])
-    flat = dense_f32(moved.reshape(moved.shape[0], -1), "log_w")
+    flat = _dense_f32_or_f64(moved.reshape(moved.shape[0], -1), "log_w")
     return _LmeFn.apply(flat).reshape(rest)
 
 
 def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None):
-    """Fused IWAE tail on ``ll [S,B]`` (+ ``extra [S,B]``): returns ``(log_w, lme_b, elbo, g_ll)`` where
-    ``g_ll = d(-elbo)/d ll`` (models/loss.py:34-37).  Not recorded by autograd -- use ``logmeanexp`` for that."""
-    ll = dense_f32(ll, "ll")
+    """Fused IWAE tail on ``ll [S,B]`` (float32 or float64) + ``extra [S,B]``: returns ``(log_w, lme_b, elbo, g_ll)``
+    (all float32) where ``g_ll = d(-elbo)/d ll`` (models/loss.py:34-37).  Not recorded by autograd."""
+    ll = _dense_f32_or_f64(ll, "ll")
     S, B = ll.shape
     ex = dense_f32(extra, "extra") if extra is not None else None
-    log_w = torch.empty_like(ll)
+    log_w = torch.empty((S, B), device=ll.device, dtype=torch.float32)
     lme_b = torch.empty(B, device=ll.device, dtype=torch.float32)
     elbo = torch.empty(1, device=ll.device, dtype=torch.float32)
-    g_ll = torch.empty_like(ll)
+    g_ll = torch.empty((S, B), device=ll.device, dtype=torch.float32)
+    is64 = ll.dtype == torch.float64
     with torch.cuda.device(ll.device):
-        check(lib().vaemdl_iwae_tail(ptr(ll), ptr(ex), S, B, ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll),
-                                     stream_ptr(ll.device)), "vaemdl_iwae_tail")
+        check(lib().vaemdl_iwae_tail(None if is64 else ptr(ll), ptr(ll) if is64 else None, ptr(ex), S, B, ptr(log_w),
+                                     ptr(lme_b), ptr(elbo), ptr(g_ll), stream_ptr(ll.device)), "vaemdl_iwae_tail")
     return log_w, lme_b, elbo, g_ll
 
 

@@ -37,7 +37,9 @@ def _lpxz(pxz, x):
     compute the per-image sum inside the kernel when the axes are the image axes."""
     axes = [a for a in pxz.axes]
     if hasattr(pxz, "log_likelihood") and sorted(axes) == [-3, -2, -1]:
-        return pxz.log_likelihood(x)
+        # float64-accumulated sums: log_w ~ -2e4 has a float32 ulp of 2e-3, which a float32 lpxz would feed straight
+        # into the softmax over importance samples.  The metric dict still reports float32 (reference dtype).
+        return pxz.log_likelihood(x, dtype=torch.float64)
     return torch.sum(pxz.log_prob(x), dim=tuple(axes))
 
 
@@ -51,7 +53,7 @@ def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
     n_dims = float(math.prod(x.shape[1:]))                              # :42 (reference semantics kept)
     bpd = -iwae_elbo / (math.log(2.0) * n_dims)                         # :43
     kl = -torch.mean(lpz - lqzx, dim=0)                                 # :46
-    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz, "lqzx": lqzx, "lpz": lpz, "kl": kl}
+    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz.float(), "lqzx": lqzx, "lpz": lpz, "kl": kl}
 
 
 def elbo_loss(x, z, pz, qzx, pxz):
@@ -60,8 +62,8 @@ def elbo_loss(x, z, pz, qzx, pxz):
     lqzx = torch.sum(qzx.log_prob(z), dim=_axes(qzx))
     lpxz = _lpxz(pxz, x)
     log_w = lpxz + (lpz - lqzx)
-    elbo = torch.mean(torch.mean(log_w, dim=0), dim=-1)
-    return -elbo, {"loss": -elbo, "lpxz": lpxz}
+    elbo = torch.mean(torch.mean(log_w, dim=0), dim=-1).float()
+    return -elbo, {"loss": -elbo, "lpxz": lpxz.float()}
 
 
 def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
@@ -72,7 +74,7 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
     lpz1z2 = torch.sum(pz1z2.dist.log_prob(qz1x.z), dim=tuple(qz1x.axes))
     dist = pxz1.dist
     if hasattr(dist, "log_likelihood") and sorted(pxz1.axes) == [-3, -2, -1]:
-        lpxz = dist.log_likelihood(x)
+        lpxz = dist.log_likelihood(x, dtype=torch.float64)
     else:
         lpxz = torch.sum(dist.log_prob(x), dim=tuple(pxz1.axes))
     log_w = lpxz + (lpz2 - lqz2z1) + (lpz1z2 - lqz1x)                    # :47
@@ -81,37 +83,20 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
     bpd = -iwae_elbo / (math.log(2.0) * n_dims)
     kl1 = -torch.mean(lpz1z2 - lqz1x, dim=0)
     kl2 = -torch.mean(lpz2 - lqz2z1, dim=0)
-    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz, "lqz1x": lqz1x, "lqz2z1": lqz2z1,
+    return -iwae_elbo, {"iwae_elbo": iwae_elbo, "bpd": bpd, "lpxz": lpxz.float(), "lqz1x": lqz1x, "lqz2z1": lqz2z1,
                         "lpz2": lpz2, "lpz1z2": lpz1z2, "kl1": kl1, "kl2": kl2}
 
 
 def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True):
-    """The whole observation-model side of one IWAE step in 3 (+1) kernel launches, no autograd graph:
-    per-image MoDL log-likelihood -> fused IWAE tail (log-mean-exp, elbo, softmax weights) -> MoDL gradient.
+    """The whole observation-model side of one IWAE step in 3 (+2 tiny) kernel launches, no autograd graph:
+    per-image MoDL log-likelihood (float64 sums) -> fused IWAE tail (log-mean-exp, elbo, softmax weights) -> MoDL gradient.
 
     ``params [S,B,H,W,10M]``, ``x [B,H,W,3]`` (uint8 or float in [0,1]), ``extra = beta*(lpz-lqzx) [S,B]`` or None.
-    Returns ``(loss=-elbo [1], lpxz [S,B], dparams or None)`` -- the same numbers ``iwae_loss`` + ``backward`` give.
+    Returns ``(loss=-elbo [1], lpxz [S,B] float64, dparams or None)`` -- the numbers ``iwae_loss`` + ``backward`` give.
     """
     with torch.no_grad():
-        lpxz = F.modl_log_likelihood(params, x)
+        lpxz = F.modl_log_likelihood(params, x, dtype=torch.float64)
         S = lpxz.shape[0]
         _, _, elbo, g_ll = F.iwae_tail(lpxz.reshape(S, -1), None if extra is None else extra.reshape(S, -1))
-        dparams = None
-        if need_grad:
-            dparams = F._ModlFn.backward(_Ctx(params, x), g_ll.reshape(lpxz.shape))[0]
+        dparams = F.modl_backward(params, x, g_image=g_ll.reshape(lpxz.shape)) if need_grad else None
     return -elbo, lpxz, dparams
-
-
-class _Ctx:
-    """Minimal stand-in for an autograd context so ``modl_iwae_step`` can call the backward kernel directly."""
-
-    def __init__(self, params, x):
-        from . import _abi
-        from .functional import _prep_x
-        p = _abi.dense_f32(params, "parameters")
-        H, W, C10 = p.shape[-3:]
-        lead = tuple(p.shape[:-3])
-        n_img = int(math.prod(lead)) if lead else 1
-        xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
-        self.saved_tensors = (p, xd)
-        self.meta = (x_dtype, _abi.RANGE_UNIT, _abi.EDGE_MDL, n_img, x_batch, H, W, C10 // 10)

@@ -34,9 +34,9 @@ class MixtureDiscretizedLogistic:
         """x in [0,1], ``[batch,h,w,3]`` or broadcastable ``[h,w,3]``; returns ``[..., h, w, 1]`` (utils/mdl.py:56-92)."""
         return F.modl_log_prob(self._parameters, x, _abi.RANGE_UNIT, _abi.EDGE_MDL).unsqueeze(-1)
 
-    def log_likelihood(self, x: torch.Tensor) -> torch.Tensor:
+    def log_likelihood(self, x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """``reduce_sum(log_prob(x), [-1,-2,-3])`` (models/loss.py:32) in one kernel, per-pixel tensor never written."""
-        return F.modl_log_likelihood(self._parameters, x, _abi.RANGE_UNIT, _abi.EDGE_MDL)
+        return F.modl_log_likelihood(self._parameters, x, _abi.RANGE_UNIT, _abi.EDGE_MDL, dtype)
 
     # ---- sampling ----------------------------------------------------------------------------------------------
     def sample(self, sample_shape=(), u_mix=None, u_log=None, generator=None, return_index=False, return_quantised=False):

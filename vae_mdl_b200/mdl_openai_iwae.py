@@ -36,9 +36,9 @@ class MixtureDiscretizedLogisticOpenaiIWAE:
         self._check_x(x)
         return F.modl_log_prob(self.logits, x, _abi.RANGE_UNIT, _abi.EDGE_OPENAI).unsqueeze(-1)
 
-    def log_likelihood(self, x):
+    def log_likelihood(self, x, dtype=torch.float32):
         self._check_x(x)
-        return F.modl_log_likelihood(self.logits, x, _abi.RANGE_UNIT, _abi.EDGE_OPENAI)
+        return F.modl_log_likelihood(self.logits, x, _abi.RANGE_UNIT, _abi.EDGE_OPENAI, dtype)
 
     def sample(self, sample_shape=(), u_mix=None, u_log=None, generator=None, **kw):
         """-> ``[n, S..., B, H, W, 3]`` in [0,1] (:69-99)."""
