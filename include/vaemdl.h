@@ -146,12 +146,15 @@ VAEMDL_API int vaemdl_logmeanexp_fwd_f64(const double* log_w, int S, long long B
 VAEMDL_API int vaemdl_logmeanexp_bwd(const float* log_w, const float* g_out, int S, long long B, float* dlog_w, void* stream);
 VAEMDL_API int vaemdl_logmeanexp_bwd_f64(const double* log_w, const float* g_out, int S, long long B, float* dlog_w, void* stream);
 
-/* Fused IWAE tail: log_w = ll + (extra ? extra : 0); lme_b = logmeanexp_s; elbo = mean_b lme_b;
- * g_ll[s,b] = d(-elbo)/d ll[s,b] = -softmax_s(log_w)[s,b] / B.       (models/loss.py:34-37)
+/* Fused IWAE tail: log_w = ll + (extra ? extra : 0); lme_b = logmeanexp_s; elbo = sum_b lme_b / B_total;
+ * g_ll[s,b] = d(-elbo)/d ll[s,b] = -softmax_s(log_w)[s,b] / B_total.       (models/loss.py:34-37)
+ * B_total: the batch size the mean is taken over; 0 means B.  A rank holding a shard of B images of a batch of
+ * B_total passes both, and the per-rank elbo values then simply add up to the global one.
  * ll [S,B] float32 or ll_f64 [S,B] float64 (exactly one may be NULL; ll_f64 wins when both are given);
  * extra [S,B] nullable (= beta*(lpz-lqzx)); outputs nullable: log_w [S,B], lme_b [B], elbo [1], g_ll [S,B].
  * Fixed summation order (bitwise reproducible). */
 VAEMDL_API int vaemdl_iwae_tail(const float* ll, const double* ll_f64, const float* extra, int S, long long B,
+                     long long B_total,
                      float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
 
 /* ------------------------------------------------------------------------ *

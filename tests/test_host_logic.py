@@ -1,0 +1,101 @@
+"""CPU tests of the host-side logic: tfd sample-shape semantics, the un-split [..,6] layout detection, sharding
+helpers, and the N>1 path on a world_size-2 gloo group."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as tmp
+
+import oracle as O
+from vae_mdl_b200 import dist as vdist
+from vae_mdl_b200._noise import sample_shape_to_n, uniform_noise
+
+
+def test_sample_shape_semantics():
+    assert sample_shape_to_n(()) == (1, True)      # tfd: sample() -> _sample_n(1), leading dim dropped
+    assert sample_shape_to_n([]) == (1, True)
+    assert sample_shape_to_n(7) == (7, False)
+    assert sample_shape_to_n([3]) == (3, False)
+    with pytest.raises(ValueError):
+        sample_shape_to_n((2, 3))
+
+
+def test_uniform_noise_range():
+    u = uniform_noise((10000,), "cpu", torch.Generator().manual_seed(0))
+    assert u.min().item() >= 1e-5 and u.max().item() <= 1 - 1e-5
+
+
+def test_unsplit_layout_detection_needs_no_copy():
+    from vae_mdl_b200.functional import _dl_layout
+    both = torch.zeros(2, 3, 4, 4, 6)
+    loc, ls = torch.split(both, 3, dim=-1)   # models/model03.py:91
+    l2, s2, C, ld = _dl_layout(loc, ls)
+    assert (C, ld) == (3, 6) and l2.data_ptr() == both.data_ptr() and s2.data_ptr() == both.data_ptr() + 12
+    mu, lstd = torch.chunk(both, 2, dim=-1)
+    assert _dl_layout(mu, lstd)[2:] == (3, 6)
+
+
+def test_shard_bounds_cover_everything_once():
+    for n in [0, 1, 7, 64, 26032]:
+        for world in [1, 2, 3, 8]:
+            seen = []
+            for r in range(world):
+                lo, hi = vdist.shard_bounds(n, r, world)
+                seen += list(range(lo, hi))
+                assert hi - lo in (n // world, n // world + 1)
+            assert seen == list(range(n))
+            rr = sorted(i for r in range(world) for i in vdist.round_robin(n, r, world))
+            assert rr == list(range(n))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_images, S, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        table = torch.randn(n_images, S, generator=g, dtype=torch.float64) * 3  # log-weights of every (image, sample)
+
+        def ll_chunk(i, s_lo, s_hi, out):
+            out.copy_(table[i, s_lo:s_hi])
+
+        ev = vdist.IwaeEvaluator(S, s_chunk=4, rank=rank, world=world, device="cpu")
+        mean, llh = ev.run(n_images, ll_chunk, lambda lw: O.logmeanexp(lw, 0))
+        want = O.logmeanexp(table.t(), 0).float()
+        assert torch.allclose(llh, want, atol=1e-6), (llh, want)
+        assert abs(mean.item() - want.mean().item()) < 1e-6
+
+        # batch-sharded step: per-rank additive shares of the loss sum to the unsharded loss
+        B = 5
+        log_w = torch.randn(S, B, generator=g, dtype=torch.float64)
+        lo, hi = vdist.shard_bounds(B, rank, world)
+
+        def fake_step(params, x, extra, need_grad, b_total):
+            lme = O.logmeanexp(extra, 0)
+            return (-(lme.sum() / b_total)).reshape(1), extra, None
+
+        loss, _, _ = vdist.sharded_modl_iwae_step(fake_step, None, None, log_w[:, lo:hi], B)
+        want_loss = -O.logmeanexp(log_w, 0).mean()
+        assert abs(loss.item() - want_loss.item()) < 1e-12
+        torch.save(llh, os.path.join(out_dir, f"llh{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [7, 8])
+def test_sharded_evaluation_world_size_2_gloo(tmp_path, n_images):
+    port = _free_port()
+    tmp.spawn(_worker, args=(2, port, n_images, 10, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(os.path.join(tmp_path, "llh0.pt"))
+    b = torch.load(os.path.join(tmp_path, "llh1.pt"))
+    assert torch.equal(a, b) and a.numel() == n_images

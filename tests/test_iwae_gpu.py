@@ -1,0 +1,156 @@
+"""GPU parity tests of logmeanexp / the IWAE tail / the loss functions (utils/utils.py:9-11, models/loss.py, model06)."""
+import math
+
+import pytest
+import torch
+import torch.distributions as td
+
+import oracle as O
+from util import GRAD_RTOL, LL_RTOL, assert_grad_close, canonical, relnorm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def V(built_lib):
+    import vae_mdl_b200
+    return vae_mdl_b200
+
+
+@pytest.mark.parametrize("shape,axis", [((5, 64), 0), ((5000, 1), 0), ((16, 256), 0), ((7, 3, 5), 1), ((4, 6), -1), ((1, 9), 0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_logmeanexp_fwd_bwd(V, shape, axis, dtype):
+    g = torch.Generator().manual_seed(sum(shape))
+    lw = torch.randn(*shape, generator=g) * 6 - 2e4   # realistic magnitude: per-image log-weights ~ -2e4
+    lw64 = lw.double().requires_grad_(True)
+    w = torch.randn(O.logmeanexp(lw64, axis).shape, generator=g)
+    out64 = O.logmeanexp(lw64, axis)
+    (out64 * w.double()).sum().backward()
+    lwd = lw.to(DEV).to(dtype).requires_grad_(True)
+    out = V.logmeanexp(lwd, axis)
+    assert out.shape == out64.shape
+    assert ((out.detach().cpu().double() - out64.detach()).abs() / out64.detach().abs()).max().item() < 2e-7
+    (out * w.to(DEV)).sum().backward()
+    assert relnorm(lwd.grad, lw64.grad) < 1e-5
+
+
+def test_iwae_tail_matches_oracle(V):
+    from vae_mdl_b200 import functional as F
+    g = torch.Generator().manual_seed(2)
+    S, B = 5, 64
+    ll = (torch.randn(S, B, generator=g, dtype=torch.float64) * 3 - 2e4)
+    extra = torch.randn(S, B, generator=g)
+    ll64 = ll.clone().requires_grad_(True)
+    loss64, met = O.iwae_loss(ll64.reshape(S, B, 1, 1, 1), extra.double(), torch.zeros(S, B, dtype=torch.float64), (B, 32, 32, 3))
+    loss64.backward()
+    log_w, lme_b, elbo, g_ll = F.iwae_tail(ll.to(DEV), extra.to(DEV))
+    assert abs(-elbo.item() - loss64.item()) <= 1e-6 * abs(loss64.item())
+    assert relnorm(g_ll, ll64.grad) < 1e-5
+    assert relnorm(log_w, (ll + extra.double())) < 1e-6
+    # float32 input: same API, float32-limited accuracy
+    _, _, elbo32, g32 = F.iwae_tail(ll.float().to(DEV), extra.to(DEV))
+    assert abs(-elbo32.item() - loss64.item()) <= 1e-6 * abs(loss64.item())
+    # sharded normaliser: two half-batches with b_total = B add up to the whole
+    _, _, e0, g0 = F.iwae_tail(ll[:, :40].to(DEV), extra[:, :40].to(DEV), b_total=B)
+    _, _, e1, g1 = F.iwae_tail(ll[:, 40:].to(DEV), extra[:, 40:].to(DEV), b_total=B)
+    assert abs((e0 + e1).item() - elbo.item()) <= 1e-6 * abs(elbo.item())
+    assert relnorm(torch.cat([g0, g1], 1), ll64.grad) < 1e-5
+
+
+def _setup_model05_like(g, S, B, H, W, M, n_latent=20):
+    params = torch.randn(S, B, H, W, 10 * M, generator=g)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    q_loc = torch.randn(B, n_latent, generator=g)
+    q_scale = torch.rand(B, n_latent, generator=g) + 0.5
+    z = q_loc + q_scale * torch.randn(S, B, n_latent, generator=g)
+    return params, x_u8, q_loc, q_scale, z
+
+
+def test_iwae_loss_drop_in(V):
+    """models/loss.py:26-55 with torch.distributions.Normal for pz / qzx and our MoDL class for pxz (model05)."""
+    g = torch.Generator().manual_seed(4)
+    S, B, H, W, M = 5, 6, 8, 8, 5
+    params, x_u8, q_loc, q_scale, z = _setup_model05_like(g, S, B, H, W, M)
+    # oracle, float64
+    p64 = params.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    lpz = td.Normal(0.0, 1.0).log_prob(z.double()).sum(-1)
+    lqzx = td.Normal(q_loc.double(), q_scale.double()).log_prob(z.double()).sum(-1)
+    loss64, met64 = O.iwae_loss(O.modl_log_prob(p64, x64), lpz, lqzx, x64.shape, beta=0.9)
+    loss64.backward()
+    # product
+    pd = params.to(DEV).requires_grad_(True)
+    x01 = O.normalize_u8(x_u8).to(DEV)
+    zd = z.to(DEV)
+    pz = td.Normal(torch.zeros_like(zd), torch.ones_like(zd))
+    pz.axes = [-1]
+    qzx = td.Normal(q_loc.to(DEV), q_scale.to(DEV))
+    qzx.axes = [-1]
+    pxz = V.MixtureDiscretizedLogistic(pd)
+    loss, met = V.iwae_loss(x01, zd, pz, qzx, pxz, beta=0.9)
+    assert set(met) == {"iwae_elbo", "bpd", "lpxz", "lqzx", "lpz", "kl"}
+    assert met["lpxz"].shape == (S, B) and met["lpxz"].dtype == torch.float32
+    assert abs(loss.item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
+    assert abs(met["bpd"].item() - met64["bpd"].item()) <= LL_RTOL * abs(met64["bpd"].item())
+    assert relnorm(met["kl"], met64["kl"]) < 1e-5
+    loss.backward()
+    assert_grad_close(pd.grad, p64.grad, M)
+    # the generic route (axes that are not the image axes -> per-pixel log_prob + torch reduce) gives the same loss
+    pxz2 = V.MixtureDiscretizedLogisticOpenaiIWAE(params.to(DEV))
+    loss2, _ = V.iwae_loss(x01, zd, pz, qzx, pxz2, beta=0.9)
+    assert abs(loss2.item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
+
+
+def test_elbo_loss_and_model06_loss_fn(V):
+    g = torch.Generator().manual_seed(5)
+    S, B, H, W = 5, 4, 8, 8
+    both = torch.randn(S, B, H, W, 6, generator=g)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    x01 = O.normalize_u8(x_u8)
+    z1 = torch.randn(S, B, 8, generator=g)
+    z2 = torch.randn(S, B, 4, generator=g)
+    mk = lambda t: t.to(DEV)  # noqa: E731
+    # ---- elbo_loss with the plain DL head (model03 shape)
+    lp64 = O.dlogistic_log_prob(x01.double(), both[..., :3].double(), both[..., 3:].double(), 0.0, 1.0, 256.0)
+    lpz = td.Normal(0.0, 1.0).log_prob(z1.double()).sum(-1)
+    lq = td.Normal(0.1, 1.3).log_prob(z1.double()).sum(-1)
+    want, _ = O.elbo_loss(lp64, lpz, lq)
+    bd = mk(both)
+    mu, lstd = torch.split(bd, 3, dim=-1)
+    pxz = V.DiscretizedLogistic(mu, lstd, low=0.0, high=1.0, levels=256.0)
+    pxz.axes = [-1, -2, -3]                                  # models/model03.py:143
+    pz = td.Normal(torch.zeros_like(mk(z1)), torch.ones_like(mk(z1)))
+    pz.axes = [-1]
+    qz = td.Normal(torch.full_like(mk(z1), 0.1), torch.full_like(mk(z1), 1.3))
+    qz.axes = [-1]
+    got, met = V.elbo_loss(mk(x01), mk(z1), pz, qz, pxz)
+    assert abs(got.item() - want.item()) <= LL_RTOL * abs(want.item())
+    # ---- model06 loss_fn (models/model06.py:38-72)
+    lpz2 = td.Normal(0.0, 1.0).log_prob(z2.double()).sum(-1)
+    lqz2z1 = td.Normal(0.2, 0.9).log_prob(z2.double()).sum(-1)
+    lpz1z2 = td.Normal(-0.1, 1.1).log_prob(z1.double()).sum(-1)
+    lqz1x = lq
+    want6, met6 = O.model06_loss(lp64, lpz2, lqz2z1, lpz1z2, lqz1x, x01.shape)
+    DT = V.DistributionTuple
+    pz_top = td.Normal(torch.zeros_like(mk(z2)), torch.ones_like(mk(z2)))
+    pz_top.axes = [-1]
+    got6, m6 = V.loss_fn(
+        mk(x01), pz_top,
+        DT(qz, mk(z1), (-1,)),
+        DT(td.Normal(torch.full_like(mk(z2), 0.2), torch.full_like(mk(z2), 0.9)), mk(z2), (-1,)),
+        DT(td.Normal(torch.full_like(mk(z1), -0.1), torch.full_like(mk(z1), 1.1)), None, (-1,)),
+        DT(pxz, None, (-1, -2, -3)))
+    assert abs(got6.item() - want6.item()) <= LL_RTOL * abs(want6.item())
+    assert abs(m6["bpd"].item() - met6["bpd"].item()) <= LL_RTOL * abs(met6["bpd"].item())
+    assert set(m6) == set(met6)
+
+
+def test_log_sum_exp_helpers(V):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 4, 4, 10, generator=g) * 5
+    a = V.log_sum_exp(x.to(DEV)).cpu()
+    assert torch.allclose(a, O.log_sum_exp(x), atol=1e-5)
+    b = V.log_prob_from_logits(x.to(DEV)).cpu()
+    assert torch.allclose(b, O.log_prob_from_logits(x), atol=1e-5)
+    assert V.int_shape(x) == [3, 4, 4, 10]

@@ -43,8 +43,8 @@ PROTOTYPES = {
     "vaemdl_logmeanexp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_logmeanexp_fwd_f64": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_logmeanexp_bwd_f64": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
-    "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p]),
+    "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "vaemdl_modl_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_sample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_longlong, c_float, c_float,

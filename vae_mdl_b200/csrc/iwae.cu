@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(kLmeThreads)
         expf(static_cast<float>(log_w[static_cast<long long>(s) * B + b] - mx)) * scale;
 }
 
-// elbo = mean_b lme_b, single block, fixed order
-__global__ void __launch_bounds__(kLmeThreads) mean_kernel(const float* __restrict__ v, long long B, float* __restrict__ out) {
+// elbo = sum_b lme_b / b_norm, single block, fixed order
+__global__ void __launch_bounds__(kLmeThreads)
+    mean_kernel(const float* __restrict__ v, long long B, float b_norm, float* __restrict__ out) {
   __shared__ float red[kLmeThreads];
   float acc = 0.0f;
   for (long long i = threadIdx.x; i < B; i += kLmeThreads) acc += v[i];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kLmeThreads) mean_kernel(const float* __restri
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = red[0] / static_cast<float>(B);  // models/loss.py:37
+  if (threadIdx.x == 0) out[0] = red[0] / b_norm;  // models/loss.py:37
 }
 
 static void lme_shape(long long B, int& BX, int& SY) {
@@ -162,14 +163,15 @@ int iwae_tail_norm(const float* ll, const double* ll64, const float* extra, int 
 }  // namespace vaemdl
 
 extern "C" int vaemdl_iwae_tail(const float* ll, const double* ll_f64, const float* extra, int S, long long B,
-                                float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream) {
-  if ((!ll && !ll_f64) || S <= 0 || B <= 0) return VAEMDL_EINVAL;
+                                long long B_total, float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream) {
+  if ((!ll && !ll_f64) || S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
+  if (B_total == 0) B_total = B;
   if (elbo && !lme_b) return VAEMDL_EINVAL;  // the mean is taken over the lme_b buffer
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = iwae_tail_norm(ll, ll_f64, extra, S, B, static_cast<float>(B), log_w, lme_b, g_ll, st);
+  int rc = iwae_tail_norm(ll, ll_f64, extra, S, B, static_cast<float>(B_total), log_w, lme_b, g_ll, st);
   if (rc) return rc;
   if (elbo) {
-    mean_kernel<<<1, kLmeThreads, 0, st>>>(lme_b, B, elbo);
+    mean_kernel<<<1, kLmeThreads, 0, st>>>(lme_b, B, static_cast<float>(B_total), elbo);
     rc = cuda_rc(cudaGetLastError());
   }
   return rc;

@@ -1,0 +1,113 @@
+"""Data-parallel sharding of the observation-model path over the GPUs of one box (one process per GPU).
+
+The path shards without any data-path collective: every (importance-sample, image) pair is independent
+until the log-mean-exp over samples, and test images are independent of each other.
+
+* training shapes: split the BATCH across ranks -- every rank holds all S samples of its images, so the log-mean-exp
+  and its gradient are rank-local; the only exchange is one scalar all-reduce of the partial ELBO sums.
+* 5000-sample evaluation (models/model05.py:168-176): images round-robin over ranks, S streamed in chunks into a
+  per-image float64 buffer, ONE all-gather of the per-image results at the very end -- no per-image host sync.
+
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is only the plumbing for those few floats.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+__all__ = ["init_from_env", "shard_bounds", "round_robin", "gather_round_robin", "allreduce_sum", "IwaeEvaluator",
+           "sharded_modl_iwae_step"]
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK (torchrun); initialises the process group when WORLD_SIZE > 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local_rank
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``range(n)``: the first ``n % world`` ranks get one extra element."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def round_robin(n: int, rank: int, world: int) -> range:
+    """Image ``i`` belongs to rank ``i % world``."""
+    return range(rank, n, world)
+
+
+def gather_round_robin(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of ``round_robin``: every rank passes its ``[len(round_robin(n_total, rank, world))]`` results and gets
+    the full ``[n_total]`` vector in image order.  One all-gather of ``ceil(n_total/world)`` elements per rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    padded = torch.zeros(per, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    out = torch.empty(world * per, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    # out[r*per + j] is image j*world + r
+    return out.reshape(world, per).t().reshape(-1)[:n_total].contiguous()
+
+
+def allreduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class IwaeEvaluator:
+    """Sharded version of ``Model05.test(n_samples)`` (models/model05.py:168-176).
+
+    ``ll_chunk_fn(image_index, s_lo, s_hi, out)`` must write the per-sample log-weights ``log_w[s_lo:s_hi]`` of image
+    ``image_index`` into ``out`` (a float64 view of length ``s_hi - s_lo`` on ``device``) -- typically
+    ``functional.modl_log_likelihood(decoder(z[s_lo:s_hi]), x[image_index], dtype=float64) + lpz - lqzx``.
+    ``lme_fn(log_w [S, n]) -> [n]`` is the log-mean-exp over axis 0 (``functional.logmeanexp`` on the GPU).
+    Nothing is synchronised with the host until ``run`` returns.
+    """
+
+    def __init__(self, n_samples: int, s_chunk: int, rank: int = 0, world: int = 1, device="cuda", group=None):
+        self.S, self.s_chunk, self.rank, self.world = int(n_samples), int(s_chunk), rank, world
+        self.device, self.group = device, group
+
+    def run(self, n_images: int, ll_chunk_fn: Callable, lme_fn: Callable):
+        mine = list(round_robin(n_images, self.rank, self.world))
+        # [n_local, S]: each image's S log-weights are contiguous, so a chunk of samples is a contiguous slice
+        log_w = torch.empty((max(1, len(mine)), self.S), dtype=torch.float64, device=self.device)
+        for j, i in enumerate(mine):
+            row = log_w[j]
+            for s_lo in range(0, self.S, self.s_chunk):
+                s_hi = min(self.S, s_lo + self.s_chunk)
+                ll_chunk_fn(i, s_lo, s_hi, row[s_lo:s_hi])
+        if mine:
+            llh_local = lme_fn(log_w[: len(mine)].t().contiguous())
+        else:
+            llh_local = torch.empty(0, device=self.device)
+        llh = gather_round_robin(llh_local.float(), n_images, self.group)
+        return llh.mean(), llh
+
+
+def sharded_modl_iwae_step(step_fn: Callable, params_shard, x_shard, extra_shard, b_total: int, group=None):
+    """One IWAE observation-model step with the batch split across ranks.  ``step_fn`` is
+    ``vae_mdl_b200.modl_iwae_step``; each rank gets its additive share of the loss, one scalar all-reduce makes it the
+    global loss.  Gradients stay rank-local (they belong to the rank's own decoder activations)."""
+    loss, lpxz, dparams = step_fn(params_shard, x_shard, extra_shard, True, b_total)
+    loss = allreduce_sum(loss.clone(), group)
+    return loss, lpxz, dparams

@@ -274,9 +274,10 @@ def logmeanexp(log_w: torch.Tensor, axis: int) -> torch.Tensor:
     return _LmeFn.apply(flat).reshape(rest)
 
 
-def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None):
+def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: int = 0):
     """Fused IWAE tail on ``ll [S,B]`` (float32 or float64) + ``extra [S,B]``: returns ``(log_w, lme_b, elbo, g_ll)``
-    (all float32) where ``g_ll = d(-elbo)/d ll`` (models/loss.py:34-37).  Not recorded by autograd."""
+    (all float32) where ``g_ll = d(-elbo)/d ll`` (models/loss.py:34-37).  ``b_total``: size of the whole batch when
+    ``ll`` holds one rank's shard of it (0 = this is the whole batch).  Not recorded by autograd."""
     ll = _dense_f32_or_f64(ll, "ll")
     S, B = ll.shape
     ex = dense_f32(extra, "extra") if extra is not None else None
@@ -286,7 +287,7 @@ def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None):
     g_ll = torch.empty((S, B), device=ll.device, dtype=torch.float32)
     is64 = ll.dtype == torch.float64
     with torch.cuda.device(ll.device):
-        check(lib().vaemdl_iwae_tail(None if is64 else ptr(ll), ptr(ll) if is64 else None, ptr(ex), S, B, ptr(log_w),
+        check(lib().vaemdl_iwae_tail(None if is64 else ptr(ll), ptr(ll) if is64 else None, ptr(ex), S, B, int(b_total), ptr(log_w),
                                      ptr(lme_b), ptr(elbo), ptr(g_ll), stream_ptr(ll.device)), "vaemdl_iwae_tail")
     return log_w, lme_b, elbo, g_ll
 

@@ -87,16 +87,19 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
                         "lpz2": lpz2, "lpz1z2": lpz1z2, "kl1": kl1, "kl2": kl2}
 
 
-def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True):
+def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True,
+                   b_total: int = 0):
     """The whole observation-model side of one IWAE step in 3 (+2 tiny) kernel launches, no autograd graph:
     per-image MoDL log-likelihood (float64 sums) -> fused IWAE tail (log-mean-exp, elbo, softmax weights) -> MoDL gradient.
 
     ``params [S,B,H,W,10M]``, ``x [B,H,W,3]`` (uint8 or float in [0,1]), ``extra = beta*(lpz-lqzx) [S,B]`` or None.
+    ``b_total``: whole-batch size when ``params`` is one rank's batch shard (the returned loss is then this rank's
+    additive share of the global loss).
     Returns ``(loss=-elbo [1], lpxz [S,B] float64, dparams or None)`` -- the numbers ``iwae_loss`` + ``backward`` give.
     """
     with torch.no_grad():
         lpxz = F.modl_log_likelihood(params, x, dtype=torch.float64)
         S = lpxz.shape[0]
-        _, _, elbo, g_ll = F.iwae_tail(lpxz.reshape(S, -1), None if extra is None else extra.reshape(S, -1))
+        _, _, elbo, g_ll = F.iwae_tail(lpxz.reshape(S, -1), None if extra is None else extra.reshape(S, -1), b_total)
         dparams = F.modl_backward(params, x, g_image=g_ll.reshape(lpxz.shape)) if need_grad else None
     return -elbo, lpxz, dparams
