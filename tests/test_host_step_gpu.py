@@ -26,8 +26,10 @@ def test_host_step_matches_device_step_and_oracle(built_lib, S, B, H, W, M, chun
                                               ll.data_ptr(), lme.data_ptr(), elbo.data_ptr(), chunk)
     assert rc == 0
     loss_d, lpxz_d, dp_d = V.modl_iwae_step(params.to(DEV), x_u8.to(DEV), extra.to(DEV))
-    assert torch.equal(ll, lpxz_d.float().cpu())
-    assert torch.equal(dp, dp_d.cpu())
+    # not bitwise: which of the two (equally accurate) exp(-h) evaluations a pixel gets is a per-warp-tile decision,
+    # and chunking the batch changes which pixels share a tile
+    assert torch.allclose(ll, lpxz_d.float().cpu(), rtol=1e-6, atol=0)
+    assert torch.allclose(dp, dp_d.cpu(), rtol=1e-4, atol=1e-7)
     assert abs(-elbo.item() - loss_d.item()) <= 1e-6 * abs(loss_d.item())
     # and against the oracle
     p64 = params.double().requires_grad_(True)

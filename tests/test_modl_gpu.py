@@ -159,13 +159,15 @@ def test_log_domain_fallback_extreme_tail(F):
 def test_logscale_clamp_masks_gradient(F):
     M = 10
     params, x_u8, g = canonical(12, 1, 2, 4, 4, M)
-    params[..., 2 * M: 3 * M] = -9.0          # sR below the clamp for every mixture
-    params[0, 0, 0, 0, 5 * M] = -7.0          # sG exactly on the clamp: gradient flows (tf.maximum tie rule)
+    params[..., 2 * M + 3] = -9.0                 # sR of mixture 3 below the clamp everywhere
+    params[..., 8 * M + 6] = -7.5                 # sB of mixture 6 below the clamp everywhere
+    params[0, 0, 0, 0, 5 * M: 6 * M] = -7.0       # sG exactly on the clamp: gradient flows (tf.maximum tie rule)
     g_image = torch.ones(1, 2)
     _, ll64, grad64 = oracle_ll_and_grad(params, x_u8, g_image)
     dp = F.modl_backward(params.to(DEV), x_u8.to(DEV), g_image=g_image.to(DEV)).cpu()
-    assert (dp[..., 2 * M: 3 * M] == 0).all()
-    assert dp[0, 0, 0, 0, 5 * M].item() != 0.0
+    assert (dp[..., 2 * M + 3] == 0).all() and (dp[..., 8 * M + 6] == 0).all()
+    assert (grad64[0, 0, 0, 0, 5 * M: 6 * M] != 0).any()
+    assert (dp[0, 0, 0, 0, 5 * M: 6 * M] != 0).any()
     assert_grad_close(dp, grad64, M)
 
 
@@ -202,8 +204,9 @@ def test_config1_full_size_properties(F, M, B):
     assert torch.equal(ll, F.modl_log_likelihood(params, x_u8))
     dp = F.modl_backward(params, x_u8, g_image=g_image)
     assert torch.equal(dp, F.modl_backward(params, x_u8, g_image=g_image))
-    # (c) the gradient is linear in the upstream weights (exactly, for a power-of-two factor)
-    assert torch.equal(F.modl_backward(params, x_u8, g_image=2 * g_image), 2 * dp)
+    # (c) the gradient is linear in the upstream weights: exact for a power-of-two factor, up to values that
+    #     flush to zero (the kernels run with denormals flushed)
+    assert (F.modl_backward(params, x_u8, g_image=2 * g_image) - 2 * dp).abs().max().item() < 1e-36
     # (d) mixture-logit gradients of a pixel sum to zero (responsibilities and softmax both sum to one)
     s = dp[..., :M].sum(-1)
     assert s.abs().max().item() < 1e-5 * g_image.abs().max().item()

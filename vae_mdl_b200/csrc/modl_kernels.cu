@@ -12,9 +12,13 @@
 //
 // Work split.  M = MC * LPP: LPP lanes share a pixel, each owning MC mixtures (M=5: 5x1, M=10: 10x1, M=20: 10x2,
 // M=30: 10x3).  Any other M runs on a plain one-thread-per-pixel kernel (correct, not tuned).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "modl_math.cuh"
+#include "packed.cuh"
 
 namespace vaemdl {
 
@@ -142,61 +146,7 @@ __device__ __forceinline__ float lg2_split(float v) {
   return static_cast<float>(e) + lg2a(m);
 }
 
-// ---- chunk <-> shared memory -------------------------------------------------------------------------------------
-// v[j*MC + i] = row[j*M + sub*MC + i],  j = 0..9 (0: logits, 1..9: muR sR kR muG sG kG muB sB kB)
-template <int MC, int LPP>
-__device__ __forceinline__ void chunk_load(float (&v)[10 * MC], const float* __restrict__ rowp, int sub) {
-  constexpr int M = MC * LPP;
-  if constexpr (LPP == 1) {
-    if constexpr ((10 * M) % 4 == 0) {
-#pragma unroll
-      for (int q = 0; q < (10 * M) / 4; ++q) {
-        const float4 t = reinterpret_cast<const float4*>(rowp)[q];
-        v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < (10 * M) / 2; ++q) {
-        const float2 t = reinterpret_cast<const float2*>(rowp)[q];
-        v[2 * q] = t.x, v[2 * q + 1] = t.y;
-      }
-    }
-  } else {
-    static_assert(MC % 2 == 0, "multi-lane chunks use 64-bit shared accesses");
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      const float2* src = reinterpret_cast<const float2*>(rowp + j * M + sub * MC);
-#pragma unroll
-      for (int q = 0; q < MC / 2; ++q) {
-        const float2 t = src[q];
-        v[j * MC + 2 * q] = t.x, v[j * MC + 2 * q + 1] = t.y;
-      }
-    }
-  }
-}
-template <int MC, int LPP>
-__device__ __forceinline__ void chunk_store(const float (&v)[10 * MC], float* __restrict__ rowp, int sub) {
-  constexpr int M = MC * LPP;
-  if constexpr (LPP == 1) {
-    if constexpr ((10 * M) % 4 == 0) {
-#pragma unroll
-      for (int q = 0; q < (10 * M) / 4; ++q)
-        reinterpret_cast<float4*>(rowp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < (10 * M) / 2; ++q) reinterpret_cast<float2*>(rowp)[q] = make_float2(v[2 * q], v[2 * q + 1]);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      float2* dst = reinterpret_cast<float2*>(rowp + j * M + sub * MC);
-#pragma unroll
-      for (int q = 0; q < MC / 2; ++q) dst[q] = make_float2(v[j * MC + 2 * q], v[j * MC + 2 * q + 1]);
-    }
-  }
-}
-
-// ---- one mixture component ------------------------------------------------------------------------------------------
+// ---- one mixture component, scalar (any-M kernel) ------------------------------------------------------------------------------------------
 // forward: returns P = prod_c f_c (linear domain)
 __device__ __forceinline__ float mix_fwd(const Pixel& px, const float mu[3], const float s[3], const float kap[3]) {
   float k0, k1, k2;
@@ -246,7 +196,147 @@ __device__ __forceinline__ float mix_bwd(const Pixel& px, const float mu[3], con
   return (f[0].num * f[1].num * f[2].num) * R;
 }
 
+// ---- packed (two mixture components per instruction) sub-pixel arithmetic --------------------------------------------
+// Same formulas as subpix<> in modl_math.cuh; `lo` half = component m, `hi` half = component m+1.
+// NARROW is a warp-uniform property of the pair (some lane has a log-scale below kLsNarrow, i.e. h >= kHSmall): only
+// then are exp(-h) and h*coth(h) evaluated on the MUFU pipe, otherwise short polynomials on the packed FMA pipe.
+constexpr float kLsNarrow = -3.6441f;  // -log(kHSmall * 255) rounded towards 0: ls <= this  <=>  h = exp(-ls)/255 >= kHSmall (conservatively)
+
+struct Sub2 {
+  f2 num, den;               // f = num / den
+  f2 nm, nh, c0, dir;        // backward numerators (see SubB)
+  f2 inv, mid;
+};
+
+template <bool NARROW, bool BWD>
+__device__ __forceinline__ void subpix2(float x, bool left, bool right, f2 loc, f2 s_raw, Sub2& o) {
+  const f2 ls = max_2(s_raw, -7.0f);                                  // utils/mdl.py:109
+  const f2 inv = ex2_2(ls * (-kLog2e));
+  const f2 mid = inv * (sp(x) - loc);
+  const f2 A = ex2_negabs_2(mid * kLog2e);
+  const f2 h = inv * kDx;
+  f2 q = fma2(h, -1.0f / 720.0f, 1.0f / 120.0f);
+  q = fma2(h, q, -1.0f / 24.0f);
+  q = fma2(h, q, 1.0f / 6.0f);
+  q = fma2(h, q, -0.5f);
+  q = fma2(h, q, 1.0f);
+  f2 omG = h * q;
+  f2 G = sp(1.0f) - omG;
+  bool nl = false, nh_ = false;
+  if constexpr (NARROW) {
+    const f2 Ge = ex2_2(h * (-kLog2e));
+    const f2 omGe = sp(1.0f) - Ge;
+    nl = lo(h) >= kHSmall;
+    nh_ = hi(h) >= kHSmall;
+    G = sel_2(nl, nh_, Ge, G);
+    omG = sel_2(nl, nh_, omGe, omG);
+  }
+  const f2 AG = A * G;
+  const f2 ApG = A + G;
+  const f2 opAG = AG + 1.0f;
+  const f2 opA = A + 1.0f;
+  const f2 opG = G + 1.0f;
+  const f2 rest_n = omG * opG;
+  const f2 num_n = A * rest_n;
+  const f2 den_n = ApG * opAG;
+  const f2 thr = den_n * 1e-5f;
+  const bool il = lo(num_n) > lo(thr), ih = hi(num_n) > hi(thr);    // sigmoid(p)-sigmoid(q) > 1e-5 (utils/mdl.py:193)
+  const f2 num_l = (A * inv) * kWidth;
+  const f2 den_l = opA * opA;
+  f2 num = sel_2(il, ih, num_n, num_l);
+  f2 den = sel_2(il, ih, den_n, den_l);
+  const bool edge = left || right;
+  const bool ool = (left == (lo(mid) >= 0.0f)), ooh = (left == (hi(mid) >= 0.0f));  // 1/(1+AG) vs A/(A+G)
+  if (edge) {
+    num = sel_2(ool, ooh, sp(1.0f), A);
+    den = sel_2(ool, ooh, opAG, ApG);
+  }
+  o.num = num;
+  o.den = den;
+  if constexpr (BWD) {
+    const f2 omA2 = (sp(1.0f) - A) * opA;
+    f2 nm = neg_sign_of_2(sel_2(il, ih, G * omA2, omA2), mid);
+    f2 nh = sel_2(il, ih, (h * -1.0f) * num_n, sp(0.0f));
+    const f2 h2 = h * h;
+    f2 hc = fma2(h2, 2.0f / 945.0f, -1.0f / 45.0f);
+    hc = fma2(h2, hc, 1.0f / 3.0f);
+    hc = fma2(h2, hc, 1.0f);
+    if constexpr (NARROW) {
+      const f2 e = h * fma2(G, G, 1.0f) * rcp_2(rest_n);
+      hc = sel_2(nl, nh_, e, hc);
+    }
+    f2 c0 = sel_2(il, ih, hc, sp(0.0f));
+    f2 dir = sel_2(il, ih, sp(0.0f), sp(-1.0f));
+    if (edge) {
+      const f2 t = sel_2(ool, ooh, AG, G);
+      nm = left ? t : t * -1.0f;
+      nh = h * t;
+      c0 = sp(0.0f);
+      dir = sp(0.0f);
+    }
+    o.nm = nm;
+    o.nh = nh;
+    o.c0 = c0;
+    o.dir = dir;
+    o.inv = inv;
+    o.mid = mid;
+  }
+}
+
+// tanh of three coefficient pairs: 6 ex2 + 2 rcp
+__device__ __forceinline__ void tanh3_2(const f2 kp[3], f2 k[3]) {
+  const float c = 2.0f * kLog2e;
+  const f2 E0 = min_2(ex2_2(kp[0] * c), 1073741824.0f);
+  const f2 E1 = min_2(ex2_2(kp[1] * c), 1073741824.0f);
+  const f2 E2 = min_2(ex2_2(kp[2] * c), 1073741824.0f);
+  const f2 d0 = E0 + 1.0f, d1 = E1 + 1.0f, d2 = E2 + 1.0f;
+  const f2 d01 = d0 * d1;
+  const f2 R = rcp_2(d01 * d2);
+  k[0] = (E0 + -1.0f) * (d1 * d2) * R;
+  k[1] = (E1 + -1.0f) * (d0 * d2) * R;
+  k[2] = (E2 + -1.0f) * d01 * R;
+}
+
+// One pair of mixture components.  Returns P = prod_c f_c (linear domain); BWD also the nine d log P / d param pairs.
+template <bool NARROW, bool BWD>
+__device__ __forceinline__ f2 pair_eval(const Pixel& px, const f2 mu[3], const f2 s[3], const f2 kp[3], f2 u[9]) {
+  f2 k[3];
+  tanh3_2(kp, k);
+  f2 loc[3];
+  loc[0] = mu[0];
+  loc[1] = fma2(k[0], px.x[0], mu[1]);                               // utils/mdl.py:140
+  loc[2] = fma2(k[2], px.x[1], fma2(k[1], px.x[0], mu[2]));          // utils/mdl.py:141-145
+  Sub2 f[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) subpix2<NARROW, BWD>(px.x[c], px.left[c], px.right[c], loc[c], s[c], f[c]);
+  const f2 d01 = f[0].den * f[1].den;
+  const f2 R = rcp_2(d01 * f[2].den);
+  const f2 P = (f[0].num * f[1].num) * (f[2].num * R);
+  if constexpr (BWD) {
+    f2 rd[3];
+    rd[0] = f[1].den * f[2].den * R;
+    rd[1] = f[0].den * f[2].den * R;
+    rd[2] = d01 * R;
+    f2 dloc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const f2 Dm = f[c].nm * rd[c];
+      dloc[c] = (f[c].inv * -1.0f) * Dm;
+      f2 dls = (f[c].dir - f[c].c0) - fma2(f[c].mid, Dm, f[c].nh * rd[c]);
+      // tf.maximum(logscale, -7): the gradient reaches logscale iff logscale >= -7
+      dls = sel_2(lo(s[c]) >= -7.0f, hi(s[c]) >= -7.0f, dls, sp(0.0f));
+      u[3 * c + 0] = dloc[c];
+      u[3 * c + 1] = dls;
+    }
+    u[2] = (dloc[1] * px.x[0]) * fma2(k[0] * -1.0f, k[0], 1.0f);
+    u[5] = (dloc[2] * px.x[0]) * fma2(k[1] * -1.0f, k[1], 1.0f);
+    u[8] = (dloc[2] * px.x[1]) * fma2(k[2] * -1.0f, k[2], 1.0f);
+  }
+  return P;
+}
+
 // ---- the tiled kernel -------------------------------------------------------------------------------------------------
+// M = MC * LPP mixtures; LPP lanes share a pixel, each owning MC consecutive components, processed two at a time.
 template <int MC, int LPP>
 struct Tile {
   static constexpr int M = MC * LPP;
@@ -254,37 +344,89 @@ struct Tile {
   static constexpr int ROWF = 10 * M;
   static constexpr int TILE_F = PPT * ROWF;
   static constexpr int TILE_B = TILE_F * 4;
+  static constexpr int AUX_F = PPT * M;  // backward: W*P per (pixel, component)
+  static constexpr int NPAIR = (MC + 1) / 2;
+  static constexpr bool ALIGNED = (M % 2 == 0) && (MC % 2 == 0);  // component pairs sit on 8-byte boundaries
   static_assert(TILE_B % 16 == 0, "bulk copies need 16-byte multiples");
 };
 
-template <int MC, int LPP, bool BWD, int STAGES>
-__global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlArgs a) {
+// a pair of consecutive floats at row[off], row[off+1]; `single`: only row[off] exists (odd MC), both halves get it
+template <bool ALIGNED>
+__device__ __forceinline__ f2 ld_pair(const float* row, int off, bool single) {
+  if constexpr (ALIGNED) {
+    const float2 t = *reinterpret_cast<const float2*>(row + off);
+    return pk(t.x, t.y);
+  } else {
+    const float a = row[off];
+    const float b = single ? a : row[off + 1];
+    return pk(a, b);
+  }
+}
+template <bool ALIGNED>
+__device__ __forceinline__ void st_pair(float* row, int off, bool single, f2 v) {
+  if constexpr (ALIGNED) {
+    *reinterpret_cast<float2*>(row + off) = make_float2(lo(v), hi(v));
+  } else {
+    row[off] = lo(v);
+    if (!single) row[off + 1] = hi(v);
+  }
+}
+
+struct PixRaw {
+  unsigned v[3];
+};
+__device__ __forceinline__ PixRaw load_pixel_raw(const ModlArgs& a, long long n, int pix) {
+  const long long xb = a.x_batch == 1 ? 0 : (n < a.x_batch ? n : n % a.x_batch);
+  const long long xo = (xb * a.HW + pix) * 3;
+  PixRaw r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    r.v[c] = a.x_u8 ? static_cast<unsigned>(static_cast<const uint8_t*>(a.x)[xo + c])
+                    : __float_as_uint(static_cast<const float*>(a.x)[xo + c]);
+  return r;
+}
+__device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r, Pixel& px) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = a.x_u8 ? __fdiv_rn(static_cast<float>(r.v[c]), 255.0f) : __uint_as_float(r.v[c]);  // utils/data.py:15-16
+    if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);                                                  // utils/mdl.py:65
+    px.x[c] = v;
+    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
+    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+  }
+}
+
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   using T = Tile<MC, LPP>;
-  constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F;
-  constexpr int SLOTS = STAGES + (BWD ? 1 : 0);  // BWD: last slot stages the gradient tile
+  constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F, NPAIR = T::NPAIR;
+  constexpr bool AL = T::ALIGNED;
+  constexpr int WARP_F = NSLOT * TILE_F + (BWD ? T::AUX_F : 0);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * SLOTS * TILE_F;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * SLOTS * T::TILE_B) + warp * STAGES;
+  float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
+  float* aux = slots + NSLOT * TILE_F;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp * NSLOT;
 
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < NSLOT; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncwarp();
 
   const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
-  const int p = (lane / LPP) < PPT ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
-  const int sub = lane % LPP;
   const bool lane_used = (lane / LPP) < PPT;
+  const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
+  const int sub = lane % LPP;
+  const int m0 = sub * MC;
 
   auto tile_rows = [&](long long t) -> int {
     const long long rem = a.n_px - t * PPT;
     return rem < PPT ? static_cast<int>(rem) : PPT;
   };
-  // bring tile t into stage slot s (bulk copy when the byte count allows it, plain loads for a ragged tail tile)
+  // bring tile t into slot s (bulk copy when the byte count allows it, plain loads for a ragged tail tile)
   auto issue = [&](long long t, int s) {
     const int rows = tile_rows(t);
     const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
@@ -302,9 +444,9 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
     }
   };
 
-  // prologue
+  // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below)
 #pragma unroll
-  for (int s = 0; s < STAGES; ++s) {
+  for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
     const long long t = gw + s * total_warps;
     if (t < a.num_tiles) issue(t, s);
   }
@@ -316,78 +458,119 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
   long long n_own = (gw * PPT + p) / a.HW;
   int pix_own = static_cast<int>((gw * PPT + p) - n_own * a.HW);
 
+  // software prefetch of the (L2-resident) pixel and upstream-gradient values one tile ahead
+  auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
+                   float& g_out) {
+    const int rows = tile_rows(t);
+    const long long n_first = __shfl_sync(kFull, n_lane, 0);
+    const int pix_first = __shfl_sync(kFull, pix_lane, 0);
+    const bool in = p < rows;  // lanes past a ragged last tile shadow the tile's first pixel
+    const long long n = in ? n_lane : n_first;
+    const int pix = in ? pix_lane : pix_first;
+    raw = load_pixel_raw(a, n, pix);
+    g_out = 0.0f;
+    if constexpr (BWD) {
+      if (a.g_image) g_out = a.g_image[n];
+      if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+    }
+    n_out = n;
+    nfirst_out = n_first;
+  };
+
+  long long n_cur = 0, nfirst_cur = 0;
+  PixRaw raw_cur{};
+  float g_cur = 0.0f;
+  if (gw < a.num_tiles) fetch(gw, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+
   long long it = 0;
   for (long long t = gw; t < a.num_tiles; t += total_warps, ++it) {
-    const int s = static_cast<int>(it % STAGES);
-    const uint32_t parity = static_cast<uint32_t>((it / STAGES) & 1);
+    const int s = static_cast<int>(it % NSLOT);
+    const uint32_t parity = static_cast<uint32_t>((it / NSLOT) & 1);
     const int rows = tile_rows(t);
     const int pp = p < rows ? p : 0;
     const bool active = lane_used && (p < rows);
     const long long i = t * PPT + pp;  // this lane's pixel-sample
-    // lanes past a ragged last tile shadow the tile's first pixel
-    const long long n_first = __shfl_sync(kFull, n_own, 0);
-    const int pix_first = __shfl_sync(kFull, pix_own, 0);
-    const long long n = p < rows ? n_own : n_first;
-    const int pix = p < rows ? pix_own : pix_first;
+    const long long n = n_cur, n_first = nfirst_cur;
+    const float g = g_cur;
+    Pixel px;
+    decode_pixel(a, raw_cur, px);
+    // advance the index and prefetch the next tile's pixel / upstream gradient
     n_own += step_n;
     pix_own += step_pix;
     if (pix_own >= a.HW) {
       pix_own -= a.HW;
       ++n_own;
     }
+    if (t + total_warps < a.num_tiles) fetch(t + total_warps, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
 
-    // the pixel itself (L2-resident, tiny) -- issued before the wait so its latency hides behind the tile copy
-    Pixel px;
-    load_pixel(a, n, pix, px);
-    float g = 0.0f;
-    if constexpr (BWD) {
-      if (a.g_image) g += a.g_image[n];
-      if (a.g_pixel) g += a.g_pixel[i];
-    }
-
+    float* slot = slots + s * TILE_F;
+    float* rowp = slot + pp * ROWF;
+    float* auxp = aux + pp * M;
     mbar_wait(&bars[s], parity);
-    float v[10 * MC];
-    chunk_load<MC, LPP>(v, slots + s * TILE_F + pp * ROWF, sub);
-    __syncwarp();
-    {
-      const long long tn = t + STAGES * total_warps;
-      if (tn < a.num_tiles) issue(tn, s);
+    if constexpr (BWD && NSLOT > 1) {
+      // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
+      // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
+      const long long tn = t + total_warps;
+      if (tn < a.num_tiles) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        issue(tn, s ^ 1);
+      }
     }
 
-    // mixture weights: W_m = exp(logit_m - max logit)
-    float lmax = v[0];
+    // W_m = exp(logit_m - max logit)
+    float lmax = rowp[m0];
 #pragma unroll
-    for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, v[m]);
+    for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, rowp[m0 + m]);
     lmax = group_max<LPP>(lmax, lane);
 
-    float sumW = 0.0f, sumWP = 0.0f;
-    float w[BWD ? MC : 1], wp[BWD ? MC : 1];
+    f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
+#pragma unroll 1
+    for (int pr = 0; pr < NPAIR; ++pr) {
+      const int m = m0 + 2 * pr;
+      const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+      f2 lg = ld_pair<AL>(rowp, m, single);
+      if (single) lg = pk(lo(lg), -INFINITY);  // the padding half gets zero weight
+      f2 mu[3], sc[3], kp[3];
 #pragma unroll
-    for (int m = 0; m < MC; ++m) {
-      const float mu[3] = {v[1 * MC + m], v[4 * MC + m], v[7 * MC + m]};
-      const float sc[3] = {v[2 * MC + m], v[5 * MC + m], v[8 * MC + m]};
-      const float kp[3] = {v[3 * MC + m], v[6 * MC + m], v[9 * MC + m]};
-      const float W = ex2a((v[m] - lmax) * kLog2e);
-      float P;
-      if constexpr (BWD) {
-        float u[9];
-        P = mix_bwd(px, mu, sc, kp, u);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) v[(1 + j) * MC + m] = u[j];
-        w[m] = W;
-        wp[m] = W * P;
-      } else {
-        P = mix_fwd(px, mu, sc, kp);
+      for (int c = 0; c < 3; ++c) {
+        mu[c] = ld_pair<AL>(rowp, (1 + 3 * c) * M + m, single);
+        sc[c] = ld_pair<AL>(rowp, (2 + 3 * c) * M + m, single);
+        kp[c] = ld_pair<AL>(rowp, (3 + 3 * c) * M + m, single);
       }
-      sumW += W;
-      sumWP = fmaf(W, P, sumWP);
+      const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
+      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+      f2 u[9];
+      f2 P;
+      if (narrow)
+        P = pair_eval<true, BWD>(px, mu, sc, kp, u);
+      else
+        P = pair_eval<false, BWD>(px, mu, sc, kp, u);
+      sumW2 = sumW2 + W;
+      sumWP2 = fma2(W, P, sumWP2);
+      if constexpr (BWD) {
+        // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          st_pair<AL>(rowp, (1 + 3 * c) * M + m, single, u[3 * c + 0]);
+          st_pair<AL>(rowp, (2 + 3 * c) * M + m, single, u[3 * c + 1]);
+          st_pair<AL>(rowp, (3 + 3 * c) * M + m, single, u[3 * c + 2]);
+        }
+        st_pair<AL>(auxp, m, single, W * P);
+      }
     }
-    const float S = group_sum<LPP>(sumWP, lane);
-    const float SW = group_sum<LPP>(sumW, lane);
+    const float S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
+    const float SW = group_sum<LPP>(lo(sumW2) + hi(sumW2), lane);
     const bool tiny = !(S > kTinySum);  // also catches NaN
     const float* grow = a.params + i * ROWF;
 
     if constexpr (!BWD) {
+      __syncwarp();
+      {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
+        const long long tn = t + NSLOT * total_warps;
+        if (tn < a.num_tiles) issue(tn, s);
+      }
       float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
       if (tiny) {
         float lt, ll;
@@ -412,37 +595,46 @@ __global__ void __launch_bounds__(BWD ? 256 : 256) modl_tile_kernel(const ModlAr
       const float rS = rcpa(S), rSW = rcpa(SW);
       float lt = 0.f, ll = 0.f;
       if (tiny) modl_pixel_logdomain(grow, M, px, lt, ll);
-#pragma unroll
-      for (int m = 0; m < MC; ++m) {
-        float r = wp[m] * rS;       // posterior responsibility of the component
-        float pi = w[m] * rSW;      // softmax(logits)
+#pragma unroll 1
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int m = m0 + 2 * pr;
+        const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+        f2 lg = ld_pair<AL>(rowp, m, single);
+        const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+        const f2 wp = ld_pair<AL>(auxp, m, single);
+        f2 r = wp * rS;     // posterior responsibility of the component
+        f2 pi = W * rSW;    // softmax(logits)
         if (tiny) {
-          r = expf(modl_logt(grow, M, sub * MC + m, px) - lt);
-          pi = expf(grow[sub * MC + m] - ll);
+          r = pk(expf(modl_logt(grow, M, m, px) - lt), single ? 0.0f : expf(modl_logt(grow, M, m + 1, px) - lt));
+          pi = pk(expf(grow[m] - ll), single ? 0.0f : expf(grow[m + 1] - ll));
         }
-        const float gr = g * r;
-        v[m] = g * (r - pi);
+        const f2 gr = r * g;
+        st_pair<AL>(rowp, m, single, (r - pi) * g);
 #pragma unroll
-        for (int j = 1; j < 10; ++j) v[j * MC + m] *= gr;
+        for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + m, single, ld_pair<AL>(rowp, j * M + m, single) * gr);
       }
-      // stage the gradient tile and hand it to the TMA engine
-      float* ob = slots + STAGES * TILE_F;
-      if (lane == 0) bulk_wait_read<0>();  // previous tile's store has finished reading the slot
-      __syncwarp();
-      if (active) chunk_store<MC, LPP>(v, ob + pp * ROWF, sub);
+      // hand the gradient tile to the TMA engine
       const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
       float* dst = a.dparams + t * TILE_F;
       if ((bytes & 15u) == 0) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(dst, ob, bytes);
+          bulk_s2g(dst, slot, bytes);
           bulk_commit();
         }
       } else {
         __syncwarp();
-        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = ob[q];
+        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = slot[q];
         __syncwarp();
+      }
+      if constexpr (NSLOT == 1) {
+        const long long tn = t + total_warps;
+        if (tn < a.num_tiles) {
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          issue(tn, 0);
+        }
       }
     }
   }
@@ -540,43 +732,67 @@ __global__ void __launch_bounds__(128) modl_generic_kernel(const ModlArgs a) {
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------------------
-struct LaunchCfg {
-  int warps;
+// Two shapes per kernel: (2 slots, <=8 warps, 255 registers) and (1 slot, <=16 warps, 128 registers).  VAEMDL_TUNE
+// ("fwd=S:W,bwd=S:W", S slots, W warps per CTA) overrides the built-in choice; used by the tuning sweeps under tools/.
+struct Shape {
+  int slots, warps;
 };
+static Shape tune_shape(bool bwd, Shape dflt) {
+  const char* env = getenv("VAEMDL_TUNE");
+  if (!env) return dflt;
+  const char* key = bwd ? "bwd=" : "fwd=";
+  const char* p = strstr(env, key);
+  if (!p) return dflt;
+  int s = 0, w = 0;
+  if (sscanf(p + 4, "%d:%d", &s, &w) == 2 && (s == 1 || s == 2) && w >= 1 && w <= 16) return Shape{s, w};
+  return dflt;
+}
 
-template <int MC, int LPP, bool BWD, int STAGES>
-static int launch_tiled(ModlArgs a, int warps, cudaStream_t st) {
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT>
+static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st) {
   using T = Tile<MC, LPP>;
-  constexpr int SLOTS = STAGES + (BWD ? 1 : 0);
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
   const DeviceInfo& di = device_info();
-  auto smem_for = [&](int w) { return static_cast<size_t>(w) * SLOTS * T::TILE_B + static_cast<size_t>(w) * STAGES * 8; };
-  while (warps > 1 && smem_for(warps) > static_cast<size_t>(di.max_smem_optin)) --warps;
-  const size_t smem = smem_for(warps);
-  auto kern = modl_tile_kernel<MC, LPP, BWD, STAGES>;
+  const size_t per_warp = (static_cast<size_t>(NSLOT) * T::TILE_F + (BWD ? T::AUX_F : 0)) * 4 + NSLOT * 8;
+  if (warps > MAXT / 32) warps = MAXT / 32;
+  while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  const size_t smem = warps * per_warp;
+  if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
+  auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return cuda_rc(e);
-  int ctas_per_sm = static_cast<int>(static_cast<size_t>(di.max_smem_optin) / (smem + 1024));
+  int ctas_per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem);
+  if (e != cudaSuccess) return cuda_rc(e);
   if (ctas_per_sm < 1) ctas_per_sm = 1;
-  long long need = (a.num_tiles + warps - 1) / warps;
-  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;
+  const long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;  // persistent: every CTA resident, tiles strided
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
   return cuda_rc(cudaGetLastError());
 }
 
+template <int MC, int LPP, bool BWD>
+static int launch_tiled(ModlArgs a, cudaStream_t st) {
+  // 1 slot x 16 warps: measured best on B200 for every M (profiles/r01_tune_shapes.txt); latency is hidden by the 4
+  // warps per scheduler rather than by a second slot per warp
+  const Shape sh = tune_shape(BWD, Shape{1, 16});
+  if (sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256>(a, sh.warps, st);
+  return launch_tiled_shape<MC, LPP, BWD, 1, 512>(a, sh.warps, st);
+}
+
 template <bool BWD>
 static int launch_modl(ModlArgs a, cudaStream_t st) {
   switch (a.M) {
     case 5:
-      return launch_tiled<5, 1, BWD, BWD ? 1 : 2>(a, 8, st);
+      return launch_tiled<5, 1, BWD>(a, st);
     case 10:
-      return launch_tiled<10, 1, BWD, BWD ? 1 : 2>(a, 8, st);
+      return launch_tiled<10, 1, BWD>(a, st);
     case 20:
-      return launch_tiled<10, 2, BWD, BWD ? 1 : 2>(a, 8, st);
+      return launch_tiled<10, 2, BWD>(a, st);
     case 30:
-      return launch_tiled<10, 3, BWD, BWD ? 1 : 2>(a, 8, st);
+      return launch_tiled<10, 3, BWD>(a, st);
     default: {
       const DeviceInfo& di = device_info();
       long long blocks = (a.n_px + 127) / 128;
