@@ -83,7 +83,7 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
   const size_t HW = static_cast<size_t>(H) * W;
   const size_t img_bytes = HW * 10 * M * sizeof(float);  // one (s,b) image of parameters
   if (chunk_b <= 0) {
-    const size_t target = 16u << 20;  // ~16 MB of parameters per chunk
+    const size_t target = 48u << 20;  // ~48 MB of parameters per chunk (tools/tune_e2e.py: best on PCIe Gen5)
     chunk_b = static_cast<int>(target / (img_bytes * S));
     if (chunk_b < 1) chunk_b = 1;
   }

@@ -550,7 +550,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       sumW2 = sumW2 + W;
       sumWP2 = fma2(W, P, sumWP2);
       if constexpr (BWD) {
-        // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip
+        // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip.
+        // Only lanes that own a real pixel write: shadow lanes (ragged tile, or lanes 30/31 when 3 lanes share a
+        // pixel) would otherwise race with the owner of pixel 0.
+        if (active) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           st_pair<AL>(rowp, (1 + 3 * c) * M + m, single, u[3 * c + 0]);
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
           st_pair<AL>(rowp, (3 + 3 * c) * M + m, single, u[3 * c + 2]);
         }
         st_pair<AL>(auxp, m, single, W * P);
+        }
       }
     }
     const float S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
@@ -609,9 +613,11 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
           pi = pk(expf(grow[m] - ll), single ? 0.0f : expf(grow[m + 1] - ll));
         }
         const f2 gr = r * g;
-        st_pair<AL>(rowp, m, single, (r - pi) * g);
+        if (active) {
+          st_pair<AL>(rowp, m, single, (r - pi) * g);
 #pragma unroll
-        for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + m, single, ld_pair<AL>(rowp, j * M + m, single) * gr);
+          for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + m, single, ld_pair<AL>(rowp, j * M + m, single) * gr);
+        }
       }
       // hand the gradient tile to the TMA engine
       const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
