@@ -144,9 +144,9 @@ def max_over_ranks(value, world, dev):
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 class ModlStep:
-    """Device-resident buffers + raw C-ABI calls for one fwd -> IWAE tail -> bwd step (5 launches)."""
+    """Device-resident buffers + raw C-ABI calls for one fwd -> finish -> bwd step (3 launches)."""
 
-    LAUNCHES_PER_STEP = 5  # modl fwd, partial-sum reduce, IWAE tail, batch mean, modl bwd
+    LAUNCHES_PER_STEP = 3  # modl fwd (tile partials), fused finish (per-image sums + IWAE tail + batch mean), modl bwd
 
     def __init__(self, S, B, H, W, M, dev, seed, b_total):
         from vae_mdl_b200 import _abi
@@ -168,14 +168,11 @@ class ModlStep:
         self.n_px = S * B * H * W
 
     def fwd(self):
-        rc = self.L.vaemdl_modl_fwd(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S * self.B, self.B, self.H,
-                                    self.W, self.M, None, None, self.ll64.data_ptr(), self.ws.data_ptr(), self.ws_bytes,
-                                    self.st)
-        assert rc == 0, rc
-
-    def tail(self):
-        rc = self.L.vaemdl_iwae_tail(None, self.ll64.data_ptr(), self.extra.data_ptr(), self.S, self.B, self.b_total,
-                                     None, self.lme.data_ptr(), self.elbo.data_ptr(), self.g_ll.data_ptr(), self.st)
+        # forward kernel + fused finish kernel: lpxz (float64), log-mean-exp, elbo, g_ll = d(-elbo)/d lpxz
+        rc = self.L.vaemdl_modl_iwae_fwd(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B, self.b_total,
+                                         self.B, self.H, self.W, self.M, self.extra.data_ptr(), None,
+                                         self.ll64.data_ptr(), None, self.lme.data_ptr(), self.elbo.data_ptr(),
+                                         self.g_ll.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.st)
         assert rc == 0, rc
 
     def bwd(self):
@@ -185,7 +182,6 @@ class ModlStep:
 
     def step(self):
         self.fwd()
-        self.tail()
         self.bwd()
 
 
@@ -194,7 +190,7 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
     for _ in range(warmup):
         step.step()
     torch.cuda.synchronize(dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     barrier(world)
     torch.cuda.synchronize(dev)
     with ClockSampler(sampler_index) as clk:
@@ -203,19 +199,15 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
             ev[k][0].record(step.stream)
             step.fwd()
             ev[k][1].record(step.stream)
-            step.tail()
-            ev[k][2].record(step.stream)
             step.bwd()
-            ev[k][3].record(step.stream)
+            ev[k][2].record(step.stream)
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
     barrier(world)
-    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
-    tail_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
-    bwd_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / steps
-    return {"total_ms": total_ms, "wall_ms": wall * 1e3, "fwd_ms": fwd_ms, "tail_ms": tail_ms, "bwd_ms": bwd_ms,
-            "clocks": clk.summary()}
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    return {"total_ms": total_ms, "wall_ms": wall * 1e3, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "clocks": clk.summary()}
 
 
 def run_e2e(S, B, H, W, M, steps, warmup, world, dev, seed):
@@ -254,6 +246,48 @@ def run_e2e(S, B, H, W, M, steps, warmup, world, dev, seed):
     return dt, h2d, d2h, float(elbo.item())
 
 
+def run_eval(world, rank, dev, peak, n_local=48, S=5000, H=32, W=32, M=10):
+    """BASELINE configs[3]: test-set IWAE evaluation with 5000 importance samples (models/model05.py:168-176), images
+    round-robin over ranks (vae_mdl_b200/dist.py).  Per image: ONE forward launch over the [5000,1,32,32,10M] decoder
+    output (2.05 GB at M=10) + ONE finish launch (per-sample sums, log-mean-exp) writing llh[i]; no host sync until the
+    single all-gather at the end.  Two parameter buffers alternate (4.1 GB >> L2).  Returns img/s over all ranks."""
+    from vae_mdl_b200 import _abi
+    from vae_mdl_b200 import dist as vdist
+    L = _abi.lib()
+    gen = torch.Generator(device=dev).manual_seed(77 + rank)
+    pool = [torch.randn(S, 1, H, W, 10 * M, device=dev, generator=gen) for _ in range(2)]
+    xs = torch.randint(0, 256, (n_local, H, W, 3), dtype=torch.uint8, device=dev, generator=gen)
+    llh = torch.empty(n_local, device=dev)
+    ws_bytes = L.vaemdl_modl_workspace_bytes(S, H, W)
+    ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def sweep():
+        for i in range(n_local):
+            rc = L.vaemdl_modl_iwae_fwd(pool[i & 1].data_ptr(), xs[i].data_ptr(), 1, 0, 0, S, 1, 0, 1, H, W, M, None, None,
+                                        None, None, llh[i:].data_ptr(), None, None, ws.data_ptr(), ws_bytes, st)
+            assert rc == 0, rc
+        return vdist.gather_round_robin(llh, n_local * world)
+
+    sweep()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = sweep()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    t = max_over_ranks(e0.elapsed_time(e1), world, dev) * 1e-3
+    bpd = float(-out.mean().item() / (math.log(2.0) * H * W * 3))
+    n_total = n_local * world
+    return {"metric": "5000-IS IWAE test evaluation img/s", "images_per_s": n_total / t, "n_images": n_total,
+            "importance_samples": S, "n_mix": M, "ms_per_image_per_gpu": t / n_local * 1e3,
+            "frac_of_hbm_peak_per_gpu": n_local * S * H * W * 40 * M / t / 1e9 / peak,
+            "full_test_set_26032_images_s": 26032 / (n_total / t), "bpd_of_synthetic_params": bpd,
+            "launches_per_image": 2, "collective": "one all_gather of the per-image results at the end"}
+
+
 def also_workloads(dev, peak):
     """Short, untimed-by-the-driver summaries of the other BASELINE configs (rank 0, N=1 only)."""
     import vae_mdl_b200 as V
@@ -279,24 +313,40 @@ def also_workloads(dev, peak):
         out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6,
                      "algorithmic_GBs": st.n_px * 120 * M / t / 1e9, "frac_of_hbm_peak": st.n_px * 120 * M / t / 1e9 / peak}
         del st
-    # config 2: plain discretized logistic fwd + IWAE tail + bwd, S=5 x B=128, 32x32x3 (models/model03.py shapes)
+    # config 2: plain discretized logistic fwd + IWAE tail + bwd, S=5 x B=128, 32x32x3 (models/model03.py shapes),
+    # raw C-ABI calls on preallocated buffers; the un-split [..,6] conv output is read in place (ld = 6)
     S, B, H, W = 5, 128, 32, 32
     gen = torch.Generator(device=dev).manual_seed(3)
     both = torch.randn(S, B, H, W, 6, device=dev, generator=gen)
     both[..., :3].uniform_(generator=gen)
-    mu, lstd = torch.split(both, 3, dim=-1)
+    dboth = torch.empty_like(both)
     x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=gen)
-    d = V.DiscretizedLogistic(mu, lstd, low=0.0, high=1.0, levels=256.0)
+    from vae_mdl_b200 import _abi
+    L = _abi.lib()
+    D = H * W * 3
+    ll64 = torch.empty(S, B, dtype=torch.float64, device=dev)
+    g_ll = torch.empty(S, B, device=dev)
+    lme = torch.empty(B, device=dev)
+    elbo = torch.empty(1, device=dev)
+    wsb = L.vaemdl_dlogistic_workspace_bytes(S * B, D)
+    ws = torch.empty(wsb // 8 + 1, dtype=torch.float64, device=dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    p_loc, p_ls = both.data_ptr(), both.data_ptr() + 12
+    d_loc, d_ls = dboth.data_ptr(), dboth.data_ptr() + 12
 
     def dl_step():
-        from vae_mdl_b200.functional import _DlFn  # noqa: F401
-        with torch.no_grad():
-            ll = d.log_likelihood(x, dtype=torch.float64)
-            _, _, _, g = F.iwae_tail(ll, None)
-        return g
+        rc = L.vaemdl_dlogistic_fwd(p_loc, p_ls, 3, 6, x.data_ptr(), 1, S * B, B, D, 0.0, 1.0, 256.0, None, None,
+                                    ll64.data_ptr(), ws.data_ptr(), wsb, st)
+        rc |= L.vaemdl_iwae_tail(None, ll64.data_ptr(), None, S, B, 0, None, lme.data_ptr(), elbo.data_ptr(),
+                                 g_ll.data_ptr(), st)
+        rc |= L.vaemdl_dlogistic_bwd(p_loc, p_ls, 3, 6, x.data_ptr(), 1, S * B, B, D, 0.0, 1.0, 256.0, g_ll.data_ptr(),
+                                     None, d_loc, d_ls, 6, st)
+        assert rc == 0, rc
 
-    t = timeit(dl_step, 20)
-    out["cfg2_dl_fwd_tail"] = {"us_per_step": t * 1e6, "px_samples_per_s": S * B * H * W / t}
+    t = timeit(dl_step, 50)
+    n_sub = S * B * H * W
+    out["cfg2_dl_fwd_tail_bwd"] = {"us_per_step": t * 1e6, "px_samples_per_s": n_sub / t,
+                                   "algorithmic_GBs": n_sub * 72 / t / 1e9, "frac_of_hbm_peak": n_sub * 72 / t / 1e9 / peak}
     # config 3: sampling from supplied uniforms, reduced to 2,000 images here (10,000 in BASELINE)
     N, M = 2000, 10
     l = torch.randn(N, 32, 32, 10 * M, device=dev, generator=gen)
@@ -305,23 +355,6 @@ def also_workloads(dev, peak):
     t = timeit(lambda: V.sample_from_discretized_mix_logistic(l, M, um, ul, return_quantised=True, return_index=True), 5)
     out["cfg3_sampling_2000img"] = {"images_per_s": N / t, "algorithmic_GBs": N * 1024 * 468 / t / 1e9}
     del l, um, ul
-    # config 4: 5000-IS evaluation, S streamed in chunks of 250 over 4 rotating parameter buffers (> L2), 8 images
-    S, Sc, M = 5000, 250, 10
-    pool = [torch.randn(Sc, 1, 32, 32, 10 * M, device=dev, generator=gen) for _ in range(4)]
-    x1 = torch.randint(0, 256, (1, 32, 32, 3), dtype=torch.uint8, device=dev, generator=gen)
-    n_img = 8
-    log_w = torch.empty(n_img, S, dtype=torch.float64, device=dev)
-
-    def eval_images():
-        k = 0
-        for i in range(n_img):
-            for s_lo in range(0, S, Sc):
-                log_w[i, s_lo:s_lo + Sc] = F.modl_log_likelihood(pool[k % 4], x1, dtype=torch.float64)[:, 0]
-                k += 1
-        return F.logmeanexp(log_w.t().contiguous(), 0)
-
-    t = timeit(eval_images, 2, warm=1)
-    out["cfg4_iwae_eval_5000is"] = {"images_per_s": n_img / t, "frac_of_hbm_peak": n_img * S * 1024 * 400 / t / 1e9 / peak}
     return out
 
 
@@ -413,6 +446,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-also", action="store_true", help="skip the summaries of the other BASELINE configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the 5000-IS evaluation (BASELINE configs[3]) leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -448,8 +482,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "modl_tile_kernel<BWD> (vaemdl_modl_bwd)", "achieved": bwd_bytes / bwd_s / 1e9,
                 "peak": peak, "peak_source": peak_how, "unit": "GB/s", "frac": bwd_bytes / bwd_s / 1e9 / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": bwd_bytes,
-                "fwd_kernel": {"achieved": fwd_bytes / fwd_s / 1e9, "frac": fwd_bytes / fwd_s / 1e9 / peak,
-                               "algorithmic_bytes_per_launch": fwd_bytes},
+                "fwd_plus_finish": {"achieved": fwd_bytes / fwd_s / 1e9, "frac": fwd_bytes / fwd_s / 1e9 / peak,
+                                    "algorithmic_bytes_per_launch": fwd_bytes},
                 "step": {"achieved": n_px * 120 * M * args.steps / total_s / 1e9,
                          "frac": n_px * 120 * M * args.steps / total_s / 1e9 / peak,
                          "frac_of_nominal_8TBs": n_px * 120 * M * args.steps / total_s / 1e9 / 8000.0}}
@@ -463,6 +497,10 @@ def main():
     e2e = {"value": world * n_px * e2e_steps / dt, "unit": "px-samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
            "api": "vaemdl_modl_iwae_step_host (pinned host buffers; H2D params+x+extra, D2H grads+ll+lme+elbo each step)"}
+
+    ev = None
+    if not args.no_eval:
+        ev = run_eval(world, rank, dev, peak)
 
     cpu = None
     also = None
@@ -484,12 +522,14 @@ def main():
                        "px_samples_per_step_per_gpu": n_px, "l2": "inputs larger than L2 "
                        f"(params {n_px * 40 * M / 2**20:.0f} MiB + grads {n_px * 40 * M / 2**20:.0f} MiB per step vs 126 MiB L2)"
                        if n_px * 40 * M > L2_BYTES else "inputs NOT larger than L2",
-                       "step": "modl_fwd (per-image ll, float64 sums) -> iwae_tail -> modl_bwd; inputs resident in HBM"},
+                       "step": "modl_fwd (tile partials, float64) -> fused finish (per-image ll, log-mean-exp, elbo, softmax weights) -> modl_bwd; inputs resident in HBM"},
             "clocks": res["clocks"], "e2e": e2e, "gpu_launches": ModlStep.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_ms": {"fwd": res["fwd_ms"], "iwae_tail": res["tail_ms"], "bwd": res["bwd_ms"]},
+            "kernel_ms": {"fwd_plus_finish": res["fwd_ms"], "bwd": res["bwd_ms"]},
             "elbo_check": {"device": elbo_device, "e2e": elbo_e2e},
         }
+        if ev is not None:
+            line["iwae_eval_5000is"] = ev
         if also is not None:
             line["also"] = also
         print(json.dumps(line), flush=True)

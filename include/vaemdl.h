@@ -94,6 +94,23 @@ VAEMDL_API int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, 
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * MoDL forward fused with the IWAE tail: TWO launches (forward, finish) when S <= 512 and M in {5,10,20,30},
+ * otherwise forward + per-image reduce + IWAE tail, for
+ *     lpxz = reduce_sum(pxz.log_prob(x), [-1,-2,-3])                    models/loss.py:32
+ *     log_w = lpxz + extra ; lme_b = logmeanexp(log_w, axis=0)          models/loss.py:34-37, utils/utils.py:9-11
+ *     elbo = sum_b lme_b / B_total ; g_ll = d(-elbo)/d lpxz = -softmax_s(log_w) / B_total
+ * params [S,B,H,W,10M]; extra [S,B] nullable (= beta*(lpz-lqzx)); B_total: whole-batch size when B is one rank's shard
+ * (0 = B).  Outputs (all nullable): ll_image [S,B] float32, ll_image_f64 [S,B], log_w [S,B], lme_b [B], elbo [1]
+ * (needs lme_b), g_ll [S,B] -- feed g_ll to vaemdl_modl_bwd(g_image=...).  Sums are float64 and in a fixed order.
+ * workspace: as for vaemdl_modl_fwd with n_img = S*B.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_iwae_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                    const float* extra,
+                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Mixture of discretized logistics -- gradient w.r.t. params
  * replaces: tf.GradientTape over the ops above              models/model05.py:141-145
  * The upstream gradient on lp_pixel[n,h,w] is

@@ -58,6 +58,41 @@ def test_iwae_tail_matches_oracle(V):
     assert relnorm(torch.cat([g0, g1], 1), ll64.grad) < 1e-5
 
 
+@pytest.mark.parametrize("S,B,H,W,M,b_total", [(5, 6, 32, 32, 10, 0), (3, 4, 16, 16, 5, 0), (4, 3, 8, 8, 30, 0),
+                                                  (2, 5, 8, 8, 20, 0), (7, 9, 4, 4, 7, 0), (1200, 2, 8, 8, 10, 0),
+                                                  (6000, 1, 4, 8, 10, 0), (5, 11, 8, 8, 10, 40), (3, 3, 2, 2, 10, 0)])
+def test_fused_forward_finish_matches_oracle(V, S, B, H, W, M, b_total):
+    """vaemdl_modl_iwae_fwd (forward kernel + ONE finish kernel) against models/loss.py:32-37 in float64, including the
+    routes that fall back to the separate tail: any-M kernel (M=7), images smaller than a tile (2x2), more than 512
+    importance samples (1200, 6000)."""
+    from vae_mdl_b200 import functional as F
+    params, x_u8, g = canonical(100 + S + M, S, B, H, W, M)
+    p64 = params.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    lp64 = O.modl_log_prob(p64, x64)
+    ll64 = lp64.sum((-1, -2, -3))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()) + torch.randn(S, B, generator=g).double()
+    loss64, _ = O.iwae_loss(lp64, extra, torch.zeros_like(extra), x64.shape)
+    if b_total:
+        loss64 = loss64 * B / b_total
+    g64 = -torch.softmax(ll64.detach() + extra, 0) / (b_total or B)   # d loss / d lpxz (models/loss.py:34-37)
+    ll, log_w, lme_b, elbo, g_ll = F.modl_iwae_forward(params.to(DEV), x_u8.to(DEV), extra.float().to(DEV), b_total)
+    assert ll.dtype == torch.float64 and ll.shape == (S, B)
+    assert ((ll.cpu() - ll64.detach()).abs() / ll64.detach().abs()).max().item() <= LL_RTOL
+    assert abs(-elbo.item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
+    assert relnorm(log_w, ll64.detach() + extra) < 1e-6
+    lme64 = O.logmeanexp(ll64.detach() + extra, 0)
+    assert relnorm(lme_b, lme64) < 1e-6
+    assert relnorm(g_ll, g64) < GRAD_RTOL
+    # the step built on it gives the parameter gradient of the loss
+    loss, lpxz, dparams = V.modl_iwae_step(params.to(DEV), x_u8.to(DEV), extra.float().to(DEV), b_total=b_total)
+    loss64.backward()
+    assert_grad_close(dparams, p64.grad, M)
+    # bitwise reproducible (fixed-order reductions) and independent of what ran before on the stream
+    ll2, _, _, elbo2, g2 = F.modl_iwae_forward(params.to(DEV), x_u8.to(DEV), extra.float().to(DEV), b_total)
+    assert torch.equal(ll, ll2) and torch.equal(elbo, elbo2) and torch.equal(g_ll, g2)
+
+
 def _setup_model05_like(g, S, B, H, W, M, n_latent=20):
     params = torch.randn(S, B, H, W, 10 * M, generator=g)
     x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)

@@ -32,6 +32,9 @@ PROTOTYPES = {
     "vaemdl_modl_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "vaemdl_modl_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),

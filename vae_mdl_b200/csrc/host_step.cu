@@ -19,7 +19,6 @@ struct Slot {
   float* params = nullptr;
   float* grads = nullptr;
   float* ll = nullptr;     // [S, cb]
-  double* ll64 = nullptr;  // [S, cb] float64 sums feeding the IWAE softmax
   float* extra = nullptr;  // [S, cb]
   float* g_ll = nullptr;   // [S, cb]
   float* lme = nullptr;    // [cb]
@@ -99,14 +98,11 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
       if (s.ll) cudaFree(s.ll);
       if (s.extra) cudaFree(s.extra);
       if (s.g_ll) cudaFree(s.g_ll);
-      if (s.ll64) cudaFree(s.ll64);
       s.ll = s.extra = s.g_ll = nullptr;
-      s.ll64 = nullptr;
       s.small_elems = 0;
       VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.ll), small));
       VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.extra), small));
       VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.g_ll), small));
-      VAEMDL_TRY(cudaMalloc(reinterpret_cast<void**>(&s.ll64), 2 * small));
       s.small_elems = small;
     }
     VAEMDL_TRY(grow(s.lme, s.lme_elems, static_cast<size_t>(chunk_b) * sizeof(float)));
@@ -131,11 +127,10 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
     if (extra_host)
       VAEMDL_TRY(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), extra_host + b0, static_cast<size_t>(B) * sizeof(float),
                                    cb * sizeof(float), S, cudaMemcpyHostToDevice, s.stream));
-    int rc = vaemdl_modl_fwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
-                             VAEMDL_EDGE_MDL, n_img, cb, H, W, M, nullptr, s.ll, s.ll64, s.ws, s.ws_bytes, s.stream);
-    if (rc) return rc;
-    rc = iwae_tail_norm(s.ll, s.ll64, extra_host ? s.extra : nullptr, S, cb, static_cast<float>(B), nullptr, s.lme,
-                        dparams_host ? s.g_ll : nullptr, s.stream);
+    // forward + fused finish (per-image sums, log-mean-exp, softmax weights normalised by the WHOLE batch): 2 launches
+    int rc = vaemdl_modl_iwae_fwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
+                                  VAEMDL_EDGE_MDL, S, cb, B, cb, H, W, M, extra_host ? s.extra : nullptr, s.ll, nullptr,
+                                  nullptr, s.lme, nullptr, dparams_host ? s.g_ll : nullptr, s.ws, s.ws_bytes, s.stream);
     if (rc) return rc;
     VAEMDL_TRY(cudaMemcpy2DAsync(ll_host + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
                                  cb * sizeof(float), S, cudaMemcpyDeviceToHost, s.stream));
@@ -168,7 +163,6 @@ extern "C" void vaemdl_host_release(void) {
       cudaFree(s.ll);
       cudaFree(s.extra);
       cudaFree(s.g_ll);
-      cudaFree(s.ll64);
       cudaFree(s.lme);
       cudaFree(s.ws);
       if (s.stream) cudaStreamDestroy(s.stream);

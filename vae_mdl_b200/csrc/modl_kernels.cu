@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include "modl_math.cuh"
@@ -30,13 +31,16 @@ struct ModlArgs {
   const float* params;
   const void* x;
   float* lp_pixel;       // nullable
-  double* partial;       // [num_tiles][2] tile partial sums in float64 (nullable)
+  double* partial;       // [total_warps][K] float64 partial sums, one per (warp, image the warp's tile range touches) (nullable)
   double* ll_atomic;     // [n_img] pre-zeroed float64 accumulators, used instead of `partial` when tiles would span >2 images
   const float* g_image;  // nullable
   const float* g_pixel;  // nullable
   float* dparams;
+  unsigned* zero_me;  // nullable: a word the forward kernel clears for the fused finish kernel that follows it
   long long n_px;  // n_img * H * W
   long long num_tiles;
+  long long tw_base, tw_rem;  // warp w owns tiles [w*tw_base + min(w, tw_rem), +tw_base + (w < tw_rem)): consecutive tiles
+  int K;                      // partial slots per warp: max number of images one warp's tile range can touch
   int HW;
   int x_batch;
   int x_u8;
@@ -414,8 +418,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     fence_barrier_init();
   }
   __syncwarp();
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
 
-  const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
   const bool lane_used = (lane / LPP) < PPT;
   const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
@@ -444,19 +448,27 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     }
   };
 
+  // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
+  // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+
   // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below)
 #pragma unroll
   for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
-    const long long t = gw + s * total_warps;
-    if (t < a.num_tiles) issue(t, s);
+    const long long t = t_begin + s;
+    if (t < t_end) issue(t, s);
   }
 
   // (image, pixel-in-image) of this lane's pixel-sample, advanced incrementally: one 64-bit division per kernel
-  const long long step_px = total_warps * PPT;
-  const long long step_n = step_px / a.HW;
-  const int step_pix = static_cast<int>(step_px - step_n * a.HW);
-  long long n_own = (gw * PPT + p) / a.HW;
-  int pix_own = static_cast<int>((gw * PPT + p) - n_own * a.HW);
+  const long long step_n = PPT / a.HW;
+  const int step_pix = static_cast<int>(PPT - step_n * a.HW);
+  long long n_own = (t_begin * PPT + p) / a.HW;
+  int pix_own = static_cast<int>((t_begin * PPT + p) - n_own * a.HW);
+  // float64 running sums of the image the warp is in (acc0, image n_base) and of the next one (acc1), per lane
+  double acc0 = 0.0, acc1 = 0.0;
+  const long long n_warp_first = (t_begin * PPT) / a.HW;
+  long long n_base = n_warp_first;
 
   // software prefetch of the (L2-resident) pixel and upstream-gradient values one tile ahead
   auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
@@ -480,10 +492,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   long long n_cur = 0, nfirst_cur = 0;
   PixRaw raw_cur{};
   float g_cur = 0.0f;
-  if (gw < a.num_tiles) fetch(gw, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+  if (t_begin < t_end) fetch(t_begin, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
 
   long long it = 0;
-  for (long long t = gw; t < a.num_tiles; t += total_warps, ++it) {
+  for (long long t = t_begin; t < t_end; ++t, ++it) {
     const int s = static_cast<int>(it % NSLOT);
     const uint32_t parity = static_cast<uint32_t>((it / NSLOT) & 1);
     const int rows = tile_rows(t);
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       pix_own -= a.HW;
       ++n_own;
     }
-    if (t + total_warps < a.num_tiles) fetch(t + total_warps, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+    if (t + 1 < t_end) fetch(t + 1, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
 
     float* slot = slots + s * TILE_F;
     float* rowp = slot + pp * ROWF;
@@ -510,8 +522,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     if constexpr (BWD && NSLOT > 1) {
       // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
       // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
-      const long long tn = t + total_warps;
-      if (tn < a.num_tiles) {
+      const long long tn = t + 1;
+      if (tn < t_end) {
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
         issue(tn, s ^ 1);
@@ -572,8 +584,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     if constexpr (!BWD) {
       __syncwarp();
       {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
-        const long long tn = t + NSLOT * total_warps;
-        if (tn < a.num_tiles) issue(tn, s);
+        const long long tn = t + NSLOT;
+        if (tn < t_end) issue(tn, s);
       }
       float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
       if (tiny) {
@@ -585,13 +597,19 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
       const float val = owner ? lp : 0.0f;
       if (a.partial) {
-        // float64 from here on: the per-image sums (~ -2e4 nats) feed a softmax over importance samples
-        const double s0 = warp_sum(n == n_first ? static_cast<double>(val) : 0.0);
-        const double s1 = warp_sum(n == n_first ? 0.0 : static_cast<double>(val));
-        if (lane == 0) {
-          a.partial[2 * t] = s0;
-          a.partial[2 * t + 1] = s1;
+        // float64 from here on: the per-image sums (~ -2e4 nats) feed a softmax over importance samples.
+        // A tile holds pixels of at most two images (HW >= PPT on this route): n_first and n_first + 1.
+        while (n_base < n_first) {  // the warp has left image n_base: its sum leaves the registers (warp-uniform)
+          const double done = warp_sum(acc0);
+          if (lane == 0) a.partial[gw * a.K + (n_base - n_warp_first)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
         }
+        if (n == n_base)
+          acc0 += static_cast<double>(val);
+        else
+          acc1 += static_cast<double>(val);
       } else if (a.ll_atomic) {
         if (owner) atomicAdd(a.ll_atomic + n, static_cast<double>(val));
       }
@@ -635,8 +653,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
         __syncwarp();
       }
       if constexpr (NSLOT == 1) {
-        const long long tn = t + total_warps;
-        if (tn < a.num_tiles) {
+        const long long tn = t + 1;
+        if (tn < t_end) {
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
           issue(tn, 0);
@@ -646,26 +664,131 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   }
   if constexpr (BWD) {
     if (lane == 0) bulk_wait_all<0>();
+  } else {
+    if (a.partial && t_begin < t_end) {
+      const long long n_last = (t_end * PPT < a.n_px ? t_end * PPT - 1 : a.n_px - 1) / a.HW;  // image of the warp's last pixel-sample
+      const double d0 = warp_sum(acc0), d1 = warp_sum(acc1);
+      if (lane == 0) {
+        a.partial[gw * a.K + (n_base - n_warp_first)] = d0;
+        if (n_base + 1 <= n_last) a.partial[gw * a.K + (n_base + 1 - n_warp_first)] = d1;
+      }
+    }
   }
 }
 
-// ---- per-image sums from the tile partials (fixed order => bitwise reproducible) ---------------------------------------
-__global__ void modl_reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ ll_image,
-                                            double* __restrict__ ll_image_f64, long long n_img, int HW, int PPT) {
-  const long long n = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= n_img) return;
-  const long long first = n * HW, last = first + HW - 1;
-  const long long t_lo = first / PPT, t_hi = last / PPT;
+// ---- per-image sums from the per-warp partials (fixed order => bitwise reproducible) ---------------------------------
+// Warp w of the forward grid owned tiles [w*base + min(w, rem), ...) and left one float64 partial per image its run
+// touched at partial[w*K + (n - first image of the run)].
+struct PartialGeom {
+  const double* partial;
+  long long tw_base, tw_rem;
+  int K, PPT, HW;
+};
+__device__ __forceinline__ double image_sum(const PartialGeom& g, long long n) {
+  const long long first = n * g.HW, last = first + g.HW - 1;
+  const long long t_lo = first / g.PPT, t_hi = last / g.PPT;
+  const long long cut = g.tw_rem * (g.tw_base + 1);
+  const long long w_lo = t_lo < cut ? t_lo / (g.tw_base + 1) : g.tw_rem + (t_lo - cut) / g.tw_base;
+  const long long w_hi = t_hi < cut ? t_hi / (g.tw_base + 1) : g.tw_rem + (t_hi - cut) / g.tw_base;
   double acc = 0.0;
-  for (long long t = t_lo + lane; t <= t_hi; t += 32) {
-    const long long n0 = (t * PPT) / HW;
-    acc += (n0 == n) ? partial[2 * t] : partial[2 * t + 1];
+  for (long long w = w_lo; w <= w_hi; ++w) {
+    const long long tb = w * g.tw_base + (w < g.tw_rem ? w : g.tw_rem);
+    const long long nf = (tb * g.PPT) / g.HW;
+    acc += g.partial[w * g.K + (n - nf)];
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    if (ll_image) ll_image[n] = static_cast<float>(acc);
-    if (ll_image_f64) ll_image_f64[n] = acc;
+  return acc;
+}
+
+__global__ void modl_reduce_partials_kernel(const PartialGeom g, float* __restrict__ ll_image,
+                                            double* __restrict__ ll_image_f64, long long n_img) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= n_img) return;
+  const double acc = image_sum(g, n);
+  if (ll_image) ll_image[n] = static_cast<float>(acc);
+  if (ll_image_f64) ll_image_f64[n] = acc;
+}
+
+// ---- fused finish: per-image sums from the partials + IWAE tail + batch mean, ONE launch --------------------------------
+// Replaces reduce_sum over [-1,-2,-3] (models/loss.py:32), log_w (:34), logmeanexp over samples (utils/utils.py:9-11),
+// the batch mean (:37) and the upstream gradient -softmax_s(log_w)/B that tf.GradientTape would derive.
+// A block owns BB consecutive batch elements and all S samples of them (one thread per image, then one warp per batch
+// element); every reduction runs in a fixed order.
+struct FinishArgs {
+  PartialGeom geom;
+  const float* extra;     // [S,B] nullable
+  float* ll;              // [S,B] nullable
+  double* ll64;           // [S,B] nullable
+  float* log_w;           // [S,B] nullable
+  float* lme_b;           // [B] nullable
+  float* elbo;            // [1] nullable
+  float* g_ll;            // [S,B] nullable
+  double* block_sums;     // [gridDim.x]
+  unsigned* counter;      // cleared by the forward kernel
+  long long B;
+  int S, BB;
+  float b_norm;
+};
+
+constexpr int kFinishThreads = 256;
+
+__global__ void __launch_bounds__(kFinishThreads) modl_finish_kernel(const FinishArgs a) {
+  extern __shared__ double lw[];  // [BB][S]
+  __shared__ double blk[kFinishThreads / 32];
+  __shared__ bool is_last;
+  constexpr int NW = kFinishThreads / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b0 = static_cast<long long>(blockIdx.x) * a.BB;
+  const int nb = static_cast<int>((a.B - b0) < a.BB ? (a.B - b0) : a.BB);
+  // (1) per-image log-likelihood, one thread per image n = s*B + b (consecutive threads: consecutive b)
+  for (int img = threadIdx.x; img < a.S * nb; img += kFinishThreads) {
+    const int s = img / nb, bb = img - s * nb;
+    const long long n = static_cast<long long>(s) * a.B + b0 + bb;
+    const double acc = image_sum(a.geom, n);
+    if (a.ll) a.ll[n] = static_cast<float>(acc);
+    if (a.ll64) a.ll64[n] = acc;
+    const double v = acc + (a.extra ? static_cast<double>(a.extra[n]) : 0.0);  // models/loss.py:34
+    if (a.log_w) a.log_w[n] = static_cast<float>(v);
+    lw[bb * a.S + s] = v;
+  }
+  __syncthreads();
+  // (2) log-mean-exp over the samples of each batch element, one warp per element
+  double wsum = 0.0;
+  for (int bb = warp; bb < nb; bb += NW) {
+    const double* v = lw + bb * a.S;
+    double mx = -INFINITY;
+    for (int s = lane; s < a.S; s += 32) mx = fmax(mx, v[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));  // utils/utils.py:10
+    float sm = 0.0f;
+    for (int s = lane; s < a.S; s += 32) sm += expf(static_cast<float>(v[s] - mx));
+    sm = warp_sum(sm);
+    const double lme = static_cast<double>(logf(sm / static_cast<float>(a.S))) + mx;  // utils/utils.py:11
+    if (lane == 0 && a.lme_b) a.lme_b[b0 + bb] = static_cast<float>(lme);
+    if (a.g_ll) {
+      const float scale = -1.0f / (sm * a.b_norm);  // d(-mean_b lme_b)/d log_w = -softmax_s / B
+      for (int s = lane; s < a.S; s += 32)
+        a.g_ll[static_cast<long long>(s) * a.B + b0 + bb] = expf(static_cast<float>(v[s] - mx)) * scale;
+    }
+    wsum += lme;  // identical in every lane
+  }
+  // (3) batch mean: block partial sums, combined in block order by whichever block finishes last
+  if (!a.elbo) return;
+  if (lane == 0) blk[warp] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < NW; ++w) t += blk[w];
+    a.block_sums[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(a.block_sums)[i];
+    a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+    *a.counter = 0u;
   }
 }
 
@@ -678,6 +801,7 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __rest
 template <bool BWD>
 __global__ void __launch_bounds__(128) modl_generic_kernel(const ModlArgs a) {
   const int M = a.M;
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const long long n_iter = (a.n_px + stride - 1) / stride;  // every lane runs the same trip count (warp votes inside)
   for (long long itn = 0; itn < n_iter; ++itn) {
@@ -754,8 +878,15 @@ static Shape tune_shape(bool bwd, Shape dflt) {
   return dflt;
 }
 
+constexpr long long kMaxGridWarps = 8192;  // bound on gridDim.x * warps per CTA (sizes the partial-sum workspace)
+
+struct TilePlan {  // how the forward grid split the tile range: what the per-image reduction needs to know
+  long long total_warps = 0, tw_base = 0, tw_rem = 0;
+  int K = 0, PPT = 0;
+};
+
 template <int MC, int LPP, bool BWD, int NSLOT, int MAXT>
-static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st) {
+static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* plan) {
   using T = Tile<MC, LPP>;
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
   const DeviceInfo& di = device_info();
@@ -765,40 +896,67 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st) {
   const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
   auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return cuda_rc(e);
-  int ctas_per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, warps * 32, smem);
-  if (e != cudaSuccess) return cuda_rc(e);
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  // the function attribute and the occupancy query cost several microseconds of host time: once per (device, shape)
+  static std::mutex mu;
+  static int c_dev = -1, c_warps = -1, c_ctas = 1;
+  int ctas_per_sm;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_dev != dev || c_warps != warps) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_rc(e);
+      int n = 1;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem);
+      if (e != cudaSuccess) return cuda_rc(e);
+      c_dev = dev;
+      c_warps = warps;
+      c_ctas = n < 1 ? 1 : n;
+    }
+    ctas_per_sm = c_ctas;
+  }
   const long long need = (a.num_tiles + warps - 1) / warps;
-  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;  // persistent: every CTA resident, tiles strided
+  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;  // persistent: every CTA resident
   if (grid > need) grid = need;
+  if (grid * warps > kMaxGridWarps) grid = kMaxGridWarps / warps;
   if (grid < 1) grid = 1;
+  const long long total_warps = grid * warps;
+  a.tw_base = a.num_tiles / total_warps;
+  a.tw_rem = a.num_tiles % total_warps;
+  const long long max_tiles = a.tw_base + (a.tw_rem ? 1 : 0);
+  a.K = static_cast<int>((max_tiles * T::PPT + a.HW - 1) / a.HW + 1);
+  if (plan) {
+    plan->total_warps = total_warps;
+    plan->tw_base = a.tw_base;
+    plan->tw_rem = a.tw_rem;
+    plan->K = a.K;
+    plan->PPT = T::PPT;
+  }
   kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
   return cuda_rc(cudaGetLastError());
 }
 
 template <int MC, int LPP, bool BWD>
-static int launch_tiled(ModlArgs a, cudaStream_t st) {
+static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   // 1 slot x 16 warps: measured best on B200 for every M (profiles/r01_tune_shapes.txt); latency is hidden by the 4
   // warps per scheduler rather than by a second slot per warp
   const Shape sh = tune_shape(BWD, Shape{1, 16});
-  if (sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256>(a, sh.warps, st);
-  return launch_tiled_shape<MC, LPP, BWD, 1, 512>(a, sh.warps, st);
+  if (sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256>(a, sh.warps, st, plan);
+  return launch_tiled_shape<MC, LPP, BWD, 1, 512>(a, sh.warps, st, plan);
 }
 
 template <bool BWD>
-static int launch_modl(ModlArgs a, cudaStream_t st) {
+static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   switch (a.M) {
     case 5:
-      return launch_tiled<5, 1, BWD>(a, st);
+      return launch_tiled<5, 1, BWD>(a, st, plan);
     case 10:
-      return launch_tiled<10, 1, BWD>(a, st);
+      return launch_tiled<10, 1, BWD>(a, st, plan);
     case 20:
-      return launch_tiled<10, 2, BWD>(a, st);
+      return launch_tiled<10, 2, BWD>(a, st, plan);
     case 30:
-      return launch_tiled<10, 3, BWD>(a, st);
+      return launch_tiled<10, 3, BWD>(a, st, plan);
     default: {
       const DeviceInfo& di = device_info();
       long long blocks = (a.n_px + 127) / 128;
@@ -809,6 +967,8 @@ static int launch_modl(ModlArgs a, cudaStream_t st) {
     }
   }
 }
+
+static size_t partial_elems(long long n_img) { return static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 1; }
 
 static int tile_ppt(int M) {
   switch (M) {
@@ -843,21 +1003,31 @@ using namespace vaemdl;
 
 extern "C" size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W) {
   if (n_img <= 0 || H <= 0 || W <= 0) return 0;
-  // two float64 per tile at the smallest tile size (10 pixels) -- an upper bound for every M
-  const long long n_px = n_img * H * W;
-  size_t bytes = static_cast<size_t>((n_px + 9) / 10) * 2 * sizeof(double);
-  const size_t acc = static_cast<size_t>(n_img) * sizeof(double);  // atomic path: one float64 accumulator per image
-  return (bytes > acc ? bytes : acc) + 256;
+  // one float64 partial per (forward warp, image its run of tiles touches): at most n_img + 3 * warps + 1 of them
+  // (also covers the atomic path's one accumulator per image); + the fused finish kernel's block sums / the unfused
+  // tail's per-image scratch (n_img) and the arrival counter
+  (void)H;
+  (void)W;
+  return partial_elems(n_img) * sizeof(double) + static_cast<size_t>(n_img) * sizeof(double) + 256;
 }
 
-extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
-                               long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
-                               double* ll_image_f64, void* workspace, size_t workspace_bytes, void* stream) {
+namespace vaemdl {
+struct IwaeOut {  // outputs of the fused finish (all nullable); used when S > 0
+  int S = 0;
+  long long B = 0, B_total = 0;
+  const float* extra = nullptr;
+  float *log_w = nullptr, *lme_b = nullptr, *elbo = nullptr, *g_ll = nullptr;
+};
+
+static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
+                         int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image, double* ll_image_f64,
+                         const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
-  if (!lp_pixel && !ll_image && !ll_image_f64) return VAEMDL_EINVAL;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool want_ll = ll_image || ll_image_f64;
+  const bool iwae = iw.S > 0;
+  if (!lp_pixel && !ll_image && !ll_image_f64 && !iwae) return VAEMDL_EINVAL;
+  if (iwae && static_cast<long long>(iw.S) * iw.B != n_img) return VAEMDL_EINVAL;
+  const bool want_ll = ll_image || ll_image_f64 || iwae;
   ModlArgs a{};
   a.params = params;
   a.x = x;
@@ -871,32 +1041,97 @@ extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, 
   a.M = M;
   const int ppt = tile_ppt(M);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
+  // fused finish: one block owns BB batch elements x all S samples (a thread per image, then a warp per batch
+  // element), which only pays while S is small; the 5000-sample evaluation shape takes the grid-parallel route below
+  int BB = 32;
+  while (iwae && BB > 1 && static_cast<long long>(BB) * iw.S > 512) BB >>= 1;
+  const bool fused = iwae && use_partials && static_cast<long long>(BB) * iw.S <= 512;
+  char* ws = static_cast<char*>(workspace);
+  size_t tail_off = 0;
   if (want_ll) {
-    if (!workspace || workspace_bytes < vaemdl_modl_workspace_bytes(n_img, H, W)) return VAEMDL_EWORKSPACE;
+    const size_t need = vaemdl_modl_workspace_bytes(n_img, H, W);
+    if (!workspace || workspace_bytes < need) return VAEMDL_EWORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
+    tail_off = partial_elems(n_img) * sizeof(double);
     if (use_partials) {
-      a.partial = static_cast<double*>(workspace);
+      a.partial = reinterpret_cast<double*>(ws);
     } else {
-      a.ll_atomic = ll_image_f64 ? ll_image_f64 : static_cast<double*>(workspace);
+      a.ll_atomic = ll_image_f64 ? ll_image_f64 : reinterpret_cast<double*>(ws);
       cudaError_t e = cudaMemsetAsync(a.ll_atomic, 0, sizeof(double) * n_img, st);
       if (e != cudaSuccess) return cuda_rc(e);
     }
   }
-  rc = launch_modl<false>(a, st);
+  unsigned* counter = want_ll ? reinterpret_cast<unsigned*>(ws + tail_off + static_cast<size_t>(n_img) * sizeof(double)) : nullptr;
+  if (fused && iw.elbo) a.zero_me = counter;
+  TilePlan plan;
+  rc = launch_modl<false>(a, st, &plan);
   if (rc) return rc;
+  PartialGeom geom{a.partial, plan.tw_base, plan.tw_rem, plan.K, plan.PPT, a.HW};
+  if (use_partials && static_cast<size_t>(plan.total_warps) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+  if (fused) {
+    FinishArgs f{};
+    f.geom = geom;
+    f.extra = iw.extra;
+    f.ll = ll_image;
+    f.ll64 = ll_image_f64;
+    f.log_w = iw.log_w;
+    f.lme_b = iw.lme_b;
+    f.elbo = iw.elbo;
+    f.g_ll = iw.g_ll;
+    f.block_sums = reinterpret_cast<double*>(ws + tail_off);
+    f.counter = counter;
+    f.B = iw.B;
+    f.S = iw.S;
+    f.BB = BB;
+    f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
+    const long long grid = (iw.B + BB - 1) / BB;
+    modl_finish_kernel<<<static_cast<unsigned>(grid), kFinishThreads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
+    return cuda_rc(cudaGetLastError());
+  }
+  double* ll64_src = ll_image_f64;
   if (use_partials) {
-    const long long threads = n_img * 32;
-    const int block = 256;
-    const long long grid = (threads + block - 1) / block;
-    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(a.partial, ll_image, ll_image_f64, n_img,
-                                                                               a.HW, ppt);
-    return cuda_rc(cudaGetLastError());
+    if (iwae && !ll64_src) ll64_src = reinterpret_cast<double*>(ws + tail_off);  // scratch [n_img] for the unfused tail
+    const int block = 128;
+    const long long grid = (n_img + block - 1) / block;
+    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(geom, ll_image, ll64_src, n_img);
+    rc = cuda_rc(cudaGetLastError());
+  } else if (want_ll) {
+    ll64_src = a.ll_atomic;
+    if (ll_image) {
+      cast_f64_f32_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
+      rc = cuda_rc(cudaGetLastError());
+    }
   }
-  if (want_ll && ll_image) {
-    cast_f64_f32_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
-    return cuda_rc(cudaGetLastError());
-  }
-  return VAEMDL_OK;
+  if (rc || !iwae) return rc;
+  // unfused IWAE tail (any-M kernel, tiny images, or more than 512 importance samples)
+  return vaemdl_iwae_tail(nullptr, ll64_src, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+}
+}  // namespace vaemdl
+
+extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                               long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
+                               double* ll_image_f64, void* workspace, size_t workspace_bytes, void* stream) {
+  return modl_fwd_impl(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, lp_pixel, ll_image, ll_image_f64,
+                       IwaeOut{}, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vaemdl_modl_iwae_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
+                                    long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
+                                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo,
+                                    float* g_ll, void* workspace, size_t workspace_bytes, void* stream) {
+  if (S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
+  if (elbo && !lme_b) return VAEMDL_EINVAL;
+  IwaeOut iw;
+  iw.S = S;
+  iw.B = B;
+  iw.B_total = B_total;
+  iw.extra = extra;
+  iw.log_w = log_w;
+  iw.lme_b = lme_b;
+  iw.elbo = elbo;
+  iw.g_ll = g_ll;
+  return modl_fwd_impl(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
+                       ll_image, ll_image_f64, iw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,

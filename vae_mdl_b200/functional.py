@@ -17,6 +17,7 @@ __all__ = [
     "modl_log_prob",
     "modl_log_likelihood",
     "modl_backward",
+    "modl_iwae_forward",
     "dlogistic_log_prob",
     "dlogistic_log_likelihood",
     "logmeanexp",
@@ -115,6 +116,38 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
         check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
                                     ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
     return dp
+
+
+def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: int = 0,
+                      x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL):
+    """MoDL forward fused with the IWAE tail in TWO launches (``vaemdl_modl_iwae_fwd``): ``params [S,B,H,W,10M]``,
+    ``x [B,H,W,3]``, ``extra = beta*(lpz-lqzx) [S,B]`` or None.  Returns ``(lpxz float64 [S,B], log_w, lme_b [B],
+    elbo [1], g_ll [S,B])`` with ``g_ll = d(-elbo)/d lpxz`` (models/loss.py:32-37).  Not recorded by autograd."""
+    p = dense_f32(params, "parameters")
+    if p.dim() != 5:
+        raise ValueError("parameters must be [S, B, H, W, 10*n_mix]")
+    S, B, H, W, C10 = p.shape
+    M = C10 // 10
+    if C10 != 10 * M or M < 1:
+        raise ValueError(f"last parameter dim must be 10*n_mix, got {C10}")
+    xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
+    if x_batch not in (1, B):
+        raise ValueError(f"x must hold {B} images (or one), got {x_batch}")
+    ex = dense_f32(extra, "extra").reshape(S, B) if extra is not None else None
+    L = lib()
+    dev = p.device
+    ll64 = torch.empty((S, B), device=dev, dtype=torch.float64)
+    log_w = torch.empty((S, B), device=dev, dtype=torch.float32)
+    lme_b = torch.empty(B, device=dev, dtype=torch.float32)
+    elbo = torch.empty(1, device=dev, dtype=torch.float32)
+    g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
+    ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
+    ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(L.vaemdl_modl_iwae_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
+                                     ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
+                                     ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
+    return ll64, log_w, lme_b, elbo, g_ll
 
 
 def modl_log_prob(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,

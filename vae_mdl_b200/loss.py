@@ -89,8 +89,9 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
 
 def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True,
                    b_total: int = 0):
-    """The whole observation-model side of one IWAE step in 3 (+2 tiny) kernel launches, no autograd graph:
-    per-image MoDL log-likelihood (float64 sums) -> fused IWAE tail (log-mean-exp, elbo, softmax weights) -> MoDL gradient.
+    """The whole observation-model side of one IWAE step in 3 kernel launches, no autograd graph:
+    MoDL forward (tile partial sums, float64) -> fused finish (per-image sums, log-mean-exp, elbo, softmax weights)
+    -> MoDL gradient.
 
     ``params [S,B,H,W,10M]``, ``x [B,H,W,3]`` (uint8 or float in [0,1]), ``extra = beta*(lpz-lqzx) [S,B]`` or None.
     ``b_total``: whole-batch size when ``params`` is one rank's batch shard (the returned loss is then this rank's
@@ -98,8 +99,6 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = 
     Returns ``(loss=-elbo [1], lpxz [S,B] float64, dparams or None)`` -- the numbers ``iwae_loss`` + ``backward`` give.
     """
     with torch.no_grad():
-        lpxz = F.modl_log_likelihood(params, x, dtype=torch.float64)
-        S = lpxz.shape[0]
-        _, _, elbo, g_ll = F.iwae_tail(lpxz.reshape(S, -1), None if extra is None else extra.reshape(S, -1), b_total)
-        dparams = F.modl_backward(params, x, g_image=g_ll.reshape(lpxz.shape)) if need_grad else None
+        lpxz, _, _, elbo, g_ll = F.modl_iwae_forward(params, x, extra, b_total)
+        dparams = F.modl_backward(params, x, g_image=g_ll) if need_grad else None
     return -elbo, lpxz, dparams
