@@ -306,12 +306,28 @@ def also_workloads(dev, peak):
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / iters * 1e-3
 
+    def time_as_graph(fn_with_stream, iters):
+        """The same launches captured once into a CUDA graph and replayed (the C-ABI calls only enqueue on the stream
+        they are given, so they capture as they are): removes the host's per-launch cost from launch-bound shapes."""
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn_with_stream(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        return timeit(g.replay, iters)
+
     for name in ["cfg1", "cfg1_m5", "cfg5_64_m30", "cfg5_128_m10"]:
         _, S, B, H, W, M = WORKLOADS[name]
         st = ModlStep(S, B, H, W, M, dev, 7, B)
         t = timeit(st.step, 20)
         out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6,
                      "algorithmic_GBs": st.n_px * 120 * M / t / 1e9, "frac_of_hbm_peak": st.n_px * 120 * M / t / 1e9 / peak}
+        if name.startswith("cfg1"):
+            def on_stream(sp, st=st):
+                keep, st.st = st.st, sp
+                st.step()
+                st.st = keep
+            tg = time_as_graph(on_stream, 50)
+            out[name]["cuda_graph_us_per_step"] = tg * 1e6
+            out[name]["cuda_graph_frac_of_hbm_peak"] = st.n_px * 120 * M / tg / 1e9 / peak
         del st
     # config 2: plain discretized logistic fwd + IWAE tail + bwd, S=5 x B=128, 32x32x3 (models/model03.py shapes),
     # raw C-ABI calls on preallocated buffers; the un-split [..,6] conv output is read in place (ld = 6)
@@ -334,19 +350,21 @@ def also_workloads(dev, peak):
     p_loc, p_ls = both.data_ptr(), both.data_ptr() + 12
     d_loc, d_ls = dboth.data_ptr(), dboth.data_ptr() + 12
 
-    def dl_step():
-        rc = L.vaemdl_dlogistic_fwd(p_loc, p_ls, 3, 6, x.data_ptr(), 1, S * B, B, D, 0.0, 1.0, 256.0, None, None,
-                                    ll64.data_ptr(), ws.data_ptr(), wsb, st)
-        rc |= L.vaemdl_iwae_tail(None, ll64.data_ptr(), None, S, B, 0, None, lme.data_ptr(), elbo.data_ptr(),
-                                 g_ll.data_ptr(), st)
+    def dl_step(sp=st):
+        rc = L.vaemdl_dlogistic_iwae_fwd(p_loc, p_ls, 3, 6, x.data_ptr(), 1, S, B, 0, B, D, 0.0, 1.0, 256.0, None, None,
+                                         ll64.data_ptr(), None, lme.data_ptr(), elbo.data_ptr(), g_ll.data_ptr(),
+                                         ws.data_ptr(), wsb, sp)
         rc |= L.vaemdl_dlogistic_bwd(p_loc, p_ls, 3, 6, x.data_ptr(), 1, S * B, B, D, 0.0, 1.0, 256.0, g_ll.data_ptr(),
-                                     None, d_loc, d_ls, 6, st)
+                                     None, d_loc, d_ls, 6, sp)
         assert rc == 0, rc
 
     t = timeit(dl_step, 50)
+    tg = time_as_graph(dl_step, 100)
     n_sub = S * B * H * W
-    out["cfg2_dl_fwd_tail_bwd"] = {"us_per_step": t * 1e6, "px_samples_per_s": n_sub / t,
-                                   "algorithmic_GBs": n_sub * 72 / t / 1e9, "frac_of_hbm_peak": n_sub * 72 / t / 1e9 / peak}
+    out["cfg2_dl_fwd_finish_bwd"] = {"us_per_step": t * 1e6, "px_samples_per_s": n_sub / t, "launches_per_step": 3,
+                                     "algorithmic_GBs": n_sub * 72 / t / 1e9, "frac_of_hbm_peak": n_sub * 72 / t / 1e9 / peak,
+                                     "cuda_graph_us_per_step": tg * 1e6,
+                                     "cuda_graph_frac_of_hbm_peak": n_sub * 72 / tg / 1e9 / peak}
     # config 3: sampling from supplied uniforms, reduced to 2,000 images here (10,000 in BASELINE)
     N, M = 2000, 10
     l = torch.randn(N, 32, 32, 10 * M, device=dev, generator=gen)

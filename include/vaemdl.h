@@ -144,6 +144,15 @@ VAEMDL_API int vaemdl_dlogistic_fwd(const float* loc, const float* logscale, int
                          float* lp_elem, float* ll_image, double* ll_image_f64,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Plain discretized logistic forward fused with the IWAE tail (model03/04/06 loss: models/loss.py:32-37,
+ * models/model06.py:45-50): same outputs and launch count as vaemdl_modl_iwae_fwd. loc/logscale [S,B,..] addressed as
+ * above with n_img = S*B; extra [S,B] nullable (= every other term of log_w). */
+VAEMDL_API int vaemdl_dlogistic_iwae_fwd(const float* loc, const float* logscale, int C, int ld,
+                         const void* x, int x_dtype, int S, long long B, long long B_total, int x_batch, long long D,
+                         float low, float high, float levels, const float* extra,
+                         float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* dloc / dlogscale use the same (C, ld_out) addressing as loc / logscale. */
 VAEMDL_API int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int C, int ld,
                          const void* x, int x_dtype, long long n_img, int x_batch, long long D,

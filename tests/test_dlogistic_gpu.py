@@ -96,3 +96,34 @@ def test_sample_explicit_noise(V):
     assert (out.cpu().double() - want).abs().max().item() < 1e-6
     assert d.sample().shape == (4, 8, 8, 3) and d.sample([2]).shape == (2, 4, 8, 8, 3)
     assert d.mean() is d.loc
+
+
+@pytest.mark.parametrize("S,B,H,W,split,b_total", [(5, 8, 32, 32, True, 0), (3, 5, 8, 8, False, 0), (16, 3, 4, 4, True, 12),
+                                                    (700, 2, 4, 4, False, 0), (4, 3, 2, 2, True, 0)])
+def test_fused_iwae_step_matches_oracle(V, S, B, H, W, split, b_total):
+    """vaemdl_dlogistic_iwae_fwd + vaemdl_dlogistic_bwd against models/loss.py:32-37 on the model03 head, float64 oracle."""
+    g = torch.Generator().manual_seed(S * 7 + B)
+    both = torch.randn(S, B, H, W, 6, generator=g)
+    both[..., :3] = torch.rand(S, B, H, W, 3, generator=g)
+    both[..., 3:] -= 1.5
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    b64 = both.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    lp64 = O.dlogistic_log_prob(x64, b64[..., :3], b64[..., 3:], 0.0, 1.0, 256.0)
+    ll64 = lp64.sum((-1, -2, -3))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()) + torch.randn(S, B, generator=g).double()
+    loss64 = -O.logmeanexp(ll64 + extra, 0).sum() / (b_total or B)
+    loss64.backward()
+    bd = both.to(DEV)
+    if split:
+        loc, ls = torch.split(bd, 3, dim=-1)          # read in place (ld = 6)
+    else:
+        loc, ls = bd[..., :3].contiguous(), bd[..., 3:].contiguous()
+    loss, lpxz, dloc, dls = V.dlogistic_iwae_step(loc, ls, x_u8.to(DEV), extra.float().to(DEV), 0.0, 1.0, 256.0,
+                                                   b_total=b_total)
+    assert_ll_close(lpxz, ll64.detach())
+    assert abs(loss.item() - loss64.item()) <= 1e-5 * abs(loss64.item())
+    assert relnorm(dloc, b64.grad[..., :3]) < GRAD_RTOL
+    assert relnorm(dls, b64.grad[..., 3:]) < GRAD_RTOL
+    if split:
+        assert dls.data_ptr() == dloc.data_ptr() + 12  # one [..,6] gradient buffer, like the un-split input

@@ -6,7 +6,7 @@ there is no CPU or pure-PyTorch fallback -- a missing library or a CPU tensor ra
 """
 from . import _abi
 from .discretized_logistic import DiscretizedLogistic
-from .loss import elbo_loss, iwae_loss, loss_fn, modl_iwae_step
+from .loss import dlogistic_iwae_step, elbo_loss, iwae_loss, loss_fn, modl_iwae_step
 from .mdl import MixtureDiscretizedLogistic
 from .mdl_openai import (MixtureDiscretizedLogisticOpenai, discretized_mix_logistic_loss, int_shape,
                          log_prob_from_logits, log_sum_exp, sample_from_discretized_mix_logistic)
@@ -30,4 +30,5 @@ __all__ = [
     "elbo_loss",
     "loss_fn",
     "modl_iwae_step",
+    "dlogistic_iwae_step",
 ]

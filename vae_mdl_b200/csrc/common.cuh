@@ -123,6 +123,29 @@ struct DeviceInfo {
 };
 const DeviceInfo& device_info();  // cached per current device (api_misc.cu)
 
+// ---- per-image sums of a forward kernel whose warps own runs of consecutive tiles (finish.cu) -------------------------------
+// Warp w of the forward grid owned tiles [w*tw_base + min(w, tw_rem), + tw_base + (w < tw_rem)) of PPT rows each and left
+// one float64 partial per image its run touched at partial[w*K + (n - first image of the run)]; HW = rows per image.
+constexpr long long kMaxGridWarps = 8192;  // bound on (CTAs x warps) of such a grid: sizes the partial-sum workspace
+inline size_t partial_elems(long long n_img) { return static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 1; }
+struct PartialGeom {
+  const double* partial;
+  long long tw_base, tw_rem;
+  int K, PPT;
+  long long HW;
+};
+struct IwaeOut {  // outputs of the fused IWAE finish (all nullable); active when S > 0
+  int S = 0;
+  long long B = 0, B_total = 0;
+  const float* extra = nullptr;
+  float *log_w = nullptr, *lme_b = nullptr, *elbo = nullptr, *g_ll = nullptr;
+};
+// ll / ll64 [n_img] nullable.  iw.S == 0: one reduction launch.  Otherwise also log_w, log-mean-exp, elbo and
+// g_ll = d(-elbo)/d ll: ONE fused launch when S <= 512, else reduction + IWAE tail.  scratch: n_img doubles;
+// counter: a zeroed word (the forward kernel clears it).
+int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll64, const IwaeOut& iw, double* scratch,
+                    unsigned* counter, cudaStream_t st);
+
 // iwae.cu: fused IWAE tail with an explicit batch normaliser
 int iwae_tail_norm(const float* ll, const double* ll64, const float* extra, int S, long long B, float b_norm,
                    float* log_w, float* lme_b, float* g_ll, cudaStream_t st);

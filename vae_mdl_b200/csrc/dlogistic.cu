@@ -17,7 +17,10 @@ struct DlArgs {
   const float* logscale;
   const void* x;
   float* lp_elem;
-  double* partial;    // [n_tiles][2] float64
+  double* partial;    // [total_warps][K] float64: one partial per (warp, image its run of tiles touches)
+  unsigned* zero_me;  // nullable: a word the forward kernel clears for the fused finish kernel that follows it
+  long long tw_base, tw_rem;  // warp w owns tiles [w*tw_base + min(w, tw_rem), + tw_base + (w < tw_rem))
+  int K;
   double* ll_atomic;  // [n_img] float64 accumulators
   const float* g_image;
   const float* g_elem;
@@ -102,11 +105,16 @@ __device__ __forceinline__ double dl_warp_sum(double v) {
 // One thread per row of CPT channels (CPT = 3 for images, 1 for anything else); one warp = 32 consecutive rows.
 template <int CPT, bool BWD>
 __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
-  const long long warps_total = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long long n_tiles = (a.n_rows + 31) / 32;
-  for (long long t = gw; t < n_tiles; t += warps_total) {
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  // a run of consecutive 32-row tiles per warp: per-image sums stay in registers until the warp leaves the image
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+  double acc0 = 0.0, acc1 = 0.0;
+  const long long n_warp_first = (t_begin * 32) / a.rows_per_img;
+  long long n_base = n_warp_first;
+  for (long long t = t_begin; t < t_end; ++t) {
     const long long r_raw = t * 32 + lane;
     const bool active = r_raw < a.n_rows;
     const long long r = active ? r_raw : t * 32;
@@ -153,15 +161,31 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
     if constexpr (!BWD) {
       const float val = active ? acc : 0.0f;
       if (a.partial) {
+        // a tile holds rows of at most two images (rows_per_img >= 32 on this route)
         const long long n_first = __shfl_sync(kFull, n, 0);
-        const double s0 = dl_warp_sum(n == n_first ? static_cast<double>(val) : 0.0);
-        const double s1 = dl_warp_sum(n == n_first ? 0.0 : static_cast<double>(val));
-        if (lane == 0) {
-          a.partial[2 * t] = s0;
-          a.partial[2 * t + 1] = s1;
+        while (n_base < n_first) {
+          const double done = dl_warp_sum(acc0);
+          if (lane == 0) a.partial[gw * a.K + (n_base - n_warp_first)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
         }
+        if (n == n_base)
+          acc0 += static_cast<double>(val);
+        else
+          acc1 += static_cast<double>(val);
       } else if (a.ll_atomic && active) {
         atomicAdd(a.ll_atomic + n, static_cast<double>(val));
+      }
+    }
+  }
+  if constexpr (!BWD) {
+    if (a.partial && t_begin < t_end) {
+      const long long n_last = (t_end * 32 < a.n_rows ? t_end * 32 - 1 : a.n_rows - 1) / a.rows_per_img;
+      const double d0 = dl_warp_sum(acc0), d1 = dl_warp_sum(acc1);
+      if (lane == 0) {
+        a.partial[gw * a.K + (n_base - n_warp_first)] = d0;
+        if (n_base + 1 <= n_last) a.partial[gw * a.K + (n_base + 1 - n_warp_first)] = d1;
       }
     }
   }
@@ -170,25 +194,6 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
 __global__ void dl_cast_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(in[i]);
-}
-
-__global__ void dl_reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ ll_image,
-                                          double* __restrict__ ll_image_f64, long long n_img, long long rows_per_img) {
-  const long long n = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= n_img) return;
-  const long long first = n * rows_per_img, last = first + rows_per_img - 1;
-  const long long t_lo = first / 32, t_hi = last / 32;
-  double acc = 0.0;
-  for (long long t = t_lo + lane; t <= t_hi; t += 32) {
-    const long long n0 = (t * 32) / rows_per_img;
-    acc += (n0 == n) ? partial[2 * t] : partial[2 * t + 1];
-  }
-  acc = dl_warp_sum(acc);
-  if (lane == 0) {
-    if (ll_image) ll_image[n] = static_cast<float>(acc);
-    if (ll_image_f64) ll_image_f64[n] = acc;
-  }
 }
 
 // sampler: clip(loc + exp(ls) * (log u - log(1-u)), low, high) in float64   (utils/discretized_logistic.py:80-85)
@@ -234,13 +239,19 @@ static int dl_fill(DlArgs& a, const float* loc, const float* logscale, int C, in
 }
 
 template <bool BWD>
-static int dl_launch(const DlArgs& a, int cpt, cudaStream_t st) {
+static int dl_launch(DlArgs a, int cpt, cudaStream_t st, PartialGeom* geom = nullptr) {
   const DeviceInfo& di = device_info();
   const long long n_tiles = (a.n_rows + 31) / 32;
   long long blocks = (n_tiles + 7) / 8;
-  const long long cap = static_cast<long long>(di.sm_count) * 8;
+  long long cap = static_cast<long long>(di.sm_count) * 8;
+  if (cap * 8 > kMaxGridWarps) cap = kMaxGridWarps / 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  const long long total_warps = blocks * 8;
+  a.tw_base = n_tiles / total_warps;
+  a.tw_rem = n_tiles % total_warps;
+  a.K = static_cast<int>(((a.tw_base + (a.tw_rem ? 1 : 0)) * 32 + a.rows_per_img - 1) / a.rows_per_img + 1);
+  if (geom) *geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, 32, a.rows_per_img};
   if (cpt == 3)
     dl_kernel<3, BWD><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
   else
@@ -254,49 +265,83 @@ using namespace vaemdl;
 
 extern "C" size_t vaemdl_dlogistic_workspace_bytes(long long n_img, long long D) {
   if (n_img <= 0 || D <= 0) return 0;
-  const size_t bytes = static_cast<size_t>((n_img * D + 31) / 32) * 2 * sizeof(double);
-  const size_t acc = static_cast<size_t>(n_img) * sizeof(double);
-  return (bytes > acc ? bytes : acc) + 256;
+  // per-(warp, image) partials (also covers the atomic route's one accumulator per image) + the finish kernel's
+  // block sums / per-image scratch + the arrival counter
+  return partial_elems(n_img) * sizeof(double) + static_cast<size_t>(n_img) * sizeof(double) + 256;
 }
+
+namespace vaemdl {
+static int dl_fwd_impl(const float* loc, const float* logscale, int C, int ld, const void* x, int x_dtype,
+                       long long n_img, int x_batch, long long D, float low, float high, float levels, float* lp_elem,
+                       float* ll_image, double* ll_image_f64, const IwaeOut& iw, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
+  DlArgs a{};
+  int cpt = 1;
+  int rc = dl_fill(a, loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, cpt);
+  if (rc) return rc;
+  const bool iwae = iw.S > 0;
+  if (iwae && static_cast<long long>(iw.S) * iw.B != n_img) return VAEMDL_EINVAL;
+  const bool want_ll = ll_image || ll_image_f64 || iwae;
+  if (!lp_elem && !want_ll) return VAEMDL_EINVAL;
+  a.lp_elem = lp_elem;
+  const bool use_partials = want_ll && a.rows_per_img >= 32;
+  char* ws = static_cast<char*>(workspace);
+  const size_t tail_off = partial_elems(n_img) * sizeof(double);
+  unsigned* counter = nullptr;
+  if (want_ll) {
+    if (!workspace || workspace_bytes < vaemdl_dlogistic_workspace_bytes(n_img, D)) return VAEMDL_EWORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
+    counter = reinterpret_cast<unsigned*>(ws + tail_off + static_cast<size_t>(n_img) * sizeof(double));
+    if (use_partials) {
+      a.partial = reinterpret_cast<double*>(ws);
+      if (iwae && iw.elbo) a.zero_me = counter;
+    } else {
+      a.ll_atomic = ll_image_f64 ? ll_image_f64 : reinterpret_cast<double*>(ws);
+      cudaError_t e = cudaMemsetAsync(a.ll_atomic, 0, sizeof(double) * n_img, st);
+      if (e != cudaSuccess) return cuda_rc(e);
+    }
+  }
+  PartialGeom geom{};
+  rc = dl_launch<false>(a, cpt, st, &geom);
+  if (rc) return rc;
+  if (use_partials)
+    return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
+  if (!want_ll) return VAEMDL_OK;
+  if (ll_image) {
+    dl_cast_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
+    rc = cuda_rc(cudaGetLastError());
+  }
+  if (rc || !iwae) return rc;
+  return vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+}
+}  // namespace vaemdl
 
 extern "C" int vaemdl_dlogistic_fwd(const float* loc, const float* logscale, int C, int ld, const void* x, int x_dtype,
                                     long long n_img, int x_batch, long long D, float low, float high, float levels,
                                     float* lp_elem, float* ll_image, double* ll_image_f64, void* workspace,
                                     size_t workspace_bytes, void* stream) {
-  DlArgs a{};
-  int cpt = 1;
-  int rc = dl_fill(a, loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, cpt);
-  if (rc) return rc;
-  const bool want_ll = ll_image || ll_image_f64;
-  if (!lp_elem && !want_ll) return VAEMDL_EINVAL;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  a.lp_elem = lp_elem;
-  const bool use_partials = want_ll && a.rows_per_img >= 32;
-  if (want_ll) {
-    if (!workspace || workspace_bytes < vaemdl_dlogistic_workspace_bytes(n_img, D)) return VAEMDL_EWORKSPACE;
-    if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
-    if (use_partials) {
-      a.partial = static_cast<double*>(workspace);
-    } else {
-      a.ll_atomic = ll_image_f64 ? ll_image_f64 : static_cast<double*>(workspace);
-      cudaError_t e = cudaMemsetAsync(a.ll_atomic, 0, sizeof(double) * n_img, st);
-      if (e != cudaSuccess) return cuda_rc(e);
-    }
-  }
-  rc = dl_launch<false>(a, cpt, st);
-  if (rc) return rc;
-  if (use_partials) {
-    const long long threads = n_img * 32;
-    dl_reduce_partials_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(a.partial, ll_image,
-                                                                                           ll_image_f64, n_img,
-                                                                                           a.rows_per_img);
-    return cuda_rc(cudaGetLastError());
-  }
-  if (want_ll && ll_image) {
-    dl_cast_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
-    return cuda_rc(cudaGetLastError());
-  }
-  return VAEMDL_OK;
+  return dl_fwd_impl(loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, lp_elem, ll_image,
+                     ll_image_f64, IwaeOut{}, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vaemdl_dlogistic_iwae_fwd(const float* loc, const float* logscale, int C, int ld, const void* x,
+                                         int x_dtype, int S, long long B, long long B_total, int x_batch, long long D,
+                                         float low, float high, float levels, const float* extra, float* ll_image,
+                                         double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
+  if (elbo && !lme_b) return VAEMDL_EINVAL;
+  IwaeOut iw;
+  iw.S = S;
+  iw.B = B;
+  iw.B_total = B_total;
+  iw.extra = extra;
+  iw.log_w = log_w;
+  iw.lme_b = lme_b;
+  iw.elbo = elbo;
+  iw.g_ll = g_ll;
+  return dl_fwd_impl(loc, logscale, C, ld, x, x_dtype, static_cast<long long>(S) * B, x_batch, D, low, high, levels,
+                     nullptr, ll_image, ll_image_f64, iw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int C, int ld, const void* x, int x_dtype,

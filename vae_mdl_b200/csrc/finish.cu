@@ -1,0 +1,170 @@
+// finish.cu -- what follows a forward kernel: per-image sums from the per-warp float64 partials, optionally fused with the
+// IWAE tail (log_w, log-mean-exp over importance samples, batch mean, upstream gradient) in ONE launch.
+//
+// Replaces reduce_sum over [-1,-2,-3] (models/loss.py:32), log_w (:34), logmeanexp over samples (utils/utils.py:9-11),
+// the batch mean (:37) and the gradient -softmax_s(log_w)/B that tf.GradientTape would derive for lpxz.
+// Shared by the MoDL (modl_kernels.cu) and plain discretized-logistic (dlogistic.cu) forward kernels.
+// Every reduction runs in a fixed order: results are bitwise reproducible run to run.
+#include "common.cuh"
+
+namespace vaemdl {
+
+// image n's sum: the partials of the forward warps whose tile runs touched it, in warp order
+template <typename I>
+__device__ __forceinline__ double image_sum_t(const PartialGeom& g, long long n64) {
+  const I n = static_cast<I>(n64), HW = static_cast<I>(g.HW), PPT = static_cast<I>(g.PPT);
+  const I base = static_cast<I>(g.tw_base), rem = static_cast<I>(g.tw_rem), K = static_cast<I>(g.K);
+  const I first = n * HW, last = first + HW - 1;
+  const I t_lo = first / PPT, t_hi = last / PPT;
+  const I cut = rem * (base + 1);
+  const I w_lo = t_lo < cut ? t_lo / (base + 1) : rem + (t_lo - cut) / base;
+  const I w_hi = t_hi < cut ? t_hi / (base + 1) : rem + (t_hi - cut) / base;
+  double acc = 0.0;
+  for (I w0 = w_lo; w0 <= w_hi; w0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // all loads first, then the adds (fixed order)
+      const I w = w0 + j;
+      const I tb = w * base + (w < rem ? w : rem);
+      const I nf = (tb * PPT) / HW;
+      v[j] = (w <= w_hi) ? g.partial[w * K + (n - nf)] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j];
+  }
+  return acc;
+}
+__device__ __forceinline__ double image_sum(const PartialGeom& g, long long n, bool small) {
+  return small ? image_sum_t<unsigned>(g, n) : image_sum_t<long long>(g, n);
+}
+
+__global__ void reduce_partials_kernel(const PartialGeom g, bool small, float* __restrict__ ll_image,
+                                       double* __restrict__ ll_image_f64, long long n_img) {
+  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= n_img) return;
+  const double acc = image_sum(g, n, small);
+  if (ll_image) ll_image[n] = static_cast<float>(acc);
+  if (ll_image_f64) ll_image_f64[n] = acc;
+}
+
+struct FinishArgs {
+  PartialGeom geom;
+  const float* extra;     // [S,B] nullable
+  float* ll;              // [S,B] nullable
+  double* ll64;           // [S,B] nullable
+  float* log_w;           // [S,B] nullable
+  float* lme_b;           // [B] nullable
+  float* elbo;            // [1] nullable
+  float* g_ll;            // [S,B] nullable
+  double* block_sums;     // [gridDim.x]
+  unsigned* counter;      // zero on entry, zero again on exit
+  long long B;
+  int S, BB;
+  float b_norm;
+  bool small;             // 32-bit index arithmetic suffices
+};
+
+constexpr int kFinishThreads = 128;
+
+// A block owns BB consecutive batch elements and all S samples of them: one thread per image, then one warp per batch
+// element, then (for the batch mean) the block that arrives last adds the block sums in block order.
+__global__ void __launch_bounds__(kFinishThreads) finish_kernel(const FinishArgs a) {
+  extern __shared__ double lw[];  // [BB][S]
+  constexpr int NW = kFinishThreads / 32;
+  __shared__ double blk[NW];
+  __shared__ bool is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b0 = static_cast<long long>(blockIdx.x) * a.BB;
+  const int nb = static_cast<int>((a.B - b0) < a.BB ? (a.B - b0) : a.BB);
+  // (1) per-image log-likelihood; consecutive threads take consecutive b of one s
+  for (int img = threadIdx.x; img < a.S * nb; img += kFinishThreads) {
+    const int s = img / nb, bb = img - s * nb;
+    const long long n = static_cast<long long>(s) * a.B + b0 + bb;
+    const double acc = image_sum(a.geom, n, a.small);
+    if (a.ll) a.ll[n] = static_cast<float>(acc);
+    if (a.ll64) a.ll64[n] = acc;
+    const double v = acc + (a.extra ? static_cast<double>(a.extra[n]) : 0.0);  // models/loss.py:34
+    if (a.log_w) a.log_w[n] = static_cast<float>(v);
+    lw[bb * a.S + s] = v;
+  }
+  __syncthreads();
+  // (2) log-mean-exp over the samples of each batch element, one warp per element
+  double wsum = 0.0;
+  for (int bb = warp; bb < nb; bb += NW) {
+    const double* v = lw + bb * a.S;
+    double mx = -INFINITY;
+    for (int s = lane; s < a.S; s += 32) mx = fmax(mx, v[s]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));  // utils/utils.py:10
+    float sm = 0.0f;
+    for (int s = lane; s < a.S; s += 32) sm += expf(static_cast<float>(v[s] - mx));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(kFull, sm, o);
+    const double lme = static_cast<double>(logf(sm / static_cast<float>(a.S))) + mx;  // utils/utils.py:11
+    if (lane == 0 && a.lme_b) a.lme_b[b0 + bb] = static_cast<float>(lme);
+    if (a.g_ll) {
+      const float scale = -1.0f / (sm * a.b_norm);  // d(-mean_b lme_b)/d log_w = -softmax_s / B
+      for (int s = lane; s < a.S; s += 32)
+        a.g_ll[static_cast<long long>(s) * a.B + b0 + bb] = expf(static_cast<float>(v[s] - mx)) * scale;
+    }
+    wsum += lme;  // identical in every lane
+  }
+  // (3) batch mean
+  if (!a.elbo) return;
+  if (lane == 0) blk[warp] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < NW; ++w) t += blk[w];
+    a.block_sums[blockIdx.x] = t;
+    __threadfence();
+    is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(a.block_sums)[i];
+    a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+    *a.counter = 0u;
+  }
+}
+
+int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll64, const IwaeOut& iw, double* scratch,
+                    unsigned* counter, cudaStream_t st) {
+  const bool iwae = iw.S > 0;
+  // 32-bit index arithmetic when every intermediate (row indices, 8 warps past the last one) fits comfortably
+  const bool small = n_img * g.HW < (1ll << 27) && (kMaxGridWarps + 8) * static_cast<long long>(g.K) < (1ll << 31);
+  // the fused finish keeps a block's [BB][S] log-weights in shared memory and walks S with one warp: only pays
+  // while S is small; the 5000-sample evaluation shape takes the grid-parallel route
+  int BB = 1;
+  while (iwae && BB < 32 && static_cast<long long>(2 * BB) * iw.S <= kFinishThreads) BB <<= 1;
+  if (iwae && iw.S <= 512) {
+    FinishArgs f{};
+    f.geom = g;
+    f.extra = iw.extra;
+    f.ll = ll;
+    f.ll64 = ll64;
+    f.log_w = iw.log_w;
+    f.lme_b = iw.lme_b;
+    f.elbo = iw.elbo;
+    f.g_ll = iw.g_ll;
+    f.block_sums = scratch;
+    f.counter = counter;
+    f.B = iw.B;
+    f.S = iw.S;
+    f.BB = BB;
+    f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
+    f.small = small;
+    const long long grid = (iw.B + BB - 1) / BB;
+    finish_kernel<<<static_cast<unsigned>(grid), kFinishThreads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
+    return cuda_rc(cudaGetLastError());
+  }
+  double* ll64_dst = ll64 ? ll64 : (iwae ? scratch : nullptr);
+  reduce_partials_kernel<<<static_cast<unsigned>((n_img + 127) / 128), 128, 0, st>>>(g, small, ll, ll64_dst, n_img);
+  int rc = cuda_rc(cudaGetLastError());
+  if (rc || !iwae) return rc;
+  return vaemdl_iwae_tail(nullptr, ll64_dst, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+}
+
+}  // namespace vaemdl

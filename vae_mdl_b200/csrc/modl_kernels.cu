@@ -426,6 +426,11 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   const int sub = lane % LPP;
   const int m0 = sub * MC;
 
+  // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
+  // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+
   auto tile_rows = [&](long long t) -> int {
     const long long rem = a.n_px - t * PPT;
     return rem < PPT ? static_cast<int>(rem) : PPT;
@@ -447,11 +452,6 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
     }
   };
-
-  // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
-  // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
-  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
-  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
 
   // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below)
 #pragma unroll
@@ -676,122 +676,6 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   }
 }
 
-// ---- per-image sums from the per-warp partials (fixed order => bitwise reproducible) ---------------------------------
-// Warp w of the forward grid owned tiles [w*base + min(w, rem), ...) and left one float64 partial per image its run
-// touched at partial[w*K + (n - first image of the run)].
-struct PartialGeom {
-  const double* partial;
-  long long tw_base, tw_rem;
-  int K, PPT, HW;
-};
-__device__ __forceinline__ double image_sum(const PartialGeom& g, long long n) {
-  const long long first = n * g.HW, last = first + g.HW - 1;
-  const long long t_lo = first / g.PPT, t_hi = last / g.PPT;
-  const long long cut = g.tw_rem * (g.tw_base + 1);
-  const long long w_lo = t_lo < cut ? t_lo / (g.tw_base + 1) : g.tw_rem + (t_lo - cut) / g.tw_base;
-  const long long w_hi = t_hi < cut ? t_hi / (g.tw_base + 1) : g.tw_rem + (t_hi - cut) / g.tw_base;
-  double acc = 0.0;
-  for (long long w = w_lo; w <= w_hi; ++w) {
-    const long long tb = w * g.tw_base + (w < g.tw_rem ? w : g.tw_rem);
-    const long long nf = (tb * g.PPT) / g.HW;
-    acc += g.partial[w * g.K + (n - nf)];
-  }
-  return acc;
-}
-
-__global__ void modl_reduce_partials_kernel(const PartialGeom g, float* __restrict__ ll_image,
-                                            double* __restrict__ ll_image_f64, long long n_img) {
-  const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (n >= n_img) return;
-  const double acc = image_sum(g, n);
-  if (ll_image) ll_image[n] = static_cast<float>(acc);
-  if (ll_image_f64) ll_image_f64[n] = acc;
-}
-
-// ---- fused finish: per-image sums from the partials + IWAE tail + batch mean, ONE launch --------------------------------
-// Replaces reduce_sum over [-1,-2,-3] (models/loss.py:32), log_w (:34), logmeanexp over samples (utils/utils.py:9-11),
-// the batch mean (:37) and the upstream gradient -softmax_s(log_w)/B that tf.GradientTape would derive.
-// A block owns BB consecutive batch elements and all S samples of them (one thread per image, then one warp per batch
-// element); every reduction runs in a fixed order.
-struct FinishArgs {
-  PartialGeom geom;
-  const float* extra;     // [S,B] nullable
-  float* ll;              // [S,B] nullable
-  double* ll64;           // [S,B] nullable
-  float* log_w;           // [S,B] nullable
-  float* lme_b;           // [B] nullable
-  float* elbo;            // [1] nullable
-  float* g_ll;            // [S,B] nullable
-  double* block_sums;     // [gridDim.x]
-  unsigned* counter;      // cleared by the forward kernel
-  long long B;
-  int S, BB;
-  float b_norm;
-};
-
-constexpr int kFinishThreads = 256;
-
-__global__ void __launch_bounds__(kFinishThreads) modl_finish_kernel(const FinishArgs a) {
-  extern __shared__ double lw[];  // [BB][S]
-  __shared__ double blk[kFinishThreads / 32];
-  __shared__ bool is_last;
-  constexpr int NW = kFinishThreads / 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long b0 = static_cast<long long>(blockIdx.x) * a.BB;
-  const int nb = static_cast<int>((a.B - b0) < a.BB ? (a.B - b0) : a.BB);
-  // (1) per-image log-likelihood, one thread per image n = s*B + b (consecutive threads: consecutive b)
-  for (int img = threadIdx.x; img < a.S * nb; img += kFinishThreads) {
-    const int s = img / nb, bb = img - s * nb;
-    const long long n = static_cast<long long>(s) * a.B + b0 + bb;
-    const double acc = image_sum(a.geom, n);
-    if (a.ll) a.ll[n] = static_cast<float>(acc);
-    if (a.ll64) a.ll64[n] = acc;
-    const double v = acc + (a.extra ? static_cast<double>(a.extra[n]) : 0.0);  // models/loss.py:34
-    if (a.log_w) a.log_w[n] = static_cast<float>(v);
-    lw[bb * a.S + s] = v;
-  }
-  __syncthreads();
-  // (2) log-mean-exp over the samples of each batch element, one warp per element
-  double wsum = 0.0;
-  for (int bb = warp; bb < nb; bb += NW) {
-    const double* v = lw + bb * a.S;
-    double mx = -INFINITY;
-    for (int s = lane; s < a.S; s += 32) mx = fmax(mx, v[s]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));  // utils/utils.py:10
-    float sm = 0.0f;
-    for (int s = lane; s < a.S; s += 32) sm += expf(static_cast<float>(v[s] - mx));
-    sm = warp_sum(sm);
-    const double lme = static_cast<double>(logf(sm / static_cast<float>(a.S))) + mx;  // utils/utils.py:11
-    if (lane == 0 && a.lme_b) a.lme_b[b0 + bb] = static_cast<float>(lme);
-    if (a.g_ll) {
-      const float scale = -1.0f / (sm * a.b_norm);  // d(-mean_b lme_b)/d log_w = -softmax_s / B
-      for (int s = lane; s < a.S; s += 32)
-        a.g_ll[static_cast<long long>(s) * a.B + b0 + bb] = expf(static_cast<float>(v[s] - mx)) * scale;
-    }
-    wsum += lme;  // identical in every lane
-  }
-  // (3) batch mean: block partial sums, combined in block order by whichever block finishes last
-  if (!a.elbo) return;
-  if (lane == 0) blk[warp] = wsum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < NW; ++w) t += blk[w];
-    a.block_sums[blockIdx.x] = t;
-    __threadfence();
-    is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0.0;
-    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(a.block_sums)[i];
-    a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
-    *a.counter = 0u;
-  }
-}
-
 __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = static_cast<float>(in[i]);
@@ -877,8 +761,6 @@ static Shape tune_shape(bool bwd, Shape dflt) {
   if (sscanf(p + 4, "%d:%d", &s, &w) == 2 && (s == 1 || s == 2) && w >= 1 && w <= 16) return Shape{s, w};
   return dflt;
 }
-
-constexpr long long kMaxGridWarps = 8192;  // bound on gridDim.x * warps per CTA (sizes the partial-sum workspace)
 
 struct TilePlan {  // how the forward grid split the tile range: what the per-image reduction needs to know
   long long total_warps = 0, tw_base = 0, tw_rem = 0;
@@ -968,8 +850,6 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   }
 }
 
-static size_t partial_elems(long long n_img) { return static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 1; }
-
 static int tile_ppt(int M) {
   switch (M) {
     case 5:
@@ -1012,13 +892,6 @@ extern "C" size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W) {
 }
 
 namespace vaemdl {
-struct IwaeOut {  // outputs of the fused finish (all nullable); used when S > 0
-  int S = 0;
-  long long B = 0, B_total = 0;
-  const float* extra = nullptr;
-  float *log_w = nullptr, *lme_b = nullptr, *elbo = nullptr, *g_ll = nullptr;
-};
-
 static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image, double* ll_image_f64,
                          const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -1041,11 +914,6 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.M = M;
   const int ppt = tile_ppt(M);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
-  // fused finish: one block owns BB batch elements x all S samples (a thread per image, then a warp per batch
-  // element), which only pays while S is small; the 5000-sample evaluation shape takes the grid-parallel route below
-  int BB = 32;
-  while (iwae && BB > 1 && static_cast<long long>(BB) * iw.S > 512) BB >>= 1;
-  const bool fused = iwae && use_partials && static_cast<long long>(BB) * iw.S <= 512;
   char* ws = static_cast<char*>(workspace);
   size_t tail_off = 0;
   if (want_ll) {
@@ -1062,49 +930,23 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
     }
   }
   unsigned* counter = want_ll ? reinterpret_cast<unsigned*>(ws + tail_off + static_cast<size_t>(n_img) * sizeof(double)) : nullptr;
-  if (fused && iw.elbo) a.zero_me = counter;
+  if (iwae && use_partials && iw.elbo) a.zero_me = counter;
   TilePlan plan;
   rc = launch_modl<false>(a, st, &plan);
   if (rc) return rc;
-  PartialGeom geom{a.partial, plan.tw_base, plan.tw_rem, plan.K, plan.PPT, a.HW};
-  if (use_partials && static_cast<size_t>(plan.total_warps) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
-  if (fused) {
-    FinishArgs f{};
-    f.geom = geom;
-    f.extra = iw.extra;
-    f.ll = ll_image;
-    f.ll64 = ll_image_f64;
-    f.log_w = iw.log_w;
-    f.lme_b = iw.lme_b;
-    f.elbo = iw.elbo;
-    f.g_ll = iw.g_ll;
-    f.block_sums = reinterpret_cast<double*>(ws + tail_off);
-    f.counter = counter;
-    f.B = iw.B;
-    f.S = iw.S;
-    f.BB = BB;
-    f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
-    const long long grid = (iw.B + BB - 1) / BB;
-    modl_finish_kernel<<<static_cast<unsigned>(grid), kFinishThreads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
-    return cuda_rc(cudaGetLastError());
-  }
-  double* ll64_src = ll_image_f64;
   if (use_partials) {
-    if (iwae && !ll64_src) ll64_src = reinterpret_cast<double*>(ws + tail_off);  // scratch [n_img] for the unfused tail
-    const int block = 128;
-    const long long grid = (n_img + block - 1) / block;
-    modl_reduce_partials_kernel<<<static_cast<unsigned>(grid), block, 0, st>>>(geom, ll_image, ll64_src, n_img);
+    if (static_cast<size_t>(plan.total_warps) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+    const PartialGeom geom{a.partial, plan.tw_base, plan.tw_rem, plan.K, plan.PPT, a.HW};
+    return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
+  }
+  if (!want_ll) return VAEMDL_OK;
+  // float64 atomics route (any-M kernel, images smaller than a tile)
+  if (ll_image) {
+    cast_f64_f32_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
     rc = cuda_rc(cudaGetLastError());
-  } else if (want_ll) {
-    ll64_src = a.ll_atomic;
-    if (ll_image) {
-      cast_f64_f32_kernel<<<static_cast<unsigned>((n_img + 255) / 256), 256, 0, st>>>(a.ll_atomic, ll_image, n_img);
-      rc = cuda_rc(cudaGetLastError());
-    }
   }
   if (rc || !iwae) return rc;
-  // unfused IWAE tail (any-M kernel, tiny images, or more than 512 importance samples)
-  return vaemdl_iwae_tail(nullptr, ll64_src, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  return vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
 }
 }  // namespace vaemdl
 

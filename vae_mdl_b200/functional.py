@@ -20,6 +20,8 @@ __all__ = [
     "modl_iwae_forward",
     "dlogistic_log_prob",
     "dlogistic_log_likelihood",
+    "dlogistic_iwae_forward",
+    "dlogistic_backward",
     "logmeanexp",
     "iwae_tail",
     "modl_sample",
@@ -259,6 +261,72 @@ def dlogistic_log_likelihood(loc, logscale, x, low=-1.0, high=1.0, levels=256.0,
                              dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """``reduce_sum(log_prob(x), last n_event_dims axes)`` (models/loss.py:32) without the element-wise tensor."""
     return _DlFn.apply(loc, logscale, x, low, high, levels, n_event_dims, "image64" if dtype == torch.float64 else "image")
+
+
+def dlogistic_iwae_forward(loc, logscale, x, extra: Optional[torch.Tensor] = None, low=-1.0, high=1.0, levels=256.0,
+                           b_total: int = 0, n_event_dims: int = 3):
+    """Plain discretized-logistic forward fused with the IWAE tail (``vaemdl_dlogistic_iwae_fwd``, two launches):
+    ``loc``/``logscale`` ``[S, B, *event]``, ``x [B, *event]``, ``extra [S,B]`` = every other term of ``log_w``.
+    Returns ``(lpxz float64 [S,B], log_w, lme_b [B], elbo [1], g_ll [S,B])`` (models/loss.py:32-37, models/model06.py:45-50)."""
+    if loc.shape != logscale.shape:
+        loc, logscale = torch.broadcast_tensors(loc, logscale)
+    _abi.require_cuda(loc, "loc")
+    if loc.dim() != 2 + n_event_dims:
+        raise ValueError("loc must be [S, B, *event]")
+    locd, lsd, C, ld = _dl_layout(loc, logscale)
+    S, B = loc.shape[:2]
+    ev = tuple(loc.shape[2:])
+    D = int(math.prod(ev))
+    xd, x_dtype, x_batch = _prep_x(x, ev, "x")
+    if x_batch not in (1, B):
+        raise ValueError(f"x must hold {B} images (or one), got {x_batch}")
+    ex = dense_f32(extra, "extra").reshape(S, B) if extra is not None else None
+    L = lib()
+    dev = loc.device
+    ll64 = torch.empty((S, B), device=dev, dtype=torch.float64)
+    log_w = torch.empty((S, B), device=dev, dtype=torch.float32)
+    lme_b = torch.empty(B, device=dev, dtype=torch.float32)
+    elbo = torch.empty(1, device=dev, dtype=torch.float32)
+    g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
+    ws_bytes = L.vaemdl_dlogistic_workspace_bytes(S * B, D)
+    ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
+    with torch.cuda.device(dev):
+        check(L.vaemdl_dlogistic_iwae_fwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, S, B, int(b_total), x_batch, D,
+                                          float(low), float(high), float(levels), ptr(ex), None, ptr(ll64), ptr(log_w),
+                                          ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes, stream_ptr(dev)),
+              "vaemdl_dlogistic_iwae_fwd")
+    return ll64, log_w, lme_b, elbo, g_ll
+
+
+def dlogistic_backward(loc, logscale, x, g_image: torch.Tensor, low=-1.0, high=1.0, levels=256.0, n_event_dims: int = 3):
+    """The plain-DL gradient kernel on its own: ``d/d(loc, logscale)`` of ``sum(g_image * ll_image)``.  For the two halves
+    of an un-split ``[..., 2C]`` tensor the two gradients are views of one ``[..., 2C]`` buffer."""
+    if loc.shape != logscale.shape:
+        loc, logscale = torch.broadcast_tensors(loc, logscale)
+    _abi.require_cuda(loc, "loc")
+    locd, lsd, C, ld = _dl_layout(loc, logscale)
+    shape = tuple(loc.shape)
+    ev = shape[len(shape) - n_event_dims:]
+    lead = shape[:len(shape) - n_event_dims]
+    D = int(math.prod(ev))
+    n_img = int(math.prod(lead)) if lead else 1
+    xd, x_dtype, x_batch = _prep_x(x, ev, "x")
+    _check_batch(n_img, x_batch, "backward")
+    gi = dense_f32(g_image, "g_image")
+    if ld == 2 * C:
+        both = torch.empty(shape[:-1] + (2 * C,), device=locd.device, dtype=torch.float32)
+        dloc, dls, ld_out = both[..., :C], both[..., C:], 2 * C
+        p_loc, p_ls = both.data_ptr(), both.data_ptr() + 4 * C
+    else:
+        dloc = torch.empty(shape, device=locd.device, dtype=torch.float32)
+        dls = torch.empty(shape, device=locd.device, dtype=torch.float32)
+        ld_out, p_loc, p_ls = C, dloc.data_ptr(), dls.data_ptr()
+    import ctypes
+    with torch.cuda.device(locd.device):
+        check(lib().vaemdl_dlogistic_bwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D, float(low),
+                                         float(high), float(levels), ptr(gi), None, ctypes.c_void_p(p_loc),
+                                         ctypes.c_void_p(p_ls), ld_out, stream_ptr(locd.device)), "vaemdl_dlogistic_bwd")
+    return dloc, dls
 
 
 # --------------------------------------------------------------------------------------------------

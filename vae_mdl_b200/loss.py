@@ -14,7 +14,7 @@ import torch.distributions as td
 from . import functional as F
 from .utils import logmeanexp
 
-__all__ = ["iwae_loss", "elbo_loss", "loss_fn", "modl_iwae_step"]
+__all__ = ["iwae_loss", "elbo_loss", "loss_fn", "modl_iwae_step", "dlogistic_iwae_step"]
 
 
 def _get_axes(self):
@@ -102,3 +102,16 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = 
         lpxz, _, _, elbo, g_ll = F.modl_iwae_forward(params, x, extra, b_total)
         dparams = F.modl_backward(params, x, g_image=g_ll) if need_grad else None
     return -elbo, lpxz, dparams
+
+
+def dlogistic_iwae_step(loc: torch.Tensor, logscale: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None,
+                        low=-1.0, high=1.0, levels=256.0, need_grad: bool = True, b_total: int = 0):
+    """The plain discretized-logistic counterpart of ``modl_iwae_step`` (models 03/04/06): forward -> fused finish ->
+    gradient, 3 launches.  ``loc``/``logscale [S,B,H,W,3]`` (e.g. the two halves of the ``[..,6]`` conv output,
+    models/model03.py:88-91), ``x [B,H,W,3]``.  Returns ``(loss=-elbo [1], lpxz [S,B] float64, dloc, dlogscale)``."""
+    with torch.no_grad():
+        lpxz, _, _, elbo, g_ll = F.dlogistic_iwae_forward(loc, logscale, x, extra, low, high, levels, b_total)
+        dloc = dls = None
+        if need_grad:
+            dloc, dls = F.dlogistic_backward(loc, logscale, x, g_ll, low, high, levels)
+    return -elbo, lpxz, dloc, dls
