@@ -112,6 +112,35 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+_FULL_AFFINITY = None
+
+
+def bind_near_gpu(index: int):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` (same NUMA node / PCIe root), so that the
+    pinned host buffers of the end-to-end arm are first-touched next to the GPU that DMAs them.  The previous mask is
+    kept for the CPU baseline, which uses every core."""
+    global _FULL_AFFINITY
+    if os.environ.get("VAEMDL_NO_BIND"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        if _FULL_AFFINITY is None:
+            _FULL_AFFINITY = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def unbind():
+    if _FULL_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except Exception:
+            pass
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -148,12 +177,16 @@ class ModlStep:
 
     LAUNCHES_PER_STEP = 3  # modl fwd (tile partials), fused finish (per-image sums + IWAE tail + batch mean), modl bwd
 
-    def __init__(self, S, B, H, W, M, dev, seed, b_total):
+    def __init__(self, S, B, H, W, M, dev, seed, b_total, n_buffers=2):
         from vae_mdl_b200 import _abi
         self.L = _abi.lib()
         self.S, self.B, self.H, self.W, self.M, self.dev, self.b_total = S, B, H, W, M, dev, b_total
         gen = torch.Generator(device=dev).manual_seed(seed)
-        self.params = torch.randn(S, B, H, W, 10 * M, device=dev, generator=gen)          # utils/mdl.py:295
+        # Consecutive steps alternate between n_buffers parameter tensors: the forward kernel of step k+1 must not find
+        # lines of its input in L2 that step k left there (in training every step scores NEW decoder outputs).
+        self.pool = [torch.randn(S, B, H, W, 10 * M, device=dev, generator=gen) for _ in range(n_buffers)]  # utils/mdl.py:295
+        self.k = 0
+        self.params = self.pool[0]
         self.x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=gen)
         self.extra = torch.randn(S, B, device=dev, generator=gen)                          # beta*(lpz - lqzx)
         self.dparams = torch.empty_like(self.params)
@@ -180,7 +213,12 @@ class ModlStep:
                                     self.W, self.M, self.g_ll.data_ptr(), None, self.dparams.data_ptr(), self.st)
         assert rc == 0, rc
 
+    def next_input(self):
+        self.k += 1
+        self.params = self.pool[self.k % len(self.pool)]
+
     def step(self):
+        self.next_input()
         self.fwd()
         self.bwd()
 
@@ -196,6 +234,7 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
     with ClockSampler(sampler_index) as clk:
         t0 = time.perf_counter()
         for k in range(steps):
+            step.next_input()
             ev[k][0].record(step.stream)
             step.fwd()
             ev[k][1].record(step.stream)
@@ -316,16 +355,19 @@ def also_workloads(dev, peak):
 
     for name in ["cfg1", "cfg1_m5", "cfg5_64_m30", "cfg5_128_m10"]:
         _, S, B, H, W, M = WORKLOADS[name]
-        st = ModlStep(S, B, H, W, M, dev, 7, B)
+        # small shapes rotate over enough buffers that a step's input was last touched > 2 x L2 bytes ago
+        nbuf = max(2, -(-3 * L2_BYTES // (S * B * H * W * 40 * M)))
+        st = ModlStep(S, B, H, W, M, dev, 7, B, n_buffers=nbuf)
         t = timeit(st.step, 20)
         out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6,
                      "algorithmic_GBs": st.n_px * 120 * M / t / 1e9, "frac_of_hbm_peak": st.n_px * 120 * M / t / 1e9 / peak}
         if name.startswith("cfg1"):
             def on_stream(sp, st=st):
                 keep, st.st = st.st, sp
-                st.step()
+                for _ in range(len(st.pool)):  # one graph = one pass over every buffer of the rotation
+                    st.step()
                 st.st = keep
-            tg = time_as_graph(on_stream, 50)
+            tg = time_as_graph(on_stream, 20) / len(st.pool)
             out[name]["cuda_graph_us_per_step"] = tg * 1e6
             out[name]["cuda_graph_frac_of_hbm_peak"] = st.n_px * 120 * M / tg / 1e9 / peak
         del st
@@ -476,6 +518,7 @@ def main():
     rank, world, local_rank = dist_setup(args.gpus)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    bound_cpus = bind_near_gpu(local_rank)
     kind, S, B, H, W, M = wl
     peak, peak_how = measured_hbm_peak()
 
@@ -514,7 +557,8 @@ def main():
     dt = max_over_ranks(dt, world, dev)
     e2e = {"value": world * n_px * e2e_steps / dt, "unit": "px-samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
-           "api": "vaemdl_modl_iwae_step_host (pinned host buffers; H2D params+x+extra, D2H grads+ll+lme+elbo each step)"}
+           "api": "vaemdl_modl_iwae_step_host (pinned host buffers; H2D params+x+extra, D2H grads+ll+lme+elbo each step)",
+           "host_cpus_bound_near_gpu": bound_cpus}
 
     ev = None
     if not args.no_eval:
@@ -524,6 +568,7 @@ def main():
     also = None
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
+            unbind()
             cpu = cpu_baseline_sample(S, H, W, M)
         if not args.no_also:
             try:
@@ -540,6 +585,7 @@ def main():
                        "px_samples_per_step_per_gpu": n_px, "l2": "inputs larger than L2 "
                        f"(params {n_px * 40 * M / 2**20:.0f} MiB + grads {n_px * 40 * M / 2**20:.0f} MiB per step vs 126 MiB L2)"
                        if n_px * 40 * M > L2_BYTES else "inputs NOT larger than L2",
+                       "input_rotation": "2 parameter tensors alternate between steps (no L2 carry-over of a step's input)",
                        "step": "modl_fwd (tile partials, float64) -> fused finish (per-image ll, log-mean-exp, elbo, softmax weights) -> modl_bwd; inputs resident in HBM"},
             "clocks": res["clocks"], "e2e": e2e, "gpu_launches": ModlStep.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,

@@ -99,7 +99,9 @@ def test_sample_explicit_noise(V):
 
 
 @pytest.mark.parametrize("S,B,H,W,split,b_total", [(5, 8, 32, 32, True, 0), (3, 5, 8, 8, False, 0), (16, 3, 4, 4, True, 12),
-                                                    (700, 2, 4, 4, False, 0), (4, 3, 2, 2, True, 0)])
+                                                    (700, 2, 4, 4, False, 0), (4, 3, 2, 2, True, 0),
+                                                    (2, 3, 6, 6, True, 0), (2, 3, 10, 10, True, 0), (2, 3, 10, 10, False, 0),
+                                                    (3, 5, 3, 3, True, 0), (3, 2, 5, 7, False, 0), (2, 7, 9, 8, True, 0)])
 def test_fused_iwae_step_matches_oracle(V, S, B, H, W, split, b_total):
     """vaemdl_dlogistic_iwae_fwd + vaemdl_dlogistic_bwd against models/loss.py:32-37 on the model03 head, float64 oracle."""
     g = torch.Generator().manual_seed(S * 7 + B)
@@ -127,3 +129,34 @@ def test_fused_iwae_step_matches_oracle(V, S, B, H, W, split, b_total):
     assert relnorm(dls, b64.grad[..., 3:]) < GRAD_RTOL
     if split:
         assert dls.data_ptr() == dloc.data_ptr() + 12  # one [..,6] gradient buffer, like the un-split input
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 6, 6, 3), (3, 10, 10, 3), (2, 2, 3, 3, 3), (4, 5, 7, 3), (2, 9, 8, 3), (3, 4, 4, 1), (5, 6)])
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("x_u8", [True, False])
+def test_elementwise_log_prob_and_grad_every_layout(V, shape, split, x_u8):
+    """Element-wise log_prob + autograd through every kernel variant: pixel pairs on the un-split [..,6] layout, pixel
+    pairs on separate tensors, and the generic kernel (odd pixel counts, C != 3)."""
+    g = torch.Generator().manual_seed(sum(shape) + 2 * split + x_u8)
+    C = shape[-1]
+    both = torch.randn(*shape[:-1], 2 * C, generator=g)
+    both[..., :C] = torch.rand(*shape, generator=g)
+    both[..., C:] -= 2.0
+    k = torch.randint(0, 256, shape[1:] if len(shape) > 2 else shape, dtype=torch.uint8, generator=g)
+    x01 = O.normalize_u8(k)
+    w = torch.randn(*shape, generator=g)
+    b64 = both.double().requires_grad_(True)
+    lp64 = O.dlogistic_log_prob(x01.double(), b64[..., :C], b64[..., C:], 0.0, 1.0, 256.0)
+    (lp64 * w.double()).sum().backward()
+    bd = both.to(DEV).requires_grad_(True)
+    if split:
+        loc, ls = torch.split(bd, C, dim=-1)
+    else:
+        loc, ls = bd[..., :C].contiguous(), bd[..., C:].contiguous()
+    d = V.DiscretizedLogistic(loc, ls, low=0.0, high=1.0, levels=256.0)
+    lp = d.log_prob(k.to(DEV) if x_u8 else x01.to(DEV))
+    assert lp.shape == lp64.shape
+    assert (lp.detach().cpu().double() - lp64.detach()).abs().max().item() < 5e-5
+    (lp * w.to(DEV)).sum().backward()
+    assert relnorm(bd.grad[..., :C], b64.grad[..., :C]) < GRAD_RTOL
+    assert relnorm(bd.grad[..., C:], b64.grad[..., C:]) < GRAD_RTOL

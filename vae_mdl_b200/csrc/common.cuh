@@ -125,15 +125,36 @@ const DeviceInfo& device_info();  // cached per current device (api_misc.cu)
 
 // ---- per-image sums of a forward kernel whose warps own runs of consecutive tiles (finish.cu) -------------------------------
 // Warp w of the forward grid owned tiles [w*tw_base + min(w, tw_rem), + tw_base + (w < tw_rem)) of PPT rows each and left
-// one float64 partial per image its run touched at partial[w*K + (n - first image of the run)]; HW = rows per image.
+// one float64 partial per image its run touched, at partial[n*K + (w - first warp whose run touches image n)]: the
+// partials of one image are contiguous and in warp order.  HW = rows per image.
 constexpr long long kMaxGridWarps = 8192;  // bound on (CTAs x warps) of such a grid: sizes the partial-sum workspace
-inline size_t partial_elems(long long n_img) { return static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 1; }
+inline size_t partial_elems(long long n_img) { return 3 * static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 64; }
+// K: the largest number of warp runs one image can intersect (runs are tw_base or tw_base + 1 tiles long)
+inline int partial_K(long long HW, int PPT, long long tw_base) {
+  const long long tpi = (HW + PPT - 1) / PPT + 1;  // tiles an image can overlap
+  return static_cast<int>((tw_base >= 1 ? tpi / tw_base : tpi) + 2);
+}
 struct PartialGeom {
   const double* partial;
   long long tw_base, tw_rem;
   int K, PPT;
   long long HW;
 };
+template <typename I>
+__device__ __forceinline__ I run_of_tile(I t, I base, I rem) {  // which warp's run holds tile t
+  const I cut = rem * (base + 1);
+  return t < cut ? t / (base + 1) : rem + (t - cut) / base;
+}
+__device__ __forceinline__ long long partial_slot(long long n, long long w, long long HW, int PPT, long long base,
+                                                  long long rem, int K, bool small) {
+  long long w_lo;
+  if (small)
+    w_lo = run_of_tile<unsigned>(static_cast<unsigned>(n * HW) / static_cast<unsigned>(PPT), static_cast<unsigned>(base),
+                                 static_cast<unsigned>(rem));
+  else
+    w_lo = run_of_tile<long long>((n * HW) / PPT, base, rem);
+  return n * K + (w - w_lo);
+}
 struct IwaeOut {  // outputs of the fused IWAE finish (all nullable); active when S > 0
   int S = 0;
   long long B = 0, B_total = 0;

@@ -9,6 +9,7 @@
 // The log-scale is NOT clamped in this class (utils/discretized_logistic.py:38); exp(-ls) is saturated at 3e38 so
 // that x == loc with a vanishing scale gives log 1 = 0 as the reference does instead of inf*0.
 #include "modl_math.cuh"
+#include "packed.cuh"
 
 namespace vaemdl {
 
@@ -17,7 +18,7 @@ struct DlArgs {
   const float* logscale;
   const void* x;
   float* lp_elem;
-  double* partial;    // [total_warps][K] float64: one partial per (warp, image its run of tiles touches)
+  double* partial;    // [n_img][K] float64: one partial per (image, warp whose run of tiles touches it)
   unsigned* zero_me;  // nullable: a word the forward kernel clears for the fused finish kernel that follows it
   long long tw_base, tw_rem;  // warp w owns tiles [w*tw_base + min(w, tw_rem), + tw_base + (w < tw_rem))
   int K;
@@ -30,6 +31,7 @@ struct DlArgs {
   long long rows_per_img; // D / CPT
   int x_batch;
   int x_u8;
+  int small;   // row indices fit 32 bits
   int C;       // channels of the [.., C] tensors
   int ld;      // channel-row stride of loc/logscale
   int ld_out;  // channel-row stride of dloc/dls
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
         const long long n_first = __shfl_sync(kFull, n, 0);
         while (n_base < n_first) {
           const double done = dl_warp_sum(acc0);
-          if (lane == 0) a.partial[gw * a.K + (n_base - n_warp_first)] = done;
+          if (lane == 0) a.partial[partial_slot(n_base, gw, a.rows_per_img, 32, a.tw_base, a.tw_rem, a.K, a.small)] = done;
           acc0 = acc1;
           acc1 = 0.0;
           ++n_base;
@@ -184,8 +186,252 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
       const long long n_last = (t_end * 32 < a.n_rows ? t_end * 32 - 1 : a.n_rows - 1) / a.rows_per_img;
       const double d0 = dl_warp_sum(acc0), d1 = dl_warp_sum(acc1);
       if (lane == 0) {
-        a.partial[gw * a.K + (n_base - n_warp_first)] = d0;
-        if (n_base + 1 <= n_last) a.partial[gw * a.K + (n_base + 1 - n_warp_first)] = d1;
+        a.partial[partial_slot(n_base, gw, a.rows_per_img, 32, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+        if (n_base + 1 <= n_last) a.partial[partial_slot(n_base + 1, gw, a.rows_per_img, 32, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
+      }
+    }
+  }
+}
+
+// ---- fast path for image tensors (C == 3, an even number of pixels per image): two pixels per lane -----------------------
+// The lo / hi halves of Blackwell's packed FP32 pipe (FFMA2 / FMUL2 / FADD2) hold the same channel of two
+// neighbouring pixels, the un-split [..,6] conv output of models/model03.py:88-91 arrives as three 128-bit loads per
+// lane, and (image, row) indices advance incrementally (no integer division in the loop).
+struct DlOut2 {
+  f2 lp, dloc, dls;
+};
+__device__ __forceinline__ f2 lg2_2(f2 a) { return pk(lg2a(lo(a)), lg2a(hi(a))); }
+__device__ __forceinline__ f2 abs_2(f2 a) { return pk(fabsf(lo(a)), fabsf(hi(a))); }
+
+template <bool BWD>
+__device__ __forceinline__ DlOut2 dl_elem2(f2 x, f2 loc, f2 ls, const DlArgs& a) {
+  const bool ll_ = lo(x) <= a.low, lh_ = hi(x) <= a.low;     // utils/discretized_logistic.py:71-73
+  const bool rl_ = lo(x) >= a.high, rh_ = hi(x) >= a.high;   // :74-76
+  const f2 inv = min_2(ex2_2(ls * (-kLog2e)), 3.0e38f);
+  const f2 mid = inv * (x - loc);
+  const f2 am = abs_2(mid);
+  const f2 A = ex2_2(am * (-kLog2e));
+  const f2 h = inv * a.dx;
+  f2 q = fma2(h, -1.0f / 720.0f, 1.0f / 120.0f);
+  q = fma2(h, q, -1.0f / 24.0f);
+  q = fma2(h, q, 1.0f / 6.0f);
+  q = fma2(h, q, -0.5f);
+  q = fma2(h, q, 1.0f);
+  f2 omG = h * q;
+  f2 G = sp(1.0f) - omG;
+  const bool nl = lo(h) >= kHSmall, nh_ = hi(h) >= kHSmall;
+  const bool narrow = __any_sync(kFull, nl || nh_);
+  if (narrow) {
+    const f2 Ge = ex2_2(h * (-kLog2e));
+    G = sel_2(nl, nh_, Ge, G);
+    omG = sel_2(nl, nh_, sp(1.0f) - Ge, omG);
+  }
+  const f2 AG = A * G, ApG = A + G, opAG = AG + 1.0f, opA = A + 1.0f;
+  const bool pl = lo(mid) >= 0.0f, ph = hi(mid) >= 0.0f;
+  const f2 rest_n = omG * (G + 1.0f);
+  const f2 den_n = ApG * opAG;
+  const f2 lhs = A * rest_n, thr = den_n * 1e-5f;
+  const bool il = lo(lhs) > lo(thr), ih = hi(lhs) > hi(thr);  // prob > 1e-5 (:64)
+  const bool el = ll_ || rl_, eh = lh_ || rh_;
+  const bool ol = (ll_ == pl), oh = (lh_ == ph);
+  f2 nu = sel_2(il, ih, rest_n, sp(1.0f));
+  f2 de = sel_2(il, ih, den_n, opA * opA);
+  f2 cst = sel_2(il, ih, sp(0.0f), sp(a.ln_width) - ls);
+  f2 use_mid = am;
+  if (el || eh) {
+    const f2 de_e = sel_2(ol, oh, opAG, ApG);
+    const f2 um_e = sel_2(ol, oh, sp(0.0f), am);
+    nu = sel_2(el, eh, sp(1.0f), nu);
+    de = sel_2(el, eh, de_e, de);
+    cst = sel_2(el, eh, sp(0.0f), cst);
+    use_mid = sel_2(el, eh, um_e, use_mid);
+  }
+  DlOut2 o;
+  o.lp = fma2(lg2_2(nu) - lg2_2(de), kLn2, cst - use_mid);
+  if constexpr (BWD) {
+    const f2 omA2 = (sp(1.0f) - A) * opA;
+    f2 hc;
+    {
+      const f2 h2 = h * h;
+      hc = fma2(h2, 2.0f / 945.0f, -1.0f / 45.0f);
+      hc = fma2(h2, hc, 1.0f / 3.0f);
+      hc = fma2(h2, hc, 1.0f);
+      if (narrow) {
+        const f2 e = h * fma2(G, G, 1.0f) * rcp_2(rest_n);
+        hc = sel_2(nl, nh_, e, hc);
+      }
+    }
+    f2 den = de;  // the same denominators serve the derivatives
+    f2 nm = neg_sign_of_2(sel_2(il, ih, G * omA2, omA2), mid);
+    f2 nh = sel_2(il, ih, (h * -1.0f) * lhs, sp(0.0f));
+    f2 c0 = sel_2(il, ih, hc, sp(0.0f));
+    f2 dir = sel_2(il, ih, sp(0.0f), sp(-1.0f));
+    if (el || eh) {
+      const f2 t = sel_2(ol, oh, AG, G);
+      const f2 nm_e = pk(ll_ ? lo(t) : -lo(t), lh_ ? hi(t) : -hi(t));
+      nm = sel_2(el, eh, nm_e, nm);
+      nh = sel_2(el, eh, h * t, nh);
+      c0 = sel_2(el, eh, sp(0.0f), c0);
+      dir = sel_2(el, eh, sp(0.0f), dir);
+    }
+    const f2 rden = rcp_2(den);
+    const f2 Dm = nm * rden;
+    o.dloc = (inv * -1.0f) * Dm;
+    o.dls = (dir - c0) - fma2(mid, Dm, nh * rden);
+  }
+  return o;
+}
+
+// IL: loc/logscale are the two halves of one [.., 6] tensor (ld = 6, logscale = loc + 3) and so are dloc/dls.
+template <bool BWD, bool IL>
+__global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+  if (t_begin >= t_end) return;
+  const long long rpi = a.rows_per_img;
+  // image of the warp's first row: the only integer divisions of the kernel (32-bit when the problem allows it)
+  long long n_warp_first, xb;
+  if (a.small) {
+    n_warp_first = static_cast<unsigned>(t_begin * 64) / static_cast<unsigned>(rpi);
+    xb = a.x_batch == 1 ? 0 : static_cast<unsigned>(n_warp_first) % static_cast<unsigned>(a.x_batch);
+  } else {
+    n_warp_first = (t_begin * 64) / rpi;
+    xb = a.x_batch == 1 ? 0 : n_warp_first % a.x_batch;
+  }
+  // this lane's pixel pair: rows r0, r0 + 1 of image n (rows_per_img is even: a pair never straddles two images)
+  long long r0 = t_begin * 64 + 2 * lane;
+  long long n = n_warp_first;
+  long long rr = r0 - n * rpi;
+  while (rr >= rpi) {
+    rr -= rpi;
+    ++n;
+    if (a.x_batch != 1 && ++xb == a.x_batch) xb = 0;
+  }
+  double acc0 = 0.0, acc1 = 0.0;
+  long long n_base = n_warp_first;
+  bool any1 = false;  // some row of the current tile belongs to image n_base + 1 (warp-uniform)
+  for (long long t = t_begin; t < t_end; ++t) {
+    const bool active = r0 < a.n_rows;
+    f2 loc[3], ls[3], xv[3];
+    if (active) {
+      if constexpr (IL) {
+        const float4* p = reinterpret_cast<const float4*>(a.loc + r0 * 6);
+        const float4 u0 = p[0], u1 = p[1], u2 = p[2];  // [locA(3) lsA(3) locB(3) lsB(3)]
+        loc[0] = pk(u0.x, u1.z);
+        loc[1] = pk(u0.y, u1.w);
+        loc[2] = pk(u0.z, u2.x);
+        ls[0] = pk(u0.w, u2.y);
+        ls[1] = pk(u1.x, u2.z);
+        ls[2] = pk(u1.y, u2.w);
+      } else {
+        const float2* p = reinterpret_cast<const float2*>(a.loc + r0 * 3);
+        const float2* q = reinterpret_cast<const float2*>(a.logscale + r0 * 3);
+        const float2 u0 = p[0], u1 = p[1], u2 = p[2], v0 = q[0], v1 = q[1], v2 = q[2];  // [A0 A1 | A2 B0 | B1 B2]
+        loc[0] = pk(u0.x, u1.y);
+        loc[1] = pk(u0.y, u2.x);
+        loc[2] = pk(u1.x, u2.y);
+        ls[0] = pk(v0.x, v1.y);
+        ls[1] = pk(v0.y, v2.x);
+        ls[2] = pk(v1.x, v2.y);
+      }
+      const long long xo = (xb * rpi + rr) * 3;
+      if (a.x_u8) {
+        const uint8_t* xp = static_cast<const uint8_t*>(a.x) + xo;  // 6 bytes, 2-byte aligned (xo is a multiple of 6)
+        const ushort3 w = *reinterpret_cast<const ushort3*>(xp);
+        xv[0] = pk(__fdiv_rn(static_cast<float>(w.x & 0xff), 255.0f), __fdiv_rn(static_cast<float>(w.y >> 8), 255.0f));
+        xv[1] = pk(__fdiv_rn(static_cast<float>(w.x >> 8), 255.0f), __fdiv_rn(static_cast<float>(w.z & 0xff), 255.0f));
+        xv[2] = pk(__fdiv_rn(static_cast<float>(w.y & 0xff), 255.0f), __fdiv_rn(static_cast<float>(w.z >> 8), 255.0f));
+      } else {
+        const float2* xp = reinterpret_cast<const float2*>(static_cast<const float*>(a.x) + xo);
+        const float2 w0 = xp[0], w1 = xp[1], w2 = xp[2];
+        xv[0] = pk(w0.x, w1.y);
+        xv[1] = pk(w0.y, w2.x);
+        xv[2] = pk(w1.x, w2.y);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) loc[c] = ls[c] = xv[c] = sp(0.0f);
+    }
+    DlOut2 o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = dl_elem2<BWD>(xv[c], loc[c], ls[c], a);  // every lane runs it (warp votes inside)
+    if constexpr (!BWD) {
+      if (a.lp_elem && active) {
+        float2* out = reinterpret_cast<float2*>(a.lp_elem + r0 * 3);
+        out[0] = make_float2(lo(o[0].lp), lo(o[1].lp));
+        out[1] = make_float2(lo(o[2].lp), hi(o[0].lp));
+        out[2] = make_float2(hi(o[1].lp), hi(o[2].lp));
+      }
+      const f2 s2 = o[0].lp + o[1].lp + o[2].lp;
+      const float val = active ? lo(s2) + hi(s2) : 0.0f;
+      if (a.partial) {
+        const long long n_first = __shfl_sync(kFull, n, 0);
+        while (n_base < n_first) {
+          const double done = dl_warp_sum(acc0);
+          if (lane == 0) a.partial[partial_slot(n_base, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
+        }
+        if (n == n_base)
+          acc0 += static_cast<double>(val);
+        else
+          acc1 += static_cast<double>(val);
+        any1 = __any_sync(kFull, active && n != n_base);
+      } else if (a.ll_atomic && active) {
+        atomicAdd(a.ll_atomic + n, static_cast<double>(val));
+      }
+    } else if (active) {
+      const float g = a.g_image ? a.g_image[n] : 0.0f;
+      f2 ge[3] = {sp(g), sp(g), sp(g)};
+      if (a.g_elem) {
+        const float2* gp = reinterpret_cast<const float2*>(a.g_elem + r0 * 3);
+        const float2 w0 = gp[0], w1 = gp[1], w2 = gp[2];
+        ge[0] = ge[0] + pk(w0.x, w1.y);
+        ge[1] = ge[1] + pk(w0.y, w2.x);
+        ge[2] = ge[2] + pk(w1.x, w2.y);
+      }
+      f2 dl[3], ds[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        dl[c] = ge[c] * o[c].dloc;
+        ds[c] = ge[c] * o[c].dls;
+      }
+      if constexpr (IL) {
+        float4* out = reinterpret_cast<float4*>(a.dloc + r0 * 6);
+        out[0] = make_float4(lo(dl[0]), lo(dl[1]), lo(dl[2]), lo(ds[0]));
+        out[1] = make_float4(lo(ds[1]), lo(ds[2]), hi(dl[0]), hi(dl[1]));
+        out[2] = make_float4(hi(dl[2]), hi(ds[0]), hi(ds[1]), hi(ds[2]));
+      } else {
+        float2* o1 = reinterpret_cast<float2*>(a.dloc + r0 * 3);
+        float2* o2 = reinterpret_cast<float2*>(a.dls + r0 * 3);
+        o1[0] = make_float2(lo(dl[0]), lo(dl[1]));
+        o1[1] = make_float2(lo(dl[2]), hi(dl[0]));
+        o1[2] = make_float2(hi(dl[1]), hi(dl[2]));
+        o2[0] = make_float2(lo(ds[0]), lo(ds[1]));
+        o2[1] = make_float2(lo(ds[2]), hi(ds[0]));
+        o2[2] = make_float2(hi(ds[1]), hi(ds[2]));
+      }
+    }
+    // next tile: 64 rows further on
+    r0 += 64;
+    rr += 64;
+    while (rr >= rpi) {
+      rr -= rpi;
+      ++n;
+      if (a.x_batch != 1 && ++xb == a.x_batch) xb = 0;
+    }
+  }
+  if constexpr (!BWD) {
+    if (a.partial) {
+      const double d0 = dl_warp_sum(acc0);
+      if (lane == 0) a.partial[partial_slot(n_base, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+      if (any1) {
+        const double d1 = dl_warp_sum(acc1);
+        if (lane == 0) a.partial[partial_slot(n_base + 1, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
       }
     }
   }
@@ -224,6 +470,7 @@ static int dl_fill(DlArgs& a, const float* loc, const float* logscale, int C, in
   a.x = x;
   a.rows_per_img = D / cpt;
   a.n_rows = n_img * a.rows_per_img;
+  a.small = a.n_rows < (1ll << 31) - 64;
   a.x_batch = x_batch;
   a.x_u8 = x_dtype == VAEMDL_X_U8;
   a.C = C;
@@ -238,10 +485,29 @@ static int dl_fill(DlArgs& a, const float* loc, const float* logscale, int C, in
   return VAEMDL_OK;
 }
 
+// which kernel serves these arguments: 0 = generic (one row of CPT channels per lane, 32-row tiles),
+// 1 = pixel pairs on the un-split [..,6] layout, 2 = pixel pairs on separate dense [..,3] tensors (64-row tiles)
+static int dl_kind(const DlArgs& a, int cpt, bool bwd) {
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & (m - 1)) == 0; };
+  if (cpt != 3 || a.C != 3 || (a.rows_per_img & 1)) return 0;
+  if (!a.x_u8 && !al(a.x, 8)) return 0;
+  if (a.lp_elem && !al(a.lp_elem, 8)) return 0;
+  if (a.g_elem && !al(a.g_elem, 8)) return 0;
+  if (a.ld == 6 && a.logscale == a.loc + 3 && al(a.loc, 16)) {
+    if (!bwd || (a.ld_out == 6 && a.dls == a.dloc + 3 && al(a.dloc, 16))) return 1;
+  }
+  if (a.ld == 3 && al(a.loc, 8) && al(a.logscale, 8)) {
+    if (!bwd || (a.ld_out == 3 && al(a.dloc, 8) && al(a.dls, 8))) return 2;
+  }
+  return 0;
+}
+static int dl_tile_rows(int kind) { return kind ? 64 : 32; }
+
 template <bool BWD>
-static int dl_launch(DlArgs a, int cpt, cudaStream_t st, PartialGeom* geom = nullptr) {
+static int dl_launch(DlArgs a, int cpt, int kind, cudaStream_t st, PartialGeom* geom = nullptr) {
   const DeviceInfo& di = device_info();
-  const long long n_tiles = (a.n_rows + 31) / 32;
+  const int TR = dl_tile_rows(kind);
+  const long long n_tiles = (a.n_rows + TR - 1) / TR;
   long long blocks = (n_tiles + 7) / 8;
   long long cap = static_cast<long long>(di.sm_count) * 8;
   if (cap * 8 > kMaxGridWarps) cap = kMaxGridWarps / 8;
@@ -250,12 +516,17 @@ static int dl_launch(DlArgs a, int cpt, cudaStream_t st, PartialGeom* geom = nul
   const long long total_warps = blocks * 8;
   a.tw_base = n_tiles / total_warps;
   a.tw_rem = n_tiles % total_warps;
-  a.K = static_cast<int>(((a.tw_base + (a.tw_rem ? 1 : 0)) * 32 + a.rows_per_img - 1) / a.rows_per_img + 1);
-  if (geom) *geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, 32, a.rows_per_img};
-  if (cpt == 3)
-    dl_kernel<3, BWD><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  a.K = partial_K(a.rows_per_img, TR, a.tw_base);
+  if (geom) *geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, TR, a.rows_per_img};
+  const unsigned grid = static_cast<unsigned>(blocks);
+  if (kind == 1)
+    dl_pair_kernel<BWD, true><<<grid, 256, 0, st>>>(a);
+  else if (kind == 2)
+    dl_pair_kernel<BWD, false><<<grid, 256, 0, st>>>(a);
+  else if (cpt == 3)
+    dl_kernel<3, BWD><<<grid, 256, 0, st>>>(a);
   else
-    dl_kernel<1, BWD><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+    dl_kernel<1, BWD><<<grid, 256, 0, st>>>(a);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -284,7 +555,8 @@ static int dl_fwd_impl(const float* loc, const float* logscale, int C, int ld, c
   const bool want_ll = ll_image || ll_image_f64 || iwae;
   if (!lp_elem && !want_ll) return VAEMDL_EINVAL;
   a.lp_elem = lp_elem;
-  const bool use_partials = want_ll && a.rows_per_img >= 32;
+  const int kind = dl_kind(a, cpt, false);
+  const bool use_partials = want_ll && a.rows_per_img >= dl_tile_rows(kind);
   char* ws = static_cast<char*>(workspace);
   const size_t tail_off = partial_elems(n_img) * sizeof(double);
   unsigned* counter = nullptr;
@@ -302,8 +574,9 @@ static int dl_fwd_impl(const float* loc, const float* logscale, int C, int ld, c
     }
   }
   PartialGeom geom{};
-  rc = dl_launch<false>(a, cpt, st, &geom);
+  rc = dl_launch<false>(a, cpt, kind, st, &geom);
   if (rc) return rc;
+  if (use_partials && static_cast<size_t>(n_img) * geom.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
   if (use_partials)
     return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
   if (!want_ll) return VAEMDL_OK;
@@ -358,7 +631,7 @@ extern "C" int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int
   a.dloc = dloc;
   a.dls = dlogscale;
   a.ld_out = ld_out;
-  return dl_launch<true>(a, cpt, static_cast<cudaStream_t>(stream));
+  return dl_launch<true>(a, cpt, dl_kind(a, cpt, true), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vaemdl_dlogistic_sample(const float* loc, const float* logscale, int C, int ld, const float* u,

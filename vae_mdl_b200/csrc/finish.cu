@@ -9,26 +9,20 @@
 
 namespace vaemdl {
 
-// image n's sum: the partials of the forward warps whose tile runs touched it, in warp order
+// image n's sum: the partials of the forward warps whose tile runs touched it -- contiguous, added in warp order
 template <typename I>
 __device__ __forceinline__ double image_sum_t(const PartialGeom& g, long long n64) {
   const I n = static_cast<I>(n64), HW = static_cast<I>(g.HW), PPT = static_cast<I>(g.PPT);
-  const I base = static_cast<I>(g.tw_base), rem = static_cast<I>(g.tw_rem), K = static_cast<I>(g.K);
+  const I base = static_cast<I>(g.tw_base), rem = static_cast<I>(g.tw_rem);
   const I first = n * HW, last = first + HW - 1;
-  const I t_lo = first / PPT, t_hi = last / PPT;
-  const I cut = rem * (base + 1);
-  const I w_lo = t_lo < cut ? t_lo / (base + 1) : rem + (t_lo - cut) / base;
-  const I w_hi = t_hi < cut ? t_hi / (base + 1) : rem + (t_hi - cut) / base;
+  const I w_lo = run_of_tile<I>(first / PPT, base, rem), w_hi = run_of_tile<I>(last / PPT, base, rem);
+  const int cnt = static_cast<int>(w_hi - w_lo) + 1;
+  const double* p = g.partial + n64 * g.K;
   double acc = 0.0;
-  for (I w0 = w_lo; w0 <= w_hi; w0 += 8) {
+  for (int j0 = 0; j0 < cnt; j0 += 8) {
     double v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {  // all loads first, then the adds (fixed order)
-      const I w = w0 + j;
-      const I tb = w * base + (w < rem ? w : rem);
-      const I nf = (tb * PPT) / HW;
-      v[j] = (w <= w_hi) ? g.partial[w * K + (n - nf)] : 0.0;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = (j0 + j < cnt) ? p[j0 + j] : 0.0;  // all loads first, then the adds (fixed order)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += v[j];
   }
@@ -64,20 +58,21 @@ struct FinishArgs {
   bool small;             // 32-bit index arithmetic suffices
 };
 
-constexpr int kFinishThreads = 128;
+constexpr int kFinishThreads = 128;    // block size when several blocks share the batch
+constexpr int kFinishMaxThreads = 1024;  // a single block takes the whole problem when S*B fits: no fences, no atomics
 
 // A block owns BB consecutive batch elements and all S samples of them: one thread per image, then one warp per batch
 // element, then (for the batch mean) the block that arrives last adds the block sums in block order.
-__global__ void __launch_bounds__(kFinishThreads) finish_kernel(const FinishArgs a) {
+__global__ void __launch_bounds__(kFinishMaxThreads) finish_kernel(const FinishArgs a) {
   extern __shared__ double lw[];  // [BB][S]
-  constexpr int NW = kFinishThreads / 32;
-  __shared__ double blk[NW];
+  const int NT = blockDim.x, NW = NT / 32;
+  __shared__ double blk[kFinishMaxThreads / 32];
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b0 = static_cast<long long>(blockIdx.x) * a.BB;
   const int nb = static_cast<int>((a.B - b0) < a.BB ? (a.B - b0) : a.BB);
   // (1) per-image log-likelihood; consecutive threads take consecutive b of one s
-  for (int img = threadIdx.x; img < a.S * nb; img += kFinishThreads) {
+  for (int img = threadIdx.x; img < a.S * nb; img += NT) {
     const int s = img / nb, bb = img - s * nb;
     const long long n = static_cast<long long>(s) * a.B + b0 + bb;
     const double acc = image_sum(a.geom, n, a.small);
@@ -109,10 +104,18 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const FinishArgs
     }
     wsum += lme;  // identical in every lane
   }
-  // (3) batch mean
+  // (3) batch mean: the block that arrives last adds the block sums in block order
   if (!a.elbo) return;
   if (lane == 0) blk[warp] = wsum;
   __syncthreads();
+  if (gridDim.x == 1) {  // the whole batch lives in this block
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < NW; ++w) t += blk[w];
+      a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < NW; ++w) t += blk[w];
@@ -121,11 +124,23 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const FinishArgs
     is_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0.0;
-    for (unsigned i = 0; i < gridDim.x; ++i) t += reinterpret_cast<volatile double*>(a.block_sums)[i];
-    a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+  if (!is_last) return;
+  __threadfence();
+  __shared__ double chunk[kFinishThreads];
+  double total = 0.0;
+  for (unsigned i0 = 0; i0 < gridDim.x; i0 += kFinishThreads) {  // loads in parallel, adds in order
+    const unsigned i = i0 + threadIdx.x;
+    if (threadIdx.x < kFinishThreads)
+      chunk[threadIdx.x] = i < gridDim.x ? reinterpret_cast<volatile double*>(a.block_sums)[i] : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned m = gridDim.x - i0 < kFinishThreads ? gridDim.x - i0 : kFinishThreads;
+      for (unsigned j = 0; j < m; ++j) total += chunk[j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.elbo[0] = static_cast<float>(total / static_cast<double>(a.b_norm));  // models/loss.py:37
     *a.counter = 0u;
   }
 }
@@ -133,12 +148,17 @@ __global__ void __launch_bounds__(kFinishThreads) finish_kernel(const FinishArgs
 int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll64, const IwaeOut& iw, double* scratch,
                     unsigned* counter, cudaStream_t st) {
   const bool iwae = iw.S > 0;
-  // 32-bit index arithmetic when every intermediate (row indices, 8 warps past the last one) fits comfortably
-  const bool small = n_img * g.HW < (1ll << 27) && (kMaxGridWarps + 8) * static_cast<long long>(g.K) < (1ll << 31);
+  const bool small = n_img * g.HW < (1ll << 31);  // 32-bit index arithmetic suffices
   // the fused finish keeps a block's [BB][S] log-weights in shared memory and walks S with one warp: only pays
   // while S is small; the 5000-sample evaluation shape takes the grid-parallel route
-  int BB = 1;
-  while (iwae && BB < 32 && static_cast<long long>(2 * BB) * iw.S <= kFinishThreads) BB <<= 1;
+  int BB = 1, threads = kFinishThreads;
+  if (iwae && static_cast<long long>(iw.S) * iw.B <= kFinishMaxThreads) {  // one block, one thread per image
+    BB = static_cast<int>(iw.B);
+    threads = static_cast<int>((iw.S * iw.B + 31) / 32 * 32);
+    if (threads < 32 * BB && 32 * BB <= kFinishMaxThreads) threads = 32 * BB;  // a warp per batch element for step (2)
+  } else {
+    while (iwae && BB < 32 && static_cast<long long>(2 * BB) * iw.S <= kFinishThreads) BB <<= 1;
+  }
   if (iwae && iw.S <= 512) {
     FinishArgs f{};
     f.geom = g;
@@ -157,7 +177,7 @@ int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll
     f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
     f.small = small;
     const long long grid = (iw.B + BB - 1) / BB;
-    finish_kernel<<<static_cast<unsigned>(grid), kFinishThreads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
+    finish_kernel<<<static_cast<unsigned>(grid), threads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
     return cuda_rc(cudaGetLastError());
   }
   double* ll64_dst = ll64 ? ll64 : (iwae ? scratch : nullptr);

@@ -31,7 +31,7 @@ struct ModlArgs {
   const float* params;
   const void* x;
   float* lp_pixel;       // nullable
-  double* partial;       // [total_warps][K] float64 partial sums, one per (warp, image the warp's tile range touches) (nullable)
+  double* partial;       // [n_img][K] float64 partial sums, one per (image, warp whose tile run touches it) (nullable)
   double* ll_atomic;     // [n_img] pre-zeroed float64 accumulators, used instead of `partial` when tiles would span >2 images
   const float* g_image;  // nullable
   const float* g_pixel;  // nullable
@@ -40,7 +40,12 @@ struct ModlArgs {
   long long n_px;  // n_img * H * W
   long long num_tiles;
   long long tw_base, tw_rem;  // warp w owns tiles [w*tw_base + min(w, tw_rem), +tw_base + (w < tw_rem)): consecutive tiles
-  int K;                      // partial slots per warp: max number of images one warp's tile range can touch
+  int K;                      // partial slots per image: max number of warp runs one image can intersect
+  int small;                  // n_px fits 32 bits
+  int reverse;                // backward only: walk the run from its last tile to its first (the tiles the forward kernel
+                              // read last are the ones still in L2)
+  int keep_tiles;             // forward: the last keep_tiles tiles of a run are loaded with an L2 evict_last hint
+  int bwd_hint;               // backward: parameter loads and gradient stores carry an L2 evict_first hint
   int HW;
   int x_batch;
   int x_u8;
@@ -436,6 +441,11 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     return rem < PPT ? static_cast<int>(rem) : PPT;
   };
   // bring tile t into slot s (bulk copy when the byte count allows it, plain loads for a ragged tail tile)
+  const long long t_cnt = t_end - t_begin;
+  const bool rev = BWD && a.reverse;
+  const long long t_first = rev ? t_end - 1 : t_begin;
+  const long long t_dir = rev ? -1 : 1;
+  const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
   auto issue = [&](long long t, int s) {
     const int rows = tile_rows(t);
     const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
@@ -444,7 +454,17 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     if ((bytes & 15u) == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&bars[s], bytes);
-        bulk_g2s(dst, src, bytes, &bars[s]);
+        if (BWD) {
+          if (a.bwd_hint)
+            bulk_g2s_hint(dst, src, bytes, &bars[s], pol_first);
+          else
+            bulk_g2s(dst, src, bytes, &bars[s]);
+        } else {
+          if (a.keep_tiles > 0)
+            bulk_g2s_hint(dst, src, bytes, &bars[s], (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
+          else
+            bulk_g2s(dst, src, bytes, &bars[s]);
+        }
       }
     } else {
       for (int i = lane; i < rows * ROWF; i += 32) dst[i] = src[i];
@@ -456,15 +476,14 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below)
 #pragma unroll
   for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
-    const long long t = t_begin + s;
-    if (t < t_end) issue(t, s);
+    if (s < t_cnt) issue(t_first + s * t_dir, s);
   }
 
   // (image, pixel-in-image) of this lane's pixel-sample, advanced incrementally: one 64-bit division per kernel
   const long long step_n = PPT / a.HW;
   const int step_pix = static_cast<int>(PPT - step_n * a.HW);
-  long long n_own = (t_begin * PPT + p) / a.HW;
-  int pix_own = static_cast<int>((t_begin * PPT + p) - n_own * a.HW);
+  long long n_own = (t_first * PPT + p) / a.HW;
+  int pix_own = static_cast<int>((t_first * PPT + p) - n_own * a.HW);
   // float64 running sums of the image the warp is in (acc0, image n_base) and of the next one (acc1), per lane
   double acc0 = 0.0, acc1 = 0.0;
   const long long n_warp_first = (t_begin * PPT) / a.HW;
@@ -492,10 +511,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   long long n_cur = 0, nfirst_cur = 0;
   PixRaw raw_cur{};
   float g_cur = 0.0f;
-  if (t_begin < t_end) fetch(t_begin, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
 
-  long long it = 0;
-  for (long long t = t_begin; t < t_end; ++t, ++it) {
+  for (long long it = 0; it < t_cnt; ++it) {
+    const long long t = t_first + it * t_dir;
     const int s = static_cast<int>(it % NSLOT);
     const uint32_t parity = static_cast<uint32_t>((it / NSLOT) & 1);
     const int rows = tile_rows(t);
@@ -507,13 +526,22 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     Pixel px;
     decode_pixel(a, raw_cur, px);
     // advance the index and prefetch the next tile's pixel / upstream gradient
-    n_own += step_n;
-    pix_own += step_pix;
-    if (pix_own >= a.HW) {
-      pix_own -= a.HW;
-      ++n_own;
+    if (!rev) {
+      n_own += step_n;
+      pix_own += step_pix;
+      if (pix_own >= a.HW) {
+        pix_own -= a.HW;
+        ++n_own;
+      }
+    } else {
+      n_own -= step_n;
+      pix_own -= step_pix;
+      if (pix_own < 0) {
+        pix_own += a.HW;
+        --n_own;
+      }
     }
-    if (t + 1 < t_end) fetch(t + 1, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
 
     float* slot = slots + s * TILE_F;
     float* rowp = slot + pp * ROWF;
@@ -522,11 +550,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     if constexpr (BWD && NSLOT > 1) {
       // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
       // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
-      const long long tn = t + 1;
-      if (tn < t_end) {
+      if (it + 1 < t_cnt) {
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
-        issue(tn, s ^ 1);
+        issue(t + t_dir, s ^ 1);
       }
     }
 
@@ -584,8 +611,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     if constexpr (!BWD) {
       __syncwarp();
       {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
-        const long long tn = t + NSLOT;
-        if (tn < t_end) issue(tn, s);
+        if (it + NSLOT < t_cnt) issue(t + NSLOT * t_dir, s);
       }
       float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
       if (tiny) {
@@ -601,7 +627,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
         // A tile holds pixels of at most two images (HW >= PPT on this route): n_first and n_first + 1.
         while (n_base < n_first) {  // the warp has left image n_base: its sum leaves the registers (warp-uniform)
           const double done = warp_sum(acc0);
-          if (lane == 0) a.partial[gw * a.K + (n_base - n_warp_first)] = done;
+          if (lane == 0) a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = done;
           acc0 = acc1;
           acc1 = 0.0;
           ++n_base;
@@ -644,7 +670,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(dst, slot, bytes);
+          if (a.bwd_hint)
+            bulk_s2g_hint(dst, slot, bytes, pol_first);
+          else
+            bulk_s2g(dst, slot, bytes);
           bulk_commit();
         }
       } else {
@@ -653,11 +682,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
         __syncwarp();
       }
       if constexpr (NSLOT == 1) {
-        const long long tn = t + 1;
-        if (tn < t_end) {
+        if (it + 1 < t_cnt) {
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
-          issue(tn, 0);
+          issue(t + t_dir, 0);
         }
       }
     }
@@ -669,8 +697,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       const long long n_last = (t_end * PPT < a.n_px ? t_end * PPT - 1 : a.n_px - 1) / a.HW;  // image of the warp's last pixel-sample
       const double d0 = warp_sum(acc0), d1 = warp_sum(acc1);
       if (lane == 0) {
-        a.partial[gw * a.K + (n_base - n_warp_first)] = d0;
-        if (n_base + 1 <= n_last) a.partial[gw * a.K + (n_base + 1 - n_warp_first)] = d1;
+        a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+        if (n_base + 1 <= n_last) a.partial[partial_slot(n_base + 1, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
       }
     }
   }
@@ -806,8 +834,26 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   const long long total_warps = grid * warps;
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
-  const long long max_tiles = a.tw_base + (a.tw_rem ? 1 : 0);
-  a.K = static_cast<int>((max_tiles * T::PPT + a.HW - 1) / a.HW + 1);
+  a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  {
+    // VAEMDL_L2="rev=0|1,keep=<MB>,hint=0|1": L2 reuse between the forward and the backward kernel of one step
+    static const struct L2Opt {
+      int rev = 1, keep_mb = 48, hint = 0;  // measured on B200: profiles/r01_l2_reuse.txt
+      L2Opt() {
+        const char* e = getenv("VAEMDL_L2");
+        if (!e) return;
+        const char* q;
+        if ((q = strstr(e, "rev="))) rev = atoi(q + 4);
+        if ((q = strstr(e, "keep="))) keep_mb = atoi(q + 5);
+        if ((q = strstr(e, "hint="))) hint = atoi(q + 5);
+      }
+    } opt;
+    a.reverse = opt.rev;
+    a.bwd_hint = opt.hint;
+    a.keep_tiles = static_cast<int>((static_cast<long long>(opt.keep_mb) << 20) / (total_warps * T::TILE_B));
+    if (opt.keep_mb > 0 && a.keep_tiles < 1) a.keep_tiles = 1;
+  }
+  a.small = a.n_px < (1ll << 31) - 64;
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -935,7 +981,7 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   rc = launch_modl<false>(a, st, &plan);
   if (rc) return rc;
   if (use_partials) {
-    if (static_cast<size_t>(plan.total_warps) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+    if (static_cast<size_t>(n_img) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
     const PartialGeom geom{a.partial, plan.tw_base, plan.tw_rem, plan.K, plan.PPT, a.HW};
     return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
   }
