@@ -242,3 +242,45 @@ def test_abi_direct_call_and_errors(built_lib):
     # misaligned parameter pointer
     assert L.vaemdl_modl_fwd(pd.data_ptr() + 4, xd.data_ptr(), 1, 0, 0, S * B, B, H, W, M, None, ll.data_ptr(), None,
                              ws.data_ptr(), nb, st) == -2
+
+
+@pytest.mark.parametrize("force", ["0", "1"])
+@pytest.mark.parametrize("name", ["modl_m5_trained"])
+def test_both_n_mix_5_kernels_on_the_golden_fixture(F, V, monkeypatch, force, name):
+    """n_mix = 5 has two instantiations (component pairs / pixel pairs, chosen by problem size): both must reproduce the
+    fixture, including its pixels whose mixture sum underflows float32 (log-domain fallback in one half of a lane)."""
+    monkeypatch.setenv("VAEMDL_PP", force)
+    z = golden(name)
+    params = torch.from_numpy(z["params"]).to(DEV)
+    x_u8 = torch.from_numpy(z["x_u8"]).to(DEV)
+    assert_ll_close(F.modl_log_likelihood(params, x_u8, dtype=torch.float64), z["ll"], rtol=2e-7)
+    lp = F.modl_log_prob(params, x_u8)
+    assert (lp.cpu().double() - torch.from_numpy(z["lp"])).abs().max().item() < 5e-5
+    dp = F.modl_backward(params, x_u8, g_image=torch.from_numpy(z["g_image"]).to(DEV))
+    assert_grad_close(dp, z["grad_fixed"], 5)
+    loss, lpxz, dp2 = V.modl_iwae_step(params, x_u8, torch.from_numpy(z["extra"]).to(DEV))
+    assert abs(loss.item() - float(z["loss"])) <= LL_RTOL * abs(float(z["loss"]))
+    assert_grad_close(dp2, z["grad_iwae"], 5)
+
+
+@pytest.mark.parametrize("S,B,H,W,M,force", [(2, 3, 8, 8, 5, "1"), (3, 1, 5, 7, 5, "1"), (1, 2, 9, 9, 5, "1"), (2, 2, 16, 12, 5, "1"),
+                                               (1, 2, 9, 9, 2, None), (2, 1, 10, 7, 4, None), (1, 3, 8, 8, 6, None),
+                                               (2, 2, 8, 9, 8, None), (1, 1, 12, 12, 9, None)])
+def test_pixel_pair_kernel_vs_oracle(F, monkeypatch, S, B, H, W, M, force):
+    """The pixel-pair kernel (n_mix 1..9): ragged tiles, tiles straddling images, images smaller than a tile, with the
+    trained-like distribution (narrow scales, low-probability branch, underflowing mixture sums)."""
+    if force is not None:
+        monkeypatch.setenv("VAEMDL_PP", force)
+    params, x_u8, g = trained_like(500 + 11 * M + H, S, B, H, W, M)
+    x_u8[0, 0, 0] = torch.tensor([0, 255, 0], dtype=torch.uint8)      # both edges in one pixel
+    g_image = torch.randn(S, B, generator=g)
+    lp64, ll64, grad64 = oracle_ll_and_grad(params, x_u8, g_image)
+    ok = ~threshold_ambiguous(params.double(), O.normalize_u8(x_u8, torch.float64))
+    pd, xd = params.to(DEV), x_u8.to(DEV)
+    ll = F.modl_log_likelihood(pd, xd, dtype=torch.float64).cpu()
+    assert ((ll - ll64).abs() / ll64.abs())[ok].max().item() <= LL_RTOL
+    dp = F.modl_backward(pd, xd, g_image=g_image.to(DEV)).cpu().double()
+    if bool(ok.all()):
+        assert_grad_close(dp, grad64, M)
+    else:
+        assert relnorm(dp[ok], grad64[ok]) <= GRAD_RTOL

@@ -54,10 +54,25 @@ struct ModlArgs {
   int M;
 };
 
-struct Pixel {
+struct Pixel {  // one pixel: both halves of a packed register see the same observation
   float x[3];
   bool left[3], right[3];
 };
+struct PixelPair {  // two pixels: lo half = pixel A, hi half = pixel B (the pixel-pair kernel for small n_mix)
+  f2 x[3];
+  bool ll[3], lh[3], rl[3], rh[3];
+};
+struct EdgeFlags {  // x at the lowest / highest bin, per half
+  bool ll, lh, rl, rh;
+};
+__device__ __forceinline__ f2 px_x(const Pixel& p, int c) { return sp(p.x[c]); }
+__device__ __forceinline__ f2 px_x(const PixelPair& p, int c) { return p.x[c]; }
+__device__ __forceinline__ EdgeFlags px_edge(const Pixel& p, int c) {
+  return EdgeFlags{p.left[c], p.left[c], p.right[c], p.right[c]};
+}
+__device__ __forceinline__ EdgeFlags px_edge(const PixelPair& p, int c) {
+  return EdgeFlags{p.ll[c], p.lh[c], p.rl[c], p.rh[c]};
+}
 
 // pixel `pix` of image n (image n is scored against x[n % x_batch], include/vaemdl.h)
 __device__ __forceinline__ void load_pixel(const ModlArgs& a, long long n, int pix, Pixel& px) {
@@ -218,10 +233,10 @@ struct Sub2 {
 };
 
 template <bool NARROW, bool BWD>
-__device__ __forceinline__ void subpix2(float x, bool left, bool right, f2 loc, f2 s_raw, Sub2& o) {
+__device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub2& o) {
   const f2 ls = max_2(s_raw, -7.0f);                                  // utils/mdl.py:109
   const f2 inv = ex2_2(ls * (-kLog2e));
-  const f2 mid = inv * (sp(x) - loc);
+  const f2 mid = inv * (x - loc);
   const f2 A = ex2_negabs_2(mid * kLog2e);
   const f2 h = inv * kDx;
   f2 q = fma2(h, -1.0f / 720.0f, 1.0f / 120.0f);
@@ -254,11 +269,11 @@ __device__ __forceinline__ void subpix2(float x, bool left, bool right, f2 loc, 
   const f2 den_l = opA * opA;
   f2 num = sel_2(il, ih, num_n, num_l);
   f2 den = sel_2(il, ih, den_n, den_l);
-  const bool edge = left || right;
-  const bool ool = (left == (lo(mid) >= 0.0f)), ooh = (left == (hi(mid) >= 0.0f));  // 1/(1+AG) vs A/(A+G)
-  if (edge) {
-    num = sel_2(ool, ooh, sp(1.0f), A);
-    den = sel_2(ool, ooh, opAG, ApG);
+  const bool el = e.ll || e.rl, eh = e.lh || e.rh;
+  const bool ool = (e.ll == (lo(mid) >= 0.0f)), ooh = (e.lh == (hi(mid) >= 0.0f));  // 1/(1+AG) vs A/(A+G)
+  if (el || eh) {
+    num = sel_2(el, eh, sel_2(ool, ooh, sp(1.0f), A), num);
+    den = sel_2(el, eh, sel_2(ool, ooh, opAG, ApG), den);
   }
   o.num = num;
   o.den = den;
@@ -276,12 +291,12 @@ __device__ __forceinline__ void subpix2(float x, bool left, bool right, f2 loc, 
     }
     f2 c0 = sel_2(il, ih, hc, sp(0.0f));
     f2 dir = sel_2(il, ih, sp(0.0f), sp(-1.0f));
-    if (edge) {
+    if (el || eh) {
       const f2 t = sel_2(ool, ooh, AG, G);
-      nm = left ? t : t * -1.0f;
-      nh = h * t;
-      c0 = sp(0.0f);
-      dir = sp(0.0f);
+      nm = sel_2(el, eh, pk(e.ll ? lo(t) : -lo(t), e.lh ? hi(t) : -hi(t)), nm);
+      nh = sel_2(el, eh, h * t, nh);
+      c0 = sel_2(el, eh, sp(0.0f), c0);
+      dir = sel_2(el, eh, sp(0.0f), dir);
     }
     o.nm = nm;
     o.nh = nh;
@@ -307,17 +322,18 @@ __device__ __forceinline__ void tanh3_2(const f2 kp[3], f2 k[3]) {
 }
 
 // One pair of mixture components.  Returns P = prod_c f_c (linear domain); BWD also the nine d log P / d param pairs.
-template <bool NARROW, bool BWD>
-__device__ __forceinline__ f2 pair_eval(const Pixel& px, const f2 mu[3], const f2 s[3], const f2 kp[3], f2 u[9]) {
+template <bool NARROW, bool BWD, typename PX>
+__device__ __forceinline__ f2 pair_eval(const PX& px, const f2 mu[3], const f2 s[3], const f2 kp[3], f2 u[9]) {
   f2 k[3];
   tanh3_2(kp, k);
+  const f2 x0 = px_x(px, 0), x1 = px_x(px, 1);
   f2 loc[3];
   loc[0] = mu[0];
-  loc[1] = fma2(k[0], px.x[0], mu[1]);                               // utils/mdl.py:140
-  loc[2] = fma2(k[2], px.x[1], fma2(k[1], px.x[0], mu[2]));          // utils/mdl.py:141-145
+  loc[1] = fma2(k[0], x0, mu[1]);                               // utils/mdl.py:140
+  loc[2] = fma2(k[2], x1, fma2(k[1], x0, mu[2]));               // utils/mdl.py:141-145
   Sub2 f[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) subpix2<NARROW, BWD>(px.x[c], px.left[c], px.right[c], loc[c], s[c], f[c]);
+  for (int c = 0; c < 3; ++c) subpix2<NARROW, BWD>(px_x(px, c), px_edge(px, c), loc[c], s[c], f[c]);
   const f2 d01 = f[0].den * f[1].den;
   const f2 R = rcp_2(d01 * f[2].den);
   const f2 P = (f[0].num * f[1].num) * (f[2].num * R);
@@ -337,9 +353,9 @@ __device__ __forceinline__ f2 pair_eval(const Pixel& px, const f2 mu[3], const f
       u[3 * c + 0] = dloc[c];
       u[3 * c + 1] = dls;
     }
-    u[2] = (dloc[1] * px.x[0]) * fma2(k[0] * -1.0f, k[0], 1.0f);
-    u[5] = (dloc[2] * px.x[0]) * fma2(k[1] * -1.0f, k[1], 1.0f);
-    u[8] = (dloc[2] * px.x[1]) * fma2(k[2] * -1.0f, k[2], 1.0f);
+    u[2] = (dloc[1] * x0) * fma2(k[0] * -1.0f, k[0], 1.0f);
+    u[5] = (dloc[2] * x0) * fma2(k[1] * -1.0f, k[1], 1.0f);
+    u[8] = (dloc[2] * x1) * fma2(k[2] * -1.0f, k[2], 1.0f);
   }
   return P;
 }
@@ -583,9 +599,9 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       f2 u[9];
       f2 P;
       if (narrow)
-        P = pair_eval<true, BWD>(px, mu, sc, kp, u);
+        P = pair_eval<true, BWD, Pixel>(px, mu, sc, kp, u);
       else
-        P = pair_eval<false, BWD>(px, mu, sc, kp, u);
+        P = pair_eval<false, BWD, Pixel>(px, mu, sc, kp, u);
       sumW2 = sumW2 + W;
       sumWP2 = fma2(W, P, sumWP2);
       if constexpr (BWD) {
@@ -709,6 +725,350 @@ __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __rest
   if (i < n) out[i] = static_cast<float>(in[i]);
 }
 
+// ---- the pixel-pair kernel (small n_mix, e.g. the reference's own default n_mix = 5) ---------------------------------------
+// Same pipeline as modl_tile_kernel (per-warp TMA bulk loads, runs of consecutive tiles, in-place gradient staging), but
+// the two halves of a packed register hold the SAME mixture component of TWO pixels: lane l owns rows l and l + 32 of a
+// 64-row tile.  Nothing is wasted on an odd component count, the tile is as large as the n_mix = 10 one (12.8 KB at
+// n_mix = 5), and the two rows of a lane sit 32 rows apart so that the scalar shared-memory loads spread over the banks.
+template <int M>
+struct TilePP {
+  static constexpr int PPT = 64;
+  static constexpr int ROWF = 10 * M;
+  static constexpr int TILE_F = PPT * ROWF;
+  static constexpr int TILE_B = TILE_F * 4;
+  static constexpr int AUX_F = PPT * M;
+};
+
+__device__ __forceinline__ Pixel half_pixel(const PixelPair& pp, bool hi_half) {
+  Pixel px;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    px.x[c] = hi_half ? hi(pp.x[c]) : lo(pp.x[c]);
+    px.left[c] = hi_half ? pp.lh[c] : pp.ll[c];
+    px.right[c] = hi_half ? pp.rh[c] : pp.rl[c];
+  }
+  return px;
+}
+
+template <int M, bool BWD, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
+  using T = TilePP<M>;
+  constexpr int PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F;
+  constexpr int WARP_F = TILE_F + (BWD ? T::AUX_F : 0);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* slot = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
+  float* aux = slot + TILE_F;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+
+  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+  const long long t_cnt = t_end - t_begin;
+  const bool rev = BWD && a.reverse;
+  const long long t_first = rev ? t_end - 1 : t_begin;
+  const long long t_dir = rev ? -1 : 1;
+  const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+
+  auto tile_rows = [&](long long t) -> int {
+    const long long rem = a.n_px - t * PPT;
+    return rem < PPT ? static_cast<int>(rem) : PPT;
+  };
+  auto issue = [&](long long t) {
+    const int rows = tile_rows(t);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+    const float* src = a.params + t * TILE_F;
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, bytes);
+        if (BWD) {
+          if (a.bwd_hint)
+            bulk_g2s_hint(slot, src, bytes, bar, pol_first);
+          else
+            bulk_g2s(slot, src, bytes, bar);
+        } else {
+          if (a.keep_tiles > 0)
+            bulk_g2s_hint(slot, src, bytes, bar, (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
+          else
+            bulk_g2s(slot, src, bytes, bar);
+        }
+      }
+    } else {
+      for (int i = lane; i < rows * ROWF; i += 32) slot[i] = src[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, 0);
+    }
+  };
+  if (t_cnt > 0) issue(t_first);
+
+  // (image, pixel-in-image) of this lane's FIRST pixel-sample (row `lane` of the tile), advanced incrementally
+  const long long step_n = PPT / a.HW;
+  const int step_pix = static_cast<int>(PPT - step_n * a.HW);
+  long long n_own = (t_first * PPT + lane) / a.HW;
+  int pix_own = static_cast<int>((t_first * PPT + lane) - n_own * a.HW);
+  double acc0 = 0.0, acc1 = 0.0;
+  const long long n_warp_first = (t_begin * PPT) / a.HW;
+  long long n_base = n_warp_first;
+
+  struct Fetched {
+    long long nA, nB, n_first;
+    int pixA, pixB;
+    PixRaw rawA, rawB;
+    float gA, gB;
+  };
+  auto fetch = [&](long long t, long long n_lane, int pix_lane, Fetched& f) {
+    const int rows = tile_rows(t);
+    const long long n_first = __shfl_sync(kFull, n_lane, 0);
+    const int pix_first = __shfl_sync(kFull, pix_lane, 0);
+    long long nB = n_lane;
+    int pixB = pix_lane + 32;  // the lane's second row, 32 rows further on
+    while (pixB >= a.HW) {
+      pixB -= a.HW;
+      ++nB;
+    }
+    const bool inA = lane < rows, inB = lane + 32 < rows;  // rows past a ragged last tile shadow the tile's first pixel
+    f.nA = inA ? n_lane : n_first;
+    f.pixA = inA ? pix_lane : pix_first;
+    f.nB = inB ? nB : n_first;
+    f.pixB = inB ? pixB : pix_first;
+    f.n_first = n_first;
+    f.rawA = load_pixel_raw(a, f.nA, f.pixA);
+    f.rawB = load_pixel_raw(a, f.nB, f.pixB);
+    f.gA = f.gB = 0.0f;
+    if constexpr (BWD) {
+      if (a.g_image) {
+        f.gA = a.g_image[f.nA];
+        f.gB = a.g_image[f.nB];
+      }
+      if (a.g_pixel) {
+        f.gA += a.g_pixel[f.nA * a.HW + f.pixA];
+        f.gB += a.g_pixel[f.nB * a.HW + f.pixB];
+      }
+    }
+  };
+  Fetched cur{};
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, cur);
+
+  for (long long it = 0; it < t_cnt; ++it) {
+    const long long t = t_first + it * t_dir;
+    const uint32_t parity = static_cast<uint32_t>(it & 1);
+    const int rows = tile_rows(t);
+    const bool actA = lane < rows, actB = lane + 32 < rows;
+    const int ppA = actA ? lane : 0, ppB = actB ? lane + 32 : 0;
+    const long long iA = t * PPT + ppA, iB = t * PPT + ppB;
+    const long long nA = cur.nA, nB = cur.nB, n_first = cur.n_first;
+    const f2 g2 = pk(cur.gA, cur.gB);
+    PixelPair px;
+    {
+      Pixel pa, pb;
+      decode_pixel(a, cur.rawA, pa);
+      decode_pixel(a, cur.rawB, pb);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        px.x[c] = pk(pa.x[c], pb.x[c]);
+        px.ll[c] = pa.left[c];
+        px.lh[c] = pb.left[c];
+        px.rl[c] = pa.right[c];
+        px.rh[c] = pb.right[c];
+      }
+    }
+    if (!rev) {
+      n_own += step_n;
+      pix_own += step_pix;
+      if (pix_own >= a.HW) {
+        pix_own -= a.HW;
+        ++n_own;
+      }
+    } else {
+      n_own -= step_n;
+      pix_own -= step_pix;
+      if (pix_own < 0) {
+        pix_own += a.HW;
+        --n_own;
+      }
+    }
+    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, cur);
+
+    float* rowA = slot + ppA * ROWF;
+    float* rowB = slot + ppB * ROWF;
+    float* auxA = aux + ppA * M;
+    float* auxB = aux + ppB * M;
+    mbar_wait(bar, parity);
+
+    f2 lmax = pk(rowA[0], rowB[0]);
+#pragma unroll
+    for (int m = 1; m < M; ++m) lmax = pk(fmaxf(lo(lmax), rowA[m]), fmaxf(hi(lmax), rowB[m]));
+
+    f2 sumW = sp(0.0f), sumWP = sp(0.0f);
+#pragma unroll 1
+    for (int m = 0; m < M; ++m) {
+      const f2 lg = pk(rowA[m], rowB[m]);
+      f2 mu[3], sc[3], kp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mu[c] = pk(rowA[(1 + 3 * c) * M + m], rowB[(1 + 3 * c) * M + m]);
+        sc[c] = pk(rowA[(2 + 3 * c) * M + m], rowB[(2 + 3 * c) * M + m]);
+        kp[c] = pk(rowA[(3 + 3 * c) * M + m], rowB[(3 + 3 * c) * M + m]);
+      }
+      const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
+      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const f2 W = ex2_2((lg - lmax) * kLog2e);
+      f2 u[9];
+      f2 P;
+      if (narrow)
+        P = pair_eval<true, BWD, PixelPair>(px, mu, sc, kp, u);
+      else
+        P = pair_eval<false, BWD, PixelPair>(px, mu, sc, kp, u);
+      sumW = sumW + W;
+      sumWP = fma2(W, P, sumWP);
+      if constexpr (BWD) {
+        // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip (owners only)
+        const f2 wp = W * P;
+        if (actA) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) rowA[(1 + j) * M + m] = lo(u[j]);
+          auxA[m] = lo(wp);
+        }
+        if (actB) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) rowB[(1 + j) * M + m] = hi(u[j]);
+          auxB[m] = hi(wp);
+        }
+      }
+    }
+    const bool tinyA = !(lo(sumWP) > kTinySum), tinyB = !(hi(sumWP) > kTinySum);  // also catches NaN
+    const float* growA = a.params + iA * ROWF;
+    const float* growB = a.params + iB * ROWF;
+
+    if constexpr (!BWD) {
+      __syncwarp();
+      if (it + 1 < t_cnt) issue(t + t_dir);  // every lane has read its rows: re-arm the slot with the warp's next tile
+      float lpA = (lg2_split(lo(sumWP)) - lg2_split(lo(sumW))) * kLn2;  // utils/mdl.py:78-89 in one step
+      float lpB = (lg2_split(hi(sumWP)) - lg2_split(hi(sumW))) * kLn2;
+      if (tinyA) {
+        float lt, ll;
+        modl_pixel_logdomain(growA, M, half_pixel(px, false), lt, ll);
+        lpA = lt - ll;
+      }
+      if (tinyB) {
+        float lt, ll;
+        modl_pixel_logdomain(growB, M, half_pixel(px, true), lt, ll);
+        lpB = lt - ll;
+      }
+      if (a.lp_pixel) {
+        if (actA) a.lp_pixel[iA] = lpA;
+        if (actB) a.lp_pixel[iB] = lpB;
+      }
+      const float valA = actA ? lpA : 0.0f, valB = actB ? lpB : 0.0f;
+      if (a.partial) {
+        // a tile holds pixels of at most two images (HW >= 64 on this route): n_first and n_first + 1
+        while (n_base < n_first) {
+          const double done = warp_sum(acc0);
+          if (lane == 0) a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
+        }
+        if (nA == n_base)
+          acc0 += static_cast<double>(valA);
+        else
+          acc1 += static_cast<double>(valA);
+        if (nB == n_base)
+          acc0 += static_cast<double>(valB);
+        else
+          acc1 += static_cast<double>(valB);
+      } else if (a.ll_atomic) {
+        if (actA) atomicAdd(a.ll_atomic + nA, static_cast<double>(valA));
+        if (actB) atomicAdd(a.ll_atomic + nB, static_cast<double>(valB));
+      }
+    } else {
+      const f2 rS = rcp_2(sumWP), rSW = rcp_2(sumW);
+      float ltA = 0.f, llA = 0.f, ltB = 0.f, llB = 0.f;
+      Pixel pxa, pxb;
+      if (tinyA || tinyB) {
+        pxa = half_pixel(px, false);
+        pxb = half_pixel(px, true);
+        if (tinyA) modl_pixel_logdomain(growA, M, pxa, ltA, llA);
+        if (tinyB) modl_pixel_logdomain(growB, M, pxb, ltB, llB);
+      }
+#pragma unroll 1
+      for (int m = 0; m < M; ++m) {
+        const f2 lg = pk(rowA[m], rowB[m]);
+        const f2 W = ex2_2((lg - lmax) * kLog2e);
+        const f2 wp = pk(auxA[m], auxB[m]);
+        f2 r = wp * rS;     // posterior responsibility of the component
+        f2 pi = W * rSW;    // softmax(logits)
+        if (tinyA || tinyB) {
+          float rA = lo(r), rB = hi(r), piA = lo(pi), piB = hi(pi);
+          if (tinyA) {
+            rA = expf(modl_logt(growA, M, m, pxa) - ltA);
+            piA = expf(growA[m] - llA);
+          }
+          if (tinyB) {
+            rB = expf(modl_logt(growB, M, m, pxb) - ltB);
+            piB = expf(growB[m] - llB);
+          }
+          r = pk(rA, rB);
+          pi = pk(piA, piB);
+        }
+        const f2 gr = r * g2;
+        const f2 dl = (r - pi) * g2;
+        if (actA) {
+          rowA[m] = lo(dl);
+#pragma unroll
+          for (int j = 1; j < 10; ++j) rowA[j * M + m] *= lo(gr);
+        }
+        if (actB) {
+          rowB[m] = hi(dl);
+#pragma unroll
+          for (int j = 1; j < 10; ++j) rowB[j * M + m] *= hi(gr);
+        }
+      }
+      // hand the gradient tile to the TMA engine
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+      float* dst = a.dparams + t * TILE_F;
+      if ((bytes & 15u) == 0) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (a.bwd_hint)
+            bulk_s2g_hint(dst, slot, bytes, pol_first);
+          else
+            bulk_s2g(dst, slot, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = slot[q];
+        __syncwarp();
+      }
+      if (it + 1 < t_cnt) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        issue(t + t_dir);
+      }
+    }
+  }
+  if constexpr (BWD) {
+    if (lane == 0) bulk_wait_all<0>();
+  } else {
+    if (a.partial && t_cnt > 0) {
+      const long long n_last = (t_end * PPT < a.n_px ? t_end * PPT - 1 : a.n_px - 1) / a.HW;
+      const double d0 = warp_sum(acc0), d1 = warp_sum(acc1);
+      if (lane == 0) {
+        a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+        if (n_base + 1 <= n_last) a.partial[partial_slot(n_base + 1, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
+      }
+    }
+  }
+}
+
 // ---- any-M kernel: one thread per pixel-sample, parameters straight from global memory (correct, not tuned) --------------
 template <bool BWD>
 __global__ void __launch_bounds__(128) modl_generic_kernel(const ModlArgs a) {
@@ -790,6 +1150,45 @@ static Shape tune_shape(bool bwd, Shape dflt) {
   return dflt;
 }
 
+// Small problems: with only a few tiles per warp the rounding of tiles/warp up to an integer costs more than a little
+// occupancy does, so pick the warp count (>= 10) whose runs come out most even.  Large problems keep `max_warps`.
+static int pick_warps(long long num_tiles, int sm_count, int max_warps) {
+  if (getenv("VAEMDL_TUNE")) return max_warps;
+  if (num_tiles >= static_cast<long long>(sm_count) * max_warps * 8) return max_warps;
+  int best = max_warps;
+  double best_score = -1.0;
+  for (int w = max_warps; w >= 10 && w >= max_warps - 6; --w) {
+    const double per = static_cast<double>(num_tiles) / (static_cast<double>(sm_count) * w);
+    if (per <= 1.0) break;  // fewer tiles than warps: the grid shrinks instead
+    const double longest = static_cast<double>((num_tiles + static_cast<long long>(sm_count) * w - 1) / (static_cast<long long>(sm_count) * w));
+    const double score = per / longest * (0.8 + 0.2 * w / max_warps);
+    if (score > best_score) {
+      best_score = score;
+      best = w;
+    }
+  }
+  return best;
+}
+
+struct L2Opt {  // VAEMDL_L2="rev=0|1,keep=<MB>,hint=0|1": L2 reuse between the forward and the backward kernel of a step
+  int rev = 1, keep_mb = 48, hint = 0;  // measured on B200: profiles/r01_l2_reuse.txt
+  L2Opt() {
+    const char* e = getenv("VAEMDL_L2");
+    if (!e) return;
+    const char* q;
+    if ((q = strstr(e, "rev="))) rev = atoi(q + 4);
+    if ((q = strstr(e, "keep="))) keep_mb = atoi(q + 5);
+    if ((q = strstr(e, "hint="))) hint = atoi(q + 5);
+  }
+};
+static void apply_l2_opt(ModlArgs& a, long long total_warps, long long tile_bytes) {
+  static const L2Opt opt;
+  a.reverse = opt.rev;
+  a.bwd_hint = opt.hint;
+  a.keep_tiles = static_cast<int>((static_cast<long long>(opt.keep_mb) << 20) / (total_warps * tile_bytes));
+  if (opt.keep_mb > 0 && a.keep_tiles < 1) a.keep_tiles = 1;
+}
+
 struct TilePlan {  // how the forward grid split the tile range: what the per-image reduction needs to know
   long long total_warps = 0, tw_base = 0, tw_rem = 0;
   int K = 0, PPT = 0;
@@ -803,6 +1202,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   const size_t per_warp = (static_cast<size_t>(NSLOT) * T::TILE_F + (BWD ? T::AUX_F : 0)) * 4 + NSLOT * 8;
   if (warps > MAXT / 32) warps = MAXT / 32;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  warps = pick_warps(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
   auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT>;
@@ -835,25 +1235,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
-  {
-    // VAEMDL_L2="rev=0|1,keep=<MB>,hint=0|1": L2 reuse between the forward and the backward kernel of one step
-    static const struct L2Opt {
-      int rev = 1, keep_mb = 48, hint = 0;  // measured on B200: profiles/r01_l2_reuse.txt
-      L2Opt() {
-        const char* e = getenv("VAEMDL_L2");
-        if (!e) return;
-        const char* q;
-        if ((q = strstr(e, "rev="))) rev = atoi(q + 4);
-        if ((q = strstr(e, "keep="))) keep_mb = atoi(q + 5);
-        if ((q = strstr(e, "hint="))) hint = atoi(q + 5);
-      }
-    } opt;
-    a.reverse = opt.rev;
-    a.bwd_hint = opt.hint;
-    a.keep_tiles = static_cast<int>((static_cast<long long>(opt.keep_mb) << 20) / (total_warps * T::TILE_B));
-    if (opt.keep_mb > 0 && a.keep_tiles < 1) a.keep_tiles = 1;
-  }
-  a.small = a.n_px < (1ll << 31) - 64;
+  apply_l2_opt(a, total_warps, T::TILE_B);
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -874,8 +1256,85 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   return launch_tiled_shape<MC, LPP, BWD, 1, 512>(a, sh.warps, st, plan);
 }
 
+// pixel-pair kernel, n_mix = M (1 <= M <= 9): one slot per warp, as many warps as shared memory allows (<= 16)
+template <int M, bool BWD>
+static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
+  using T = TilePP<M>;
+  a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
+  const DeviceInfo& di = device_info();
+  const size_t per_warp = (static_cast<size_t>(T::TILE_F) + (BWD ? T::AUX_F : 0)) * 4 + 8;
+  int warps = tune_shape(BWD, Shape{1, 16}).warps;
+  while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  const size_t smem = warps * per_warp;
+  auto kern = modl_pp_kernel<M, BWD, 512>;
+  static std::mutex mu;
+  static int c_dev = -1, c_warps = -1, c_ctas = 1;
+  int ctas_per_sm;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_dev != dev || c_warps != warps) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_rc(e);
+      int n = 1;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem);
+      if (e != cudaSuccess) return cuda_rc(e);
+      c_dev = dev;
+      c_warps = warps;
+      c_ctas = n < 1 ? 1 : n;
+    }
+    ctas_per_sm = c_ctas;
+  }
+  const long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = static_cast<long long>(di.sm_count) * ctas_per_sm;
+  if (grid > need) grid = need;
+  if (grid * warps > kMaxGridWarps) grid = kMaxGridWarps / warps;
+  if (grid < 1) grid = 1;
+  const long long total_warps = grid * warps;
+  a.tw_base = a.num_tiles / total_warps;
+  a.tw_rem = a.num_tiles % total_warps;
+  a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  a.small = a.n_px < (1ll << 31) - 64;
+  apply_l2_opt(a, total_warps, T::TILE_B);
+  if (plan) {
+    plan->total_warps = total_warps;
+    plan->tw_base = a.tw_base;
+    plan->tw_rem = a.tw_rem;
+    plan->K = a.K;
+    plan->PPT = T::PPT;
+  }
+  kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
+  return cuda_rc(cudaGetLastError());
+}
+
+// n_mix 1..9 run on the pixel-pair kernel.  n_mix = 5 also has a component-pair instantiation with 32-row tiles, which
+// is a little faster while the problem is so small that a warp only sees a handful of tiles (measured: 112 vs 117 us
+// per step at 5 x 128 x 32 x 32, 345 vs 314 us backward at 16 x 64 x 64 x 64).
+static bool use_pixel_pairs(int M, long long n_px) {
+  const char* env = getenv("VAEMDL_PP");  // "0" / "1" force the choice for n_mix = 5 (A/B measurements, tests)
+  if (M < 1 || M > 9) return false;
+  if (M != 5) return true;
+  if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
+  return n_px >= 64ll * 148 * 16 * 6;
+}
+
 template <bool BWD>
 static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
+  if (use_pixel_pairs(a.M, a.n_px)) {
+    switch (a.M) {
+      case 1: return launch_pp<1, BWD>(a, st, plan);
+      case 2: return launch_pp<2, BWD>(a, st, plan);
+      case 3: return launch_pp<3, BWD>(a, st, plan);
+      case 4: return launch_pp<4, BWD>(a, st, plan);
+      case 5: return launch_pp<5, BWD>(a, st, plan);
+      case 6: return launch_pp<6, BWD>(a, st, plan);
+      case 7: return launch_pp<7, BWD>(a, st, plan);
+      case 8: return launch_pp<8, BWD>(a, st, plan);
+      case 9: return launch_pp<9, BWD>(a, st, plan);
+    }
+  }
   switch (a.M) {
     case 5:
       return launch_tiled<5, 1, BWD>(a, st, plan);
@@ -896,7 +1355,8 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   }
 }
 
-static int tile_ppt(int M) {
+static int tile_ppt(int M, long long n_px) {
+  if (use_pixel_pairs(M, n_px)) return 64;
   switch (M) {
     case 5:
     case 10:
@@ -958,7 +1418,7 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.x_unit = x_range == VAEMDL_RANGE_UNIT;
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
-  const int ppt = tile_ppt(M);
+  const int ppt = tile_ppt(M, a.n_px);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
   char* ws = static_cast<char*>(workspace);
   size_t tail_off = 0;
