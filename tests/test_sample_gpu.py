@@ -98,3 +98,35 @@ def test_random_sampler_statistics(V):
     x, idx = V.sample_from_discretized_mix_logistic(l.to(DEV), M, generator=gen, return_index=True)
     freq = torch.bincount(idx.flatten().long().cpu(), minlength=M).double() / idx.numel()
     assert (freq - torch.softmax(logits.double(), 0)).abs().max().item() < 1e-2
+
+
+def test_gumbel_near_ties_are_decided_in_float64(V):
+    """Winners that lead by less than float32 can resolve (1e-9 .. 1e-5), exact ties (first maximum wins) and a
+    degenerate u -> the kernel's float32 search must hand over to float64 and agree with the oracle everywhere."""
+    g = torch.Generator().manual_seed(77)
+    N, H, W, M = 6, 16, 16, 10
+    l = torch.randn(N, H, W, 10 * M, generator=g)
+    u_mix = torch.rand(N, H, W, M, generator=g) * (1 - 2e-5) + 1e-5
+    u_log = torch.rand(N, H, W, 3, generator=g) * (1 - 2e-5) + 1e-5
+    # make component 7 trail the current winner by a tiny margin that differs per image (float64 arithmetic)
+    gum = l[..., :M].double() - torch.log(-torch.log(u_mix.double()))
+    best, arg = gum.max(-1)
+    margins = torch.tensor([0.0, 1e-9, 1e-7, 1e-6, 1e-5, -1e-7]).view(N, 1, 1)
+    other = torch.where(arg == 7, torch.full_like(arg, 2), torch.full_like(arg, 7))
+    noise_other = -torch.log(-torch.log(u_mix.double().gather(-1, other[..., None])))[..., 0]
+    new_logit = (best - margins - noise_other).float()      # float32 logit: the realised margin is whatever float32 leaves
+    l[..., :M].scatter_(-1, other[..., None], new_logit[..., None])
+    x64, idx64 = O.sample_from_discretized_mix_logistic(l, M, u_mix, u_log)
+    x, xq, idx = V.sample_from_discretized_mix_logistic(l.to(DEV), M, u_mix.to(DEV), u_log.to(DEV), return_index=True,
+                                                        return_quantised=True)
+    assert int((idx.cpu().long() != idx64).sum()) == 0
+    assert int((xq.cpu() != O.quantise(x64 * 0.5 + 0.5)).sum()) == 0
+    # exact ties: identical logits and identical noise in two components -> the first one wins on both sides
+    l2 = torch.randn(2, 8, 8, 10 * M, generator=g)
+    l2[..., 3] = l2[..., 8] = 9.0
+    u2 = torch.rand(2, 8, 8, M, generator=g) * (1 - 2e-5) + 1e-5
+    u2[..., 8] = u2[..., 3]
+    ul2 = torch.rand(2, 8, 8, 3, generator=g) * (1 - 2e-5) + 1e-5
+    _, i64 = O.sample_from_discretized_mix_logistic(l2, M, u2, ul2)
+    _, i2 = V.sample_from_discretized_mix_logistic(l2.to(DEV), M, u2.to(DEV), ul2.to(DEV), return_index=True)
+    assert int((i2.cpu().long() != i64).sum()) == 0 and int((i64 == 8).sum()) == 0
