@@ -39,6 +39,7 @@ WORKLOADS = {
     "cfg5_128_m30": ("modl", 16, 32, 128, 128, 30),
     "cfg1": ("modl", 5, 64, 32, 32, 10),
     "cfg1_m5": ("modl", 5, 128, 32, 32, 5),
+    "cfg5_64_m5": ("modl", 16, 64, 64, 64, 5),
 }
 DEFAULT_WORKLOAD = "cfg5_64_m10"
 L2_BYTES = 126 * 1024 * 1024
@@ -353,7 +354,7 @@ def also_workloads(dev, peak):
             fn_with_stream(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         return timeit(g.replay, iters)
 
-    for name in ["cfg1", "cfg1_m5", "cfg5_64_m30", "cfg5_128_m10"]:
+    for name in ["cfg1", "cfg1_m5", "cfg5_64_m5", "cfg5_64_m30", "cfg5_128_m10", "cfg5_128_m30"]:
         _, S, B, H, W, M = WORKLOADS[name]
         # small shapes rotate over enough buffers that a step's input was last touched > 2 x L2 bytes ago
         nbuf = max(2, -(-3 * L2_BYTES // (S * B * H * W * 40 * M)))
