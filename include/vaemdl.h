@@ -65,6 +65,8 @@ extern "C" {
 /* sampler variants */
 #define VAEMDL_SAMPLE_OPENAI 0 /* select mixture first, one logistic draw per sub-pixel (utils/mdl_openai.py:160-193); u_log [n,H,W,3] */
 #define VAEMDL_SAMPLE_MDL 1    /* a draw for every mixture, then select (utils/mdl.py:209-252); u_log [n,H,W,3,M] */
+#define VAEMDL_SAMPLE_PLAIN 2  /* utils/mdl_plain.py:68-102: means chained on the means, channels drawn independently, clip
+                                  to [-1,1]; u_log [n,H,W,3,M], or NULL for .mean() (:104-121: the selected locations) */
 
 VAEMDL_API int vaemdl_version(void);
 VAEMDL_API const char* vaemdl_strerror(int code);
@@ -120,6 +122,28 @@ VAEMDL_API int vaemdl_modl_iwae_fwd(const float* params, const void* x, int x_dt
  * The log-scale gradient is masked with (raw_log_scale >= -7) (tf.maximum, utils/mdl.py:109).
  * ------------------------------------------------------------------------ */
 VAEMDL_API int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    const float* g_image, const float* g_pixel,
+                    float* dparams, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Pixel mixture of discretized logistics WITHOUT conditioning on the observed x
+ * replaces: PixelMixtureDiscretizedLogistic.log_prob + get_mixture_params   utils/mdl_plain.py:36-66, :124-168
+ * Same parameter row, same outputs and workspace as the entry points above; the only difference is the chain of
+ * means: loc_g = mu_g + tanh(kR)*loc_r, loc_b = mu_b + tanh(kG)*loc_r + tanh(kB)*loc_g (utils/mdl_plain.py:160-162)
+ * instead of the observed x_r, x_g.  x in [0,1] (the class rescales, :45), edges x <= -1 / x >= 1, the class's default
+ * low = -1, high = 1, levels = 256.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_plain_fwd(const float* params, const void* x, int x_dtype,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    float* lp_pixel, float* ll_image, double* ll_image_f64,
+                    void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_plain_iwae_fwd(const float* params, const void* x, int x_dtype,
+                    int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                    const float* extra,
+                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                    void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_plain_bwd(const float* params, const void* x, int x_dtype,
                     long long n_img, int x_batch, int H, int W, int M,
                     const float* g_image, const float* g_pixel,
                     float* dparams, void* stream);

@@ -32,6 +32,9 @@ __all__ = [
     "modl_openai_log_prob",
     "modl_openai_iwae_log_prob",
     "modl_sample_mdl",
+    "mdl_plain_get_mixture_params",
+    "mdl_plain_log_prob",
+    "mdl_plain_sample",
     "modl_openai_sample",
     "modl_openai_iwae_sample",
     "dlogistic_log_prob",
@@ -273,6 +276,49 @@ def modl_sample_mdl(parameters: torch.Tensor, u_mix: torch.Tensor, u_log: torch.
     onehot = torch.nn.functional.one_hot(idx, mix_logits.shape[-1]).to(ar.dtype).unsqueeze(-2)  # :240
     selected = torch.sum(ar * onehot, dim=-1)                                    # :245-247
     return selected * 0.5 + 0.5, idx                                             # :250
+
+
+# --------------------------------------------------------------------------- #
+# utils/mdl_plain.py : PixelMixtureDiscretizedLogistic (no conditioning on x)    #
+# --------------------------------------------------------------------------- #
+def mdl_plain_get_mixture_params(parameters: torch.Tensor):
+    """``get_mixture_params`` -- utils/mdl_plain.py:124-168: the green / blue means are chained on the component's OWN
+    red / green means (:160-162), not on the observed x.  Returns ``loc, logscale [..., 3, M]``, ``mix_logits [..., M]``."""
+    _loc, logscale, coeffs, mix_logits = modl_split_params(parameters)           # :143-154 (same split, clamp, tanh)
+    loc_r = _loc[..., 0, :]                                                      # :160
+    loc_g = _loc[..., 1, :] + coeffs[..., 0, :] * loc_r                          # :161
+    loc_b = _loc[..., 2, :] + coeffs[..., 1, :] * loc_r + coeffs[..., 2, :] * loc_g  # :162
+    loc = torch.cat([loc_r[..., None, :], loc_g[..., None, :], loc_b[..., None, :]], dim=-2)  # :164-166
+    return loc, logscale, mix_logits
+
+
+def mdl_plain_log_prob(parameters: torch.Tensor, x01: torch.Tensor) -> torch.Tensor:
+    """``PixelMixtureDiscretizedLogistic.log_prob`` -- utils/mdl_plain.py:36-66 (default low=-1, high=1, levels=256).
+    Returns ``[..., H, W]`` (no trailing 1: :66 reduces over the mixture axis only)."""
+    loc, logscale, mix_logits = mdl_plain_get_mixture_params(parameters)         # :27
+    x = x01 * 2.0 - 1.0                                                          # :45
+    lp = dlogistic_log_prob(x[..., None], loc, logscale, -1.0, 1.0, 256.0)       # :49-51 (DiscretizedLogistic.log_prob)
+    mix_log_weights = _log_softmax(mix_logits, -1)                               # :55
+    weighted = torch.sum(lp, dim=-2) + mix_log_weights                           # :59-61
+    return _reduce_logsumexp(weighted, -1)                                       # :66
+
+
+def mdl_plain_sample(parameters: torch.Tensor, u_mix: torch.Tensor, u_log):
+    """``PixelMixtureDiscretizedLogistic.sample`` (utils/mdl_plain.py:68-102) / ``.mean`` (:104-121) with explicit noise:
+    ``u_mix [..., H, W, M]`` selects the component (Gumbel-argmax stands in for tfd.Categorical), ``u_log
+    [..., H, W, 3, M]`` drives ``DiscretizedLogistic.sample`` for every component (:86-88); ``u_log=None`` gives
+    ``mean()``: the selected, clipped locations.  float64.  Returns ``(x01 [..., H, W, 3], idx)``."""
+    loc, logscale, mix_logits = mdl_plain_get_mixture_params(parameters.double())
+    idx = gumbel_argmax(mix_logits, u_mix)                                       # :77-78 / :107-108
+    onehot = torch.nn.functional.one_hot(idx, mix_logits.shape[-1]).to(loc.dtype).unsqueeze(-2)  # :79-81
+    if u_log is None:
+        vals = loc                                                               # :116-118
+    else:
+        vals = dlogistic_sample(loc, logscale, u_log, -1.0, 1.0)                 # :86-88 (clipped to [low, high])
+    sel = torch.sum(vals * onehot, dim=-1)                                       # :93-95
+    if u_log is None:
+        sel = torch.clamp(sel, -1.0, 1.0)                                        # :119
+    return (sel + 1.0) / 2.0, idx                                                # :98 / :120
 
 
 # --------------------------------------------------------------------------- #

@@ -1,0 +1,91 @@
+"""GPU parity tests of ``PixelMixtureDiscretizedLogistic`` (utils/mdl_plain.py: means chained on the means)."""
+import pytest
+import torch
+
+import oracle as O
+from util import GRAD_RTOL, LL_RTOL, assert_grad_close, canonical, relnorm, trained_like
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def V(built_lib):
+    import vae_mdl_b200
+    return vae_mdl_b200
+
+
+def _oracle(params, x_u8, g_image):
+    p64 = params.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    lp = O.mdl_plain_log_prob(p64, x64)
+    ll = lp.sum((-1, -2))
+    (ll * g_image.double()).sum().backward()
+    return lp.detach(), ll.detach(), p64.grad
+
+
+@pytest.mark.parametrize("S,B,H,W,M", [(2, 3, 8, 8, 10), (2, 2, 8, 8, 5), (1, 2, 8, 8, 20), (1, 2, 8, 9, 30), (2, 1, 5, 7, 3),
+                                        (1, 2, 4, 4, 13), (1, 1, 16, 16, 10), (2, 2, 3, 3, 7)])
+@pytest.mark.parametrize("dist", ["canonical", "trained"])
+def test_log_prob_and_gradient_vs_oracle(V, S, B, H, W, M, dist):
+    make = canonical if dist == "canonical" else trained_like
+    params, x_u8, g = make(900 + 13 * M + W, S, B, H, W, M)
+    x_u8[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    g_image = torch.randn(S, B, generator=g)
+    lp64, ll64, grad64 = _oracle(params, x_u8, g_image)
+    pd = params.to(DEV).requires_grad_(True)
+    d = V.PixelMixtureDiscretizedLogistic(pd)
+    lp = d.log_prob(O.normalize_u8(x_u8).to(DEV))
+    assert lp.shape == (S, B, H, W)
+    if dist == "canonical":
+        assert (lp.detach().cpu().double() - lp64).abs().max().item() < 5e-5
+    ll = d.log_likelihood(x_u8.to(DEV), dtype=torch.float64)
+    # trained-like data: an element within rounding of the 1e-5 branch threshold may take either branch (see util)
+    rel = ((ll.detach().cpu() - ll64).abs() / ll64.abs())
+    ok = rel <= LL_RTOL
+    assert bool(ok.all()) or dist == "trained" and float(ok.float().mean()) >= 0.5
+    (d.log_likelihood(x_u8.to(DEV)) * g_image.to(DEV)).sum().backward()
+    if bool(ok.all()):
+        assert_grad_close(pd.grad, grad64, M)
+    else:
+        assert relnorm(pd.grad.cpu()[ok], grad64[ok]) <= GRAD_RTOL
+
+
+def test_fused_iwae_step_plain(V):
+    from vae_mdl_b200 import functional as F
+    S, B, H, W, M = 4, 5, 8, 8, 10
+    params, x_u8, g = canonical(77, S, B, H, W, M)
+    p64 = params.double().requires_grad_(True)
+    ll64 = O.mdl_plain_log_prob(p64, O.normalize_u8(x_u8, torch.float64)).sum((-1, -2))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()) + torch.randn(S, B, generator=g).double()
+    loss64 = -O.logmeanexp(ll64 + extra, 0).mean()
+    loss64.backward()
+    ll, log_w, lme_b, elbo, g_ll = F.modl_iwae_forward(params.to(DEV), x_u8.to(DEV), extra.float().to(DEV), plain=True)
+    assert abs(-elbo.item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
+    dp = F.modl_backward(params.to(DEV), x_u8.to(DEV), g_image=g_ll, plain=True)
+    assert_grad_close(dp, p64.grad, M)
+
+
+def test_sample_mean_and_attributes(V):
+    g = torch.Generator().manual_seed(8)
+    B, H, W, M = 3, 8, 8, 5
+    p = torch.randn(B, H, W, 10 * M, generator=g)
+    n = 3
+    um = torch.rand(n, B, H, W, M, generator=g) * (1 - 2e-5) + 1e-5
+    ul = torch.rand(n, B, H, W, 3, M, generator=g) * (1 - 2e-5) + 1e-5
+    d = V.PixelMixtureDiscretizedLogistic(p.to(DEV))
+    x, xq, idx = d.sample(n, u_mix=um.to(DEV), u_log=ul.to(DEV), return_index=True, return_quantised=True)
+    want, widx = O.mdl_plain_sample(p.expand(n, B, H, W, 10 * M), um, ul)
+    assert x.shape == (n, B, H, W, 3)
+    assert int((idx.cpu().long() != widx).sum()) == 0
+    assert int((xq.cpu() != O.quantise(want)).sum()) == 0
+    assert (x.cpu().double() - want).abs().max().item() < 1e-6
+    m = d.mean(u_mix=um[:1].to(DEV))
+    wm, _ = O.mdl_plain_sample(p, um[0], None)
+    assert m.shape == (B, H, W, 3) and (m.cpu().double() - wm).abs().max().item() < 1e-6
+    assert d.sample().shape == (B, H, W, 3) and d.sample([2]).shape == (2, B, H, W, 3)
+    assert d.n_mix == M and d.mix_logits.shape == (B, H, W, M) and d.loc.shape == (B, H, W, 3, M)
+    loc64, ls64, _ = O.mdl_plain_get_mixture_params(p.double())
+    assert relnorm(d.loc, loc64) < 1e-6 and relnorm(d.logscale, ls64) < 1e-6
+    with pytest.raises(ValueError):
+        V.PixelMixtureDiscretizedLogistic(p.to(DEV), low=0.0)

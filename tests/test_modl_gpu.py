@@ -284,3 +284,49 @@ def test_pixel_pair_kernel_vs_oracle(F, monkeypatch, S, B, H, W, M, force):
         assert_grad_close(dp, grad64, M)
     else:
         assert relnorm(dp[ok], grad64[ok]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("S,B,H,W,M", [(2, 3, 8, 8, 10), (3, 1, 5, 7, 5), (1, 3, 3, 3, 10), (2, 1, 7, 3, 30), (1, 2, 9, 9, 2),
+                                        (2, 2, 5, 5, 7), (1, 1, 1, 1, 10), (5, 2, 16, 12, 5), (2, 2, 6, 6, 20), (1, 2, 4, 4, 13)])
+def test_no_write_outside_the_callers_buffers(built_lib, S, B, H, W, M):
+    """Guard words around every output and around the workspace (exactly vaemdl_modl_workspace_bytes long) must survive
+    the forward, fused-finish and backward launches on ragged shapes (compute-sanitizer is not available on this pool)."""
+    L = built_lib
+    n_img, n_px = S * B, S * B * H * W
+    g = torch.Generator().manual_seed(S + B + H + W + M)
+    params = torch.randn(S, B, H, W, 10 * M, generator=g).to(DEV)
+    x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).to(DEV)
+    G = 64  # guard elements on each side
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+
+    ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W)
+    ws_buf, ws = guarded((ws_bytes + 7) // 8, torch.float64, -7.0)
+    lp_buf, lp = guarded(n_px, torch.float32, -7.0)
+    ll_buf, ll = guarded(n_img, torch.float32, -7.0)
+    ll64_buf, ll64 = guarded(n_img, torch.float64, -7.0)
+    lw_buf, lw = guarded(n_img, torch.float32, -7.0)
+    gl_buf, gl = guarded(n_img, torch.float32, -7.0)
+    lme_buf, lme = guarded(B, torch.float32, -7.0)
+    el_buf, el = guarded(1, torch.float32, -7.0)
+    dp_buf, dp = guarded(n_px * 10 * M + 0, torch.float32, -7.0)
+    assert ws.data_ptr() % 8 == 0
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if dp.data_ptr() % 16:  # the gradient pointer must be 16-byte aligned: shift the view inside the guard band
+        pytest.skip("allocator returned an unaligned guard view")
+    rc = L.vaemdl_modl_fwd(params.data_ptr(), x.data_ptr(), 1, 0, 0, n_img, B, H, W, M, lp.data_ptr(), ll.data_ptr(),
+                           ll64.data_ptr(), ws.data_ptr(), ws_bytes, st)
+    assert rc == 0
+    rc = L.vaemdl_modl_iwae_fwd(params.data_ptr(), x.data_ptr(), 1, 0, 0, S, B, 0, B, H, W, M, None, ll.data_ptr(),
+                                ll64.data_ptr(), lw.data_ptr(), lme.data_ptr(), el.data_ptr(), gl.data_ptr(), ws.data_ptr(),
+                                ws_bytes, st)
+    assert rc == 0
+    rc = L.vaemdl_modl_bwd(params.data_ptr(), x.data_ptr(), 1, 0, 0, n_img, B, H, W, M, gl.data_ptr(), None, dp.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for name, buf in [("ws", ws_buf), ("lp", lp_buf), ("ll", ll_buf), ("ll64", ll64_buf), ("log_w", lw_buf), ("g_ll", gl_buf),
+                      ("lme", lme_buf), ("elbo", el_buf), ("dparams", dp_buf)]:
+        assert bool((buf[:G] == -7.0).all()) and bool((buf[-G:] == -7.0).all()), f"guard band of {name} was overwritten"
+    assert not bool(torch.isnan(dp).any()) and bool((lp != -7.0).all()) and bool((dp != -7.0).any())

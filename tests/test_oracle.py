@@ -298,3 +298,55 @@ def test_oracle_reproduces_dl_and_sample_golden():
                                                     torch.from_numpy(z["u_log"]))
     assert np.array_equal(idx.numpy().astype(np.uint8), z["idx"])
     assert np.array_equal(O.quantise(x * 0.5 + 0.5).numpy(), z["q_openai"])
+
+
+# --------------------------------------------------------------------------------------------------
+# utils/mdl_plain.py (no conditioning on the observed x)
+# --------------------------------------------------------------------------------------------------
+def test_mdl_plain_equals_conditioned_class_when_the_chain_is_cut():
+    """With zero coefficients (tanh(0) = 0) both classes are the same mixture of independent channels."""
+    g = torch.Generator().manual_seed(3)
+    p = torch.randn(2, 3, 4, 4, 50, generator=g, dtype=torch.float64)
+    for c in range(3):
+        p[..., 5 + 15 * c + 10:5 + 15 * c + 15] = 0.0
+    x = torch.floor(torch.rand(3, 4, 4, 3, generator=g, dtype=torch.float64) * 256) / 255
+    assert torch.allclose(O.mdl_plain_log_prob(p, x), O.modl_log_prob(p, x)[..., 0], atol=1e-12)
+
+
+def test_mdl_plain_chain_follows_the_means_not_x():
+    """utils/mdl_plain.py:160-162: a hand-computed single-component pixel."""
+    M = 1
+    row = torch.tensor([0.3, 0.2, -1.0, 0.5, -0.1, -1.5, -0.4, 0.05, -2.0, 0.7], dtype=torch.float64)  # [logit|muR sR kR|muG sG kG|muB sB kB]
+    loc, ls, _ = O.mdl_plain_get_mixture_params(row.view(1, 1, 1, 10 * M))
+    k = torch.tanh(torch.tensor([0.5, -0.4, 0.7], dtype=torch.float64))
+    want_g = -0.1 + k[0] * 0.2
+    want_b = 0.05 + k[1] * 0.2 + k[2] * want_g
+    assert torch.allclose(loc.flatten(), torch.stack([torch.tensor(0.2, dtype=torch.float64), want_g, want_b]), atol=1e-15)
+    x = torch.tensor([[[[10, 200, 255]]]], dtype=torch.float64) / 255
+    lp = O.mdl_plain_log_prob(row.view(1, 1, 1, 10), x)
+    want = O.dlogistic_log_prob((x * 2 - 1)[..., None], loc, ls, -1.0, 1.0, 256.0).sum()
+    assert abs(lp.item() - want.item()) < 1e-12
+
+
+def test_mdl_plain_autograd_matches_finite_differences():
+    g = torch.Generator().manual_seed(5)
+    p = (torch.randn(1, 2, 2, 30, generator=g, dtype=torch.float64) * 0.7).requires_grad_(True)
+    x = torch.tensor([[[[3, 128, 255], [0, 17, 99]], [[250, 1, 64], [128, 128, 128]]]], dtype=torch.float64) / 255
+    assert torch.autograd.gradcheck(lambda q: O.mdl_plain_log_prob(q, x).sum(), (p,), eps=1e-6, atol=1e-6, rtol=1e-4)
+
+
+def test_mdl_plain_sample_and_mean():
+    g = torch.Generator().manual_seed(6)
+    p = torch.randn(2, 4, 4, 50, generator=g)
+    um = torch.rand(2, 4, 4, 5, generator=g) * (1 - 2e-5) + 1e-5
+    ul = torch.rand(2, 4, 4, 3, 5, generator=g) * (1 - 2e-5) + 1e-5
+    x, idx = O.mdl_plain_sample(p, um, ul)
+    assert x.shape == (2, 4, 4, 3) and x.min() >= 0 and x.max() <= 1
+    m, idx2 = O.mdl_plain_sample(p, um, None)
+    assert torch.equal(idx, idx2)
+    loc, _, _ = O.mdl_plain_get_mixture_params(p.double())
+    want = (torch.clamp(torch.gather(loc, -1, idx[..., None, None].expand(2, 4, 4, 3, 1))[..., 0], -1, 1) + 1) / 2
+    assert torch.allclose(m, want, atol=1e-15)
+    # u = 0.5 is a zero logistic draw: the sample equals the mean
+    x0, _ = O.mdl_plain_sample(p, um, torch.full_like(ul, 0.5))
+    assert torch.allclose(x0, m, atol=1e-15)

@@ -8,6 +8,7 @@ from . import _abi
 from .discretized_logistic import DiscretizedLogistic
 from .loss import dlogistic_iwae_step, elbo_loss, iwae_loss, loss_fn, modl_iwae_step
 from .mdl import MixtureDiscretizedLogistic
+from .mdl_plain import PixelMixtureDiscretizedLogistic, get_mixture_params
 from .mdl_openai import (MixtureDiscretizedLogisticOpenai, discretized_mix_logistic_loss, int_shape,
                          log_prob_from_logits, log_sum_exp, sample_from_discretized_mix_logistic)
 from .mdl_openai_iwae import MixtureDiscretizedLogisticOpenaiIWAE
@@ -18,6 +19,8 @@ __all__ = [
     "MixtureDiscretizedLogistic",
     "MixtureDiscretizedLogisticOpenai",
     "MixtureDiscretizedLogisticOpenaiIWAE",
+    "PixelMixtureDiscretizedLogistic",
+    "get_mixture_params",
     "discretized_mix_logistic_loss",
     "sample_from_discretized_mix_logistic",
     "log_sum_exp",

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libvaemdl_b200.so")
 X_F32, X_U8 = 0, 1
 RANGE_UNIT, RANGE_SYM = 0, 1
 EDGE_MDL, EDGE_OPENAI = 0, 1
-SAMPLE_OPENAI, SAMPLE_MDL = 0, 1
+SAMPLE_OPENAI, SAMPLE_MDL, SAMPLE_PLAIN = 0, 1, 2
 MAX_MIX = 64
 
 _LIB = None
@@ -37,6 +37,13 @@ PROTOTYPES = {
                                      c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_modl_plain_fwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_plain_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
+                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_plain_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "vaemdl_dlogistic_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_longlong,
                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

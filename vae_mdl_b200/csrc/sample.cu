@@ -25,7 +25,8 @@ struct SampleArgs {
   long long n_px;   // pixels of ONE repetition (n_img * H * W)
   long long n_rep;  // the parameters are re-used for n_rep consecutive blocks of noise / output
   int M;
-  int variant_mdl;
+  int variant_mdl;    // u_log carries a draw for every mixture: [.., 3, M]
+  int variant_plain;  // utils/mdl_plain.py: means chained on the means, no sequential dependence between the channels
   int out_unit;
 };
 
@@ -96,18 +97,36 @@ __global__ void __launch_bounds__(256) modl_sample_kernel(const SampleArgs a) {
     }
     double xs[3];
     double coef[3];
+    double noise_keep[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const double mu = static_cast<double>(row[M + c * 3 * M + sel]);                              // :177
       const double ls = fmax(static_cast<double>(row[M + c * 3 * M + M + sel]), -7.0);              // :178-180
       coef[c] = tanh(static_cast<double>(row[M + c * 3 * M + 2 * M + sel]));                        // :181
-      const double u = static_cast<double>(a.variant_mdl ? a.u_log[(i * 3 + c) * M + sel] : a.u_log[i * 3 + c]);
-      xs[c] = mu + exp(ls) * log(u / (1.0 - u));                                                    // :185-186 (log u - log(1-u))
+      double noise = 0.0;  // u_log == NULL (plain variant only): the selected location itself (utils/mdl_plain.py:104-121)
+      if (a.u_log) {
+        const double u = static_cast<double>(a.variant_mdl ? a.u_log[(i * 3 + c) * M + sel] : a.u_log[i * 3 + c]);
+        noise = exp(ls) * log(u / (1.0 - u));                                                       // :185-186 (log u - log(1-u))
+      }
+      xs[c] = a.variant_plain ? mu : mu + noise;  // plain variant: the noise goes on top of the chained means below
+      noise_keep[c] = noise;
     }
-    const double x0 = fmin(fmax(xs[0], -1.0), 1.0);                                                 // :190
-    const double x1 = fmin(fmax(xs[1] + coef[0] * x0, -1.0), 1.0);                                  // :191
-    const double x2 = fmin(fmax(xs[2] + coef[1] * x0 + coef[2] * x1, -1.0), 1.0);                   // :192
-    const double xo[3] = {x0, x1, x2};
+    double xo[3];
+    if (!a.variant_plain) {
+      const double x0 = fmin(fmax(xs[0], -1.0), 1.0);                                               // :190
+      const double x1 = fmin(fmax(xs[1] + coef[0] * x0, -1.0), 1.0);                                // :191
+      const double x2 = fmin(fmax(xs[2] + coef[1] * x0 + coef[2] * x1, -1.0), 1.0);                 // :192
+      xo[0] = x0;
+      xo[1] = x1;
+      xo[2] = x2;
+    } else {
+      const double l0 = xs[0];                                                                      // utils/mdl_plain.py:160
+      const double l1 = xs[1] + coef[0] * l0;                                                       // :161
+      const double l2 = xs[2] + coef[1] * l0 + coef[2] * l1;                                        // :162
+      xo[0] = fmin(fmax(l0 + noise_keep[0], -1.0), 1.0);                                            // discretized_logistic.py:80-85
+      xo[1] = fmin(fmax(l1 + noise_keep[1], -1.0), 1.0);
+      xo[2] = fmin(fmax(l2 + noise_keep[2], -1.0), 1.0);
+    }
     __syncwarp();  // every lane is done with the slot before the next bulk copy overwrites it
     if (active) {
 #pragma unroll
@@ -128,9 +147,10 @@ using namespace vaemdl;
 extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const float* u_log, int variant,
                                   int out_range, long long n_rep, long long n_img, int H, int W, int M, float* x_out,
                                   uint8_t* x_q, uint8_t* idx, void* stream) {
-  if (!params || !u_mix || !u_log || n_rep <= 0 || n_img <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
+  if (!params || !u_mix || n_rep <= 0 || n_img <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
+  if (!u_log && variant != VAEMDL_SAMPLE_PLAIN) return VAEMDL_EINVAL;
   if (!x_out && !x_q && !idx) return VAEMDL_EINVAL;
-  if (variant != VAEMDL_SAMPLE_OPENAI && variant != VAEMDL_SAMPLE_MDL) return VAEMDL_EINVAL;
+  if (variant != VAEMDL_SAMPLE_OPENAI && variant != VAEMDL_SAMPLE_MDL && variant != VAEMDL_SAMPLE_PLAIN) return VAEMDL_EINVAL;
   if (out_range != VAEMDL_RANGE_UNIT && out_range != VAEMDL_RANGE_SYM) return VAEMDL_EINVAL;
   if (M < 1 || M > VAEMDL_MAX_MIX) return VAEMDL_EUNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(params) & 15u) return VAEMDL_EALIGN;
@@ -144,7 +164,8 @@ extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const
   a.n_px = n_img * H * W;
   a.n_rep = n_rep;
   a.M = M;
-  a.variant_mdl = variant == VAEMDL_SAMPLE_MDL;
+  a.variant_mdl = variant != VAEMDL_SAMPLE_OPENAI;
+  a.variant_plain = variant == VAEMDL_SAMPLE_PLAIN;
   a.out_unit = out_range == VAEMDL_RANGE_UNIT;
   const DeviceInfo& di = device_info();
   const size_t tile_b = static_cast<size_t>(32) * 10 * M * 4;

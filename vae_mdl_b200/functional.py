@@ -55,8 +55,9 @@ class _ModlFn(torch.autograd.Function):
     """Forward: per-pixel log-prob or per-image log-likelihood (float32 or float64 sums).  Backward: one fused kernel."""
 
     @staticmethod
-    def forward(ctx, params, x, x_range, edge_mode, mode):
+    def forward(ctx, params, x, x_range, edge_mode, mode, plain=False):
         # mode: "pixel" -> [..., H, W] ; "image" -> [...] float32 ; "image64" -> [...] float64
+        # plain: utils/mdl_plain.py (means chained on the means) instead of utils/mdl.py (chained on the observed x)
         p = dense_f32(params, "parameters")
         H, W, C10 = p.shape[-3], p.shape[-2], p.shape[-1]
         M = C10 // 10
@@ -79,31 +80,41 @@ class _ModlFn(torch.autograd.Function):
             ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W)
             ws = torch.empty((ws_bytes + 7) // 8, device=p.device, dtype=torch.float64)
         with torch.cuda.device(p.device):
-            check(L.vaemdl_modl_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
-                                    ptr(lp), ptr(ll), ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)),
-                  "vaemdl_modl_fwd")
+            if plain:
+                if x_range != _abi.RANGE_UNIT or edge_mode != _abi.EDGE_MDL:
+                    raise ValueError("the plain pixel mixture takes x in [0,1] and the <= -1 / >= 1 edge tests")
+                check(L.vaemdl_modl_plain_fwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(lp), ptr(ll), ptr(ll64),
+                                              ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_plain_fwd")
+            else:
+                check(L.vaemdl_modl_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                                        ptr(lp), ptr(ll), ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)),
+                      "vaemdl_modl_fwd")
         ctx.save_for_backward(p, xd)
-        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode)
+        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain)
         return lp if mode == "pixel" else (ll64 if mode == "image64" else ll)
 
     @staticmethod
     def backward(ctx, g):
         p, xd = ctx.saved_tensors
-        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode = ctx.meta
+        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain = ctx.meta
         if g is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         g = dense_f32(g, "upstream gradient")
         g_pixel, g_image = (g, None) if mode == "pixel" else (None, g)
         dp = torch.empty_like(p)
         with torch.cuda.device(p.device):
-            check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
-                                        ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
-        return dp, None, None, None, None
+            if plain:
+                check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(g_image),
+                                                  ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
+            else:
+                check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                                            ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+        return dp, None, None, None, None, None
 
 
 def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch.Tensor] = None,
                   g_pixel: Optional[torch.Tensor] = None, x_range: int = _abi.RANGE_UNIT,
-                  edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
+                  edge_mode: int = _abi.EDGE_MDL, plain: bool = False) -> torch.Tensor:
     """The gradient kernel on its own: d/dparams of sum(g_image * ll_image) + sum(g_pixel * lp_pixel)."""
     p = dense_f32(params, "parameters")
     H, W, C10 = p.shape[-3:]
@@ -115,13 +126,17 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
     gp = dense_f32(g_pixel, "g_pixel") if g_pixel is not None else None
     dp = torch.empty_like(p)
     with torch.cuda.device(p.device):
-        check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
-                                    ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+        if plain:
+            check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, ptr(gi), ptr(gp),
+                                              ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
+        else:
+            check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
+                                        ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
     return dp
 
 
 def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: int = 0,
-                      x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL):
+                      x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL, plain: bool = False):
     """MoDL forward fused with the IWAE tail in TWO launches (``vaemdl_modl_iwae_fwd``): ``params [S,B,H,W,10M]``,
     ``x [B,H,W,3]``, ``extra = beta*(lpz-lqzx) [S,B]`` or None.  Returns ``(lpxz float64 [S,B], log_w, lme_b [B],
     elbo [1], g_ll [S,B])`` with ``g_ll = d(-elbo)/d lpxz`` (models/loss.py:32-37).  Not recorded by autograd."""
@@ -146,24 +161,31 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
     ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
     with torch.cuda.device(dev):
-        check(L.vaemdl_modl_iwae_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
-                                     ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
-                                     ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
+        if plain:
+            check(L.vaemdl_modl_plain_iwae_fwd(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex), None,
+                                               ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
+                                               stream_ptr(dev)), "vaemdl_modl_plain_iwae_fwd")
+        else:
+            check(L.vaemdl_modl_iwae_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
+                                         ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
+                                         ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
     return ll64, log_w, lme_b, elbo, g_ll
 
 
 def modl_log_prob(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
-                  edge_mode: int = _abi.EDGE_MDL) -> torch.Tensor:
-    """Per-pixel MoDL log-prob ``[..., H, W]`` (utils/mdl.py:56-92 without the trailing ``expand_dims``)."""
-    return _ModlFn.apply(params, x, x_range, edge_mode, "pixel")
+                  edge_mode: int = _abi.EDGE_MDL, plain: bool = False) -> torch.Tensor:
+    """Per-pixel MoDL log-prob ``[..., H, W]`` (utils/mdl.py:56-92 without the trailing ``expand_dims``;
+    ``plain=True``: utils/mdl_plain.py:36-66)."""
+    return _ModlFn.apply(params, x, x_range, edge_mode, "pixel", plain)
 
 
 def modl_log_likelihood(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,
-                        edge_mode: int = _abi.EDGE_MDL, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                        edge_mode: int = _abi.EDGE_MDL, dtype: torch.dtype = torch.float32,
+                        plain: bool = False) -> torch.Tensor:
     """Per-image MoDL log-likelihood ``[...]`` = ``reduce_sum(log_prob(x), [-1,-2,-3])`` (models/loss.py:32),
     computed without ever writing the per-pixel tensor.  ``dtype=torch.float64`` returns the float64-accumulated sums
     (same float32 per-pixel values; no float32 rounding of the ~-2e4 totals)."""
-    return _ModlFn.apply(params, x, x_range, edge_mode, "image64" if dtype == torch.float64 else "image")
+    return _ModlFn.apply(params, x, x_range, edge_mode, "image64" if dtype == torch.float64 else "image", plain)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -407,7 +429,9 @@ def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, 
     lead = tuple(p.shape[:-3])
     n_img = int(math.prod(lead)) if lead else 1
     um = dense_f32(u_mix, "u_mix")
-    ul = dense_f32(u_log, "u_log")
+    ul = dense_f32(u_log, "u_log") if u_log is not None else None
+    if ul is None and variant != _abi.SAMPLE_PLAIN:
+        raise ValueError("u_log may only be omitted for the plain variant (mean of the selected locations)")
     per_rep = n_img * H * W * M
     if um.shape[-1] != M or um.numel() % per_rep:
         raise ValueError("u_mix must have shape [n..., ..., H, W, n_mix]")
@@ -415,8 +439,8 @@ def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, 
     out_lead = tuple(um.shape[:-3])
     if int(math.prod(out_lead)) != n_rep * n_img:
         raise ValueError("u_mix leading dims must be [n...] + parameters.shape[:-3]")
-    want = n_rep * n_img * H * W * 3 * (M if variant == _abi.SAMPLE_MDL else 1)
-    if ul.numel() != want:
+    want = n_rep * n_img * H * W * 3 * (1 if variant == _abi.SAMPLE_OPENAI else M)
+    if ul is not None and ul.numel() != want:
         raise ValueError("u_log must have shape [n..., ..., H, W, 3] (openai) or [n..., ..., H, W, 3, n_mix] (mdl)")
     x = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.float32)
     xq = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.uint8) if want_quantised else None
