@@ -208,6 +208,35 @@ VAEMDL_API int vaemdl_iwae_tail(const float* ll, const double* ll_f64, const flo
                      float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Latent-side terms of the importance log-weights (sums of Normal log-densities over the latent axis)
+ * replaces: lpz / lqzx and beta*(lpz - lqzx)              models/loss.py:28-34
+ *           (lpz2 - lqz2z1) + (lpz1z2 - lqz1x)            models/model06.py:40-47
+ *           and their gradients w.r.t. z, loc, scale      (tf.GradientTape)
+ * term t:  T_t[s,b] = sum_d log N(z[s,b,d]; loc[.,b,d], scale[.,b,d]);  z [S,B,D];  loc / scale [B,D], or [S,B,D] when
+ *          params_per_sample != 0;  loc == scale == NULL: the standard normal.
+ * fwd:  extra_out[s,b] = (extra_in ? extra_in[s,b] : 0) + sum_t weight_t * T_t[s,b]   -> the `extra` of the *_iwae_fwd
+ *       entry points;  term_sums [n_terms,S,B] nullable (the lpz / lqzx metrics of models/loss.py:48-55).
+ * bwd:  given g_extra [S,B] = d loss / d extra (= g_ll of the *_iwae_fwd entry points), per term (each nullable):
+ *       dz [S,B,D], dloc / dscale (shape of loc / scale).  Terms that pass the SAME dz pointer (two densities of one z)
+ *       accumulate into it.  One launch each; sums run in a fixed order.
+ * ------------------------------------------------------------------------ */
+#define VAEMDL_MAX_LATENT_TERMS 4
+typedef struct {
+  const float* z;
+  const float* loc;   /* NULL: standard normal */
+  const float* scale; /* NULL iff loc is NULL  */
+  int D;
+  int params_per_sample;
+  float weight;
+} vaemdl_latent_term;
+
+VAEMDL_API int vaemdl_latent_terms_fwd(const vaemdl_latent_term* terms, int n_terms, int S, long long B,
+                            const float* extra_in, float* extra_out, float* term_sums, void* stream);
+VAEMDL_API int vaemdl_latent_terms_bwd(const vaemdl_latent_term* terms, int n_terms, int S, long long B,
+                            const float* g_extra, float* const* dz, float* const* dloc, float* const* dscale,
+                            void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Samplers (explicit uniform noise; float64 internal arithmetic)
  * replaces: sample_from_discretized_mix_logistic   utils/mdl_openai.py:160-193 (explicit-noise lines :167, :185-186)
  *           MixtureDiscretizedLogistic._sample_n   utils/mdl.py:209-252

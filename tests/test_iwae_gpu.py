@@ -189,3 +189,74 @@ def test_log_sum_exp_helpers(V):
     b = V.log_prob_from_logits(x.to(DEV)).cpu()
     assert torch.allclose(b, O.log_prob_from_logits(x), atol=1e-5)
     assert V.int_shape(x) == [3, 4, 4, 10]
+
+
+def test_fused_iwae_loss_gradients_wrt_latents_and_parameters(V):
+    """models/loss.py:26-46 end to end: the fused objective's gradients w.r.t. the decoder output, z, and the encoder's
+    Normal parameters against torch-CPU float64 autograd over the oracle; z itself depends on (q_loc, q_scale) through the
+    reparameterisation, as in models/model05.py:124-125."""
+    g = torch.Generator().manual_seed(21)
+    S, B, H, W, M, D = 5, 6, 8, 8, 10, 20
+    params, x_u8, q_loc, q_scale, _ = _setup_model05_like(g, S, B, H, W, M, D)
+    eps = torch.randn(S, B, D, generator=g)
+    beta = 0.8
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    pd = params.to(DEV).requires_grad_(True)
+    ql = q_loc.to(DEV).requires_grad_(True)
+    qs = q_scale.to(DEV).requires_grad_(True)
+    z = ql + qs * eps.to(DEV)
+    pz = td.Normal(torch.zeros_like(z), torch.ones_like(z))
+    pz.axes = [-1]
+    qzx = td.Normal(ql, qs)
+    qzx.axes = [-1]
+    pxz = V.MixtureDiscretizedLogistic(pd)
+    loss, met = V.iwae_loss(O.normalize_u8(x_u8).to(DEV), z, pz, qzx, pxz, beta=beta)
+    # oracle: the same graph in float64 on the CPU
+    p64b = params.double().requires_grad_(True)
+    ql64b = q_loc.double().requires_grad_(True)
+    qs64b = q_scale.double().requires_grad_(True)
+    z64b = ql64b + qs64b * eps.double()
+    lossb, metb = O.iwae_loss(O.modl_log_prob(p64b, x64), td.Normal(0.0, 1.0).log_prob(z64b).sum(-1),
+                              td.Normal(ql64b, qs64b).log_prob(z64b).sum(-1), x64.shape, beta=beta)
+    lossb.backward()
+    assert abs(loss.item() - lossb.item()) <= LL_RTOL * abs(lossb.item())
+    assert relnorm(met["lpz"], metb["lpz"]) < 1e-6 and relnorm(met["lqzx"], metb["lqzx"]) < 1e-6
+    assert relnorm(met["kl"], metb["kl"]) < 1e-5
+    loss.backward()
+    assert_grad_close(pd.grad, p64b.grad, M)
+    assert relnorm(ql.grad, ql64b.grad) < GRAD_RTOL and relnorm(qs.grad, qs64b.grad) < GRAD_RTOL
+
+
+def test_latent_terms_model06_shapes(V):
+    """models/model06.py:40-47: four Normal terms, two latent layers of different width, per-sample and shared parameters;
+    forward sums and every gradient against float64 autograd."""
+    from vae_mdl_b200 import functional as F
+    g = torch.Generator().manual_seed(22)
+    S, B, D1, D2 = 5, 7, 12, 5
+    z1 = torch.randn(S, B, D1, generator=g)
+    z2 = torch.randn(S, B, D2, generator=g)
+    q1_loc, q1_sc = torch.randn(B, D1, generator=g), torch.rand(B, D1, generator=g) + 0.5          # q(z1|x): shared over S
+    q2_loc, q2_sc = torch.randn(S, B, D2, generator=g), torch.rand(S, B, D2, generator=g) + 0.5    # q(z2|z1): per sample
+    p1_loc, p1_sc = torch.randn(S, B, D1, generator=g), torch.rand(S, B, D1, generator=g) + 0.5    # p(z1|z2): per sample
+    gex = torch.randn(S, B, generator=g)
+    leaves = [t.double().requires_grad_(True) for t in (z1, z2, q1_loc, q1_sc, q2_loc, q2_sc, p1_loc, p1_sc)]
+    a1, a2, b1, b2, c1, c2, d1, d2 = leaves
+    lpz2 = td.Normal(0.0, 1.0).log_prob(a2).sum(-1)
+    lqz2z1 = td.Normal(c1, c2).log_prob(a2).sum(-1)
+    lpz1z2 = td.Normal(d1, d2).log_prob(a1).sum(-1)
+    lqz1x = td.Normal(b1, b2).log_prob(a1).sum(-1)
+    extra64 = (lpz2 - lqz2z1) + (lpz1z2 - lqz1x)                             # models/model06.py:47
+    (extra64 * gex.double()).sum().backward()
+    dv = lambda t: t.to(DEV)  # noqa: E731
+    terms = [(dv(z2), None, None, 1.0), (dv(z2), dv(q2_loc), dv(q2_sc), -1.0),
+             (dv(z1), dv(p1_loc), dv(p1_sc), 1.0), (dv(z1), dv(q1_loc), dv(q1_sc), -1.0)]
+    extra, sums = F.latent_terms(terms)
+    assert relnorm(extra, extra64) < 1e-6
+    for got, want in zip(sums, (lpz2, lqz2z1, lpz1z2, lqz1x)):
+        assert relnorm(got, want) < 1e-6
+    dz, dloc, dsc = F.latent_terms_backward(terms, dv(gex), share_dz=((0, 1), (2, 3)))
+    assert dz[1] is None and dz[3] is None and dloc[0] is None
+    assert relnorm(dz[0], a2.grad) < 1e-5 and relnorm(dz[2], a1.grad) < 1e-5
+    assert relnorm(dloc[1], c1.grad) < 1e-5 and relnorm(dsc[1], c2.grad) < 1e-5
+    assert relnorm(dloc[2], d1.grad) < 1e-5 and relnorm(dsc[2], d2.grad) < 1e-5
+    assert relnorm(dloc[3], b1.grad) < 1e-5 and relnorm(dsc[3], b2.grad) < 1e-5

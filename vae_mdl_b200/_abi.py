@@ -22,6 +22,13 @@ RANGE_UNIT, RANGE_SYM = 0, 1
 EDGE_MDL, EDGE_OPENAI = 0, 1
 SAMPLE_OPENAI, SAMPLE_MDL, SAMPLE_PLAIN = 0, 1, 2
 MAX_MIX = 64
+MAX_LATENT_TERMS = 4
+
+
+class LatentTerm(ctypes.Structure):
+    """``vaemdl_latent_term`` of include/vaemdl.h."""
+    _fields_ = [("z", c_void_p), ("loc", c_void_p), ("scale", c_void_p), ("D", c_int), ("params_per_sample", c_int),
+                ("weight", c_float)]
 
 _LIB = None
 
@@ -56,6 +63,9 @@ PROTOTYPES = {
     "vaemdl_logmeanexp_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_logmeanexp_fwd_f64": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_logmeanexp_bwd_f64": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+    "vaemdl_latent_terms_fwd": (c_int, [c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_latent_terms_bwd": (c_int, [c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     "vaemdl_modl_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int,

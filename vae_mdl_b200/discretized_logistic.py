@@ -25,6 +25,9 @@ class DiscretizedLogistic:
         self.dx = self.interval_width / 2.0                   # :21
         self.axes = [-1, -2, -3]                              # assigned by the models (models/model03.py:143)
 
+    def _iwae_spec(self):
+        return "dl", {"low": self.low, "high": self.high, "levels": self.levels}, self.loc, self.logscale
+
     def logistic_cdf(self, x):
         """:23-25 (diagnostic helper, not on the hot path): sigmoid((x-loc) exp(-logscale))."""
         return torch.sigmoid((x - self.loc) * torch.exp(-self.logscale))

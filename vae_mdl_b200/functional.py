@@ -26,6 +26,9 @@ __all__ = [
     "iwae_tail",
     "modl_sample",
     "dlogistic_sample",
+    "latent_terms",
+    "latent_terms_backward",
+    "fused_iwae_loss",
 ]
 
 
@@ -476,3 +479,179 @@ def dlogistic_sample(loc: torch.Tensor, logscale: torch.Tensor, u: torch.Tensor,
                                                 float(low), float(high), ctypes.c_void_p(out.data_ptr() + off),
                                                 stream_ptr(loc.device)), "vaemdl_dlogistic_sample")
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# latent-side terms of log_w, and the whole IWAE objective after the networks in 3 launches (+ 2 backward)
+# --------------------------------------------------------------------------------------------------
+def _pack_terms(terms):
+    """terms: list of ``(z [S,B,D], loc | None, scale | None, weight)``; loc / scale ``[B,D]`` or ``[S,B,D]``.
+    Returns (ctypes array, tensors kept alive, S, B)."""
+    n = len(terms)
+    if not 1 <= n <= _abi.MAX_LATENT_TERMS:
+        raise ValueError(f"between 1 and {_abi.MAX_LATENT_TERMS} terms")
+    arr = (_abi.LatentTerm * n)()
+    keep = []
+    S, B = terms[0][0].shape[0], terms[0][0].shape[1]
+    for i, (z, loc, scale, w) in enumerate(terms):
+        zd = dense_f32(z, "z")
+        if zd.dim() != 3 or zd.shape[0] != S or zd.shape[1] != B:
+            raise ValueError("every z must be [S, B, D]")
+        D = zd.shape[2]
+        ld = sd = None
+        pps = 0
+        if loc is not None:
+            ld, sd = dense_f32(loc, "loc"), dense_f32(scale, "scale")
+            if tuple(ld.shape) == (S, B, D) and tuple(sd.shape) == (S, B, D):
+                pps = 1
+            elif tuple(ld.shape) != (B, D) or tuple(sd.shape) != (B, D):
+                raise ValueError("loc / scale must be [B, D] or [S, B, D]")
+        arr[i].z = zd.data_ptr()
+        arr[i].loc = ld.data_ptr() if ld is not None else None
+        arr[i].scale = sd.data_ptr() if sd is not None else None
+        arr[i].D = D
+        arr[i].params_per_sample = pps
+        arr[i].weight = float(w)
+        keep.append((zd, ld, sd))
+    return arr, keep, S, B
+
+
+def latent_terms(terms, extra_in: Optional[torch.Tensor] = None):
+    """``extra [S,B] = extra_in + sum_t w_t * sum_d log N(z_t; loc_t, scale_t)`` and the per-term sums ``[n,S,B]``
+    (models/loss.py:28-34, models/model06.py:40-47) in ONE launch.  Not recorded by autograd (see ``fused_iwae_loss``)."""
+    arr, keep, S, B = _pack_terms(terms)
+    dev = keep[0][0].device
+    extra = torch.empty((S, B), device=dev, dtype=torch.float32)
+    sums = torch.empty((len(terms), S, B), device=dev, dtype=torch.float32)
+    ex = dense_f32(extra_in, "extra_in") if extra_in is not None else None
+    with torch.cuda.device(dev):
+        check(lib().vaemdl_latent_terms_fwd(arr, len(terms), S, B, ptr(ex), ptr(extra), ptr(sums), stream_ptr(dev)),
+              "vaemdl_latent_terms_fwd")
+    return extra, sums
+
+
+def latent_terms_backward(terms, g_extra: torch.Tensor, share_dz=()):
+    """Gradients of ``sum(g_extra * extra)`` w.r.t. every term's z, loc, scale (ONE launch).  ``share_dz``: pairs
+    ``(i, j)`` of terms that are densities of the SAME z tensor -- term j then accumulates into term i's dz buffer.
+    Returns lists ``dz, dloc, dscale`` (``None`` for a standard-normal term's parameters, and for dz[j] of a shared pair)."""
+    import ctypes
+    arr, keep, S, B = _pack_terms(terms)
+    n = len(terms)
+    dev = keep[0][0].device
+    g = dense_f32(g_extra, "g_extra")
+    dz = [torch.empty_like(k[0]) for k in keep]
+    for i, j in share_dz:
+        dz[j] = dz[i]
+    dloc = [torch.empty_like(k[1]) if k[1] is not None else None for k in keep]
+    dsc = [torch.empty_like(k[2]) if k[2] is not None else None for k in keep]
+    PP = ctypes.c_void_p * n
+    mk = lambda lst: PP(*[t.data_ptr() if t is not None else None for t in lst])  # noqa: E731
+    with torch.cuda.device(dev):
+        check(lib().vaemdl_latent_terms_bwd(arr, n, S, B, ptr(g), mk(dz), mk(dloc), mk(dsc), stream_ptr(dev)),
+              "vaemdl_latent_terms_bwd")
+    shared = {j for _, j in share_dz}
+    return [None if i in shared else dz[i] for i in range(n)], dloc, dsc
+
+
+def _expand_param(t: torch.Tensor, S: int, B: int, D: int):
+    """A Normal parameter broadcast to [B, D] when it does not depend on the sample axis, else to [S, B, D]."""
+    t = t.float()
+    if t.dim() < 3 or t.shape[0] == 1:
+        tb = t.reshape(t.shape[-2:]) if t.dim() >= 3 else t
+        return tb.expand(B, D).contiguous()
+    return t.expand(S, B, D).contiguous()
+
+
+class _FusedIwaeFn(torch.autograd.Function):
+    """The IWAE objective after the networks (models/loss.py:26-46, models/model06.py:38-55): latent terms ->
+    observation-model forward -> fused finish; backward: observation-model gradient kernel + latent-term gradient kernel.
+
+    ``term_meta``: one ``(z_index, weight, param_index)`` per Normal term (``param_index = -1``: standard normal);
+    ``tensors`` = the distinct z tensors, then ``loc, scale`` of every parametrised term in order."""
+
+    @staticmethod
+    def forward(ctx, kind, meta, x, term_meta, n_z, p0, p1, *tensors):
+        zs = [dense_f32(t, "z") for t in tensors[:n_z]]
+        S, B = zs[0].shape[0], zs[0].shape[1]
+        raw = tensors[n_z:]
+        terms, expanded = [], []
+        for zi, w, pi in term_meta:
+            D = zs[zi].shape[2]
+            if pi < 0:
+                terms.append((zs[zi], None, None, w))
+            else:
+                le, se = _expand_param(raw[2 * pi], S, B, D), _expand_param(raw[2 * pi + 1], S, B, D)
+                expanded += [le, se]
+                terms.append((zs[zi], le, se, w))
+        extra, sums = latent_terms(terms)
+        if kind == "modl":
+            ll64, log_w, lme_b, elbo, g_ll = modl_iwae_forward(p0, x, extra, 0, meta["x_range"], meta["edge_mode"],
+                                                               meta["plain"])
+        else:
+            ll64, log_w, lme_b, elbo, g_ll = dlogistic_iwae_forward(p0, p1, x, extra, meta["low"], meta["high"],
+                                                                    meta["levels"])
+        ctx.kind, ctx.meta_, ctx.term_meta, ctx.n_z = kind, meta, term_meta, n_z
+        ctx.raw_shapes = [t.shape for t in raw]
+        ctx.has_p1 = p1 is not None
+        ctx.save_for_backward(x, p0, p1 if p1 is not None else p0, g_ll, *zs, *expanded)
+        lpxz = ll64.float()
+        loss = -elbo.reshape(())
+        ctx.mark_non_differentiable(lpxz, sums, lme_b)
+        return loss, lpxz, sums, lme_b
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        x, p0, p1, g_ll = ctx.saved_tensors[:4]
+        zs = ctx.saved_tensors[4:4 + ctx.n_z]
+        expanded = ctx.saved_tensors[4 + ctx.n_z:]
+        g = g_ll * g_loss                                                     # d loss / d lpxz = d loss / d extra
+        meta = ctx.meta_
+        dp0 = dp1 = None
+        if ctx.kind == "modl":
+            if ctx.needs_input_grad[5]:
+                dp0 = modl_backward(p0, x, g_image=g, x_range=meta["x_range"], edge_mode=meta["edge_mode"],
+                                    plain=meta["plain"])
+        elif ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
+            dp0, dp1 = dlogistic_backward(p0, p1, x, g, meta["low"], meta["high"], meta["levels"])
+        n_t = len(ctx.needs_input_grad) - 7
+        d_tensors = [None] * n_t
+        if any(ctx.needs_input_grad[7:]):
+            terms, first_of_z, share = [], {}, []
+            for t, (zi, w, pi) in enumerate(ctx.term_meta):
+                if pi < 0:
+                    terms.append((zs[zi], None, None, w))
+                else:
+                    terms.append((zs[zi], expanded[2 * pi], expanded[2 * pi + 1], w))
+                if zi in first_of_z:
+                    share.append((first_of_z[zi], t))
+                else:
+                    first_of_z[zi] = t
+            dzs, dlocs, dscs = latent_terms_backward(terms, g, share_dz=tuple(share))
+            for zi, t in first_of_z.items():
+                d_tensors[zi] = dzs[t]
+            for t, (zi, w, pi) in enumerate(ctx.term_meta):
+                if pi >= 0:
+                    d_tensors[ctx.n_z + 2 * pi] = dlocs[t].sum_to_size(ctx.raw_shapes[2 * pi])
+                    d_tensors[ctx.n_z + 2 * pi + 1] = dscs[t].sum_to_size(ctx.raw_shapes[2 * pi + 1])
+        if not ctx.has_p1:
+            dp1 = None
+        return (None, None, None, None, None, dp0, dp1, *d_tensors)
+
+
+def fused_iwae_loss(kind: str, meta: dict, x, p0, p1, normal_terms):
+    """``normal_terms``: list of ``(z [S,B,D], loc | None, scale | None, weight)`` -- the Normal densities that make up
+    ``log_w - lpxz`` (a term with ``loc is None`` is the standard normal); terms may share a z tensor.
+    Returns ``(loss, lpxz [S,B], term_sums [n_terms,S,B], lme_b [B])``; ``loss`` is differentiable w.r.t. the
+    observation-model parameters, every z and every loc / scale.  3 launches forward, 2 backward."""
+    z_list, term_meta, params = [], [], []
+    for z, loc, scale, w in normal_terms:
+        zi = next((i for i, t in enumerate(z_list) if t is z), None)
+        if zi is None:
+            z_list.append(z)
+            zi = len(z_list) - 1
+        if loc is None:
+            term_meta.append((zi, float(w), -1))
+        else:
+            term_meta.append((zi, float(w), len(params) // 2))
+            params += [loc, scale]
+    return _FusedIwaeFn.apply(kind, meta, x, tuple(term_meta), len(z_list), p0, p1, *z_list, *params)

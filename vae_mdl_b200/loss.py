@@ -43,8 +43,44 @@ def _lpxz(pxz, x):
     return torch.sum(pxz.log_prob(x), dim=tuple(axes))
 
 
+def _normal_ok(dist, axes, z):
+    """A Normal density reduced over the last axis of a ``[S,B,D]`` sample, parameters not wider than the sample."""
+    if not isinstance(dist, td.Normal) or list(axes) != [-1] or z is None or z.dim() != 3:
+        return False
+    for t in (dist.loc, dist.scale):
+        if t.dim() > 3 or (t.dim() == 3 and t.shape[0] not in (1, z.shape[0])):
+            return False
+    return True
+
+
+def _obs_ok(pxz, axes, x, S, B):
+    """One of this package's observation models scored over the image axes, parameters ``[S,B,H,W,...]``, x ``[B,H,W,3]``."""
+    if not hasattr(pxz, "_iwae_spec") or sorted(axes) != [-3, -2, -1]:
+        return False
+    p0 = pxz._iwae_spec()[2]
+    return p0.dim() == 5 and x.dim() == 4 and p0.shape[0] == S and p0.shape[1] == B and x.shape[0] == B
+
+
+def _fusable(x, z, pz, qzx, pxz):
+    return (_normal_ok(pz, _axes(pz), z) and _normal_ok(qzx, _axes(qzx), z)
+            and _obs_ok(pxz, pxz.axes, x, z.shape[0], z.shape[1]))
+
+
 def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
-    """models/loss.py:26-55; returns ``(-iwae_elbo, metrics)`` with the reference's metric keys."""
+    """models/loss.py:26-55; returns ``(-iwae_elbo, metrics)`` with the reference's metric keys.
+
+    With this package's observation models and Normal latents the whole objective after the networks runs fused:
+    latent terms (1 launch) -> observation-model forward -> finish (per-image sums, log-mean-exp, batch mean), and two
+    launches backward; anything else takes the generic op-by-op route below."""
+    if _fusable(x, z, pz, qzx, pxz):
+        kind, meta, p0, p1 = pxz._iwae_spec()
+        loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, [(z, pz.loc, pz.scale, beta),      # :34
+                                                                        (z, qzx.loc, qzx.scale, -beta)])
+        iwae_elbo = -loss.detach()
+        lpz, lqzx = sums[0], sums[1]
+        n_dims = float(math.prod(x.shape[1:]))                              # :42
+        return loss, {"iwae_elbo": iwae_elbo, "bpd": -iwae_elbo / (math.log(2.0) * n_dims), "lpxz": lpxz, "lqzx": lqzx,
+                      "lpz": lpz, "kl": -torch.mean(lpz - lqzx, dim=0)}
     lpz = torch.sum(pz.log_prob(z), dim=_axes(pz))                      # :28
     lqzx = torch.sum(qzx.log_prob(z), dim=_axes(qzx))                   # :30
     lpxz = _lpxz(pxz, x)                                                # :32
@@ -67,7 +103,22 @@ def elbo_loss(x, z, pz, qzx, pxz):
 
 
 def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
-    """model06's loss (models/model06.py:38-72); arguments are ``DistributionTuple``s except ``pz``."""
+    """model06's loss (models/model06.py:38-72); arguments are ``DistributionTuple``s except ``pz``.  Runs fused (latent
+    terms -> observation model -> finish) when the four latent densities are Normals over the last axis."""
+    z1, z2 = qz1x.z, qz2z1.z
+    if (z1 is not None and z2 is not None and _normal_ok(qz2z1.dist, qz2z1.axes, z2) and _normal_ok(qz1x.dist, qz1x.axes, z1)
+            and _normal_ok(pz, _axes(pz), z2) and _normal_ok(pz1z2.dist, qz1x.axes, z1)
+            and _obs_ok(pxz1.dist, pxz1.axes, x, z1.shape[0], z1.shape[1])):
+        kind, meta, p0, p1 = pxz1.dist._iwae_spec()
+        terms = [(z2, pz.loc, pz.scale, 1.0), (z2, qz2z1.dist.loc, qz2z1.dist.scale, -1.0),                # :47
+                 (z1, pz1z2.dist.loc, pz1z2.dist.scale, 1.0), (z1, qz1x.dist.loc, qz1x.dist.scale, -1.0)]
+        loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, terms)
+        iwae_elbo = -loss.detach()
+        lpz2, lqz2z1, lpz1z2, lqz1x = sums[0], sums[1], sums[2], sums[3]
+        n_dims = float(math.prod(x.shape[-len(pxz1.axes):]))            # :54
+        return loss, {"iwae_elbo": iwae_elbo, "bpd": -iwae_elbo / (math.log(2.0) * n_dims), "lpxz": lpxz, "lqz1x": lqz1x,
+                      "lqz2z1": lqz2z1, "lpz2": lpz2, "lpz1z2": lpz1z2, "kl1": -torch.mean(lpz1z2 - lqz1x, dim=0),
+                      "kl2": -torch.mean(lpz2 - lqz2z1, dim=0)}
     lqz2z1 = torch.sum(qz2z1.dist.log_prob(qz2z1.z), dim=tuple(qz2z1.axes))
     lqz1x = torch.sum(qz1x.dist.log_prob(qz1x.z), dim=tuple(qz1x.axes))
     lpz2 = torch.sum(pz.log_prob(qz2z1.z), dim=_axes(pz))

@@ -29,6 +29,10 @@ class MixtureDiscretizedLogistic:
         self._axes = [-1, -2, -3]                             # :54
         self.dtype = parameters.dtype
 
+    def _iwae_spec(self):
+        """What ``loss.iwae_loss`` needs to run the fused objective on this observation model."""
+        return "modl", {"x_range": _abi.RANGE_UNIT, "edge_mode": _abi.EDGE_MDL, "plain": False}, self._parameters, None
+
     # ---- densities -------------------------------------------------------------------------------------------
     def log_prob(self, x: torch.Tensor) -> torch.Tensor:
         """x in [0,1], ``[batch,h,w,3]`` or broadcastable ``[h,w,3]``; returns ``[..., h, w, 1]`` (utils/mdl.py:56-92)."""

@@ -25,6 +25,9 @@ class MixtureDiscretizedLogisticOpenaiIWAE:
         self.dtype = logits.dtype
         self._axes = [-1, -2, -3]
 
+    def _iwae_spec(self):
+        return "modl", {"x_range": _abi.RANGE_UNIT, "edge_mode": _abi.EDGE_OPENAI, "plain": False}, self.logits, None
+
     def _check_x(self, x):
         # the reference computes repeats = (S*B) // x.shape[0] (:49): x MUST carry its batch dim
         if x.dim() != 4:
