@@ -99,3 +99,24 @@ def test_sharded_evaluation_world_size_2_gloo(tmp_path, n_images):
     a = torch.load(os.path.join(tmp_path, "llh0.pt"))
     b = torch.load(os.path.join(tmp_path, "llh1.pt"))
     assert torch.equal(a, b) and a.numel() == n_images
+
+
+def test_fill_canvas_matches_the_reference_loop(tmp_path):
+    """utils/utils.py:74-80 restated as its double loop; ``write_ppm`` round trip."""
+    import numpy as np
+    from vae_mdl_b200.utils import fill_canvas, normalize, write_ppm
+    n, h, w, c = 3, 4, 5, 3
+    img = torch.arange(n * n * h * w * c + h * w * c, dtype=torch.int64).reshape(n * n + 1, h, w, c).to(torch.uint8)
+    want = np.empty([n * h, n * w, c], dtype=np.uint8)
+    for i in range(n):
+        for j in range(n):
+            want[i * h:(i + 1) * h, j * w:(j + 1) * w, :] = img[i * n + j].numpy()
+    got = fill_canvas(img, n, h, w, c)
+    assert got.shape == (n * h, n * w, c) and np.array_equal(got.numpy(), want)
+    assert torch.equal(normalize(img), img.float() / 255.0)
+    path = str(tmp_path / "grid.ppm")
+    write_ppm(path, got)
+    raw = open(path, "rb").read()
+    assert raw.startswith(b"P6\n15 12\n255\n") and raw[len(b"P6\n15 12\n255\n"):] == want.tobytes()
+    with pytest.raises(ValueError):
+        fill_canvas(img[:4], n, h, w, c)

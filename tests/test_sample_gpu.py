@@ -130,3 +130,18 @@ def test_gumbel_near_ties_are_decided_in_float64(V):
     _, i64 = O.sample_from_discretized_mix_logistic(l2, M, u2, ul2)
     _, i2 = V.sample_from_discretized_mix_logistic(l2.to(DEV), M, u2.to(DEV), ul2.to(DEV), return_index=True)
     assert int((i2.cpu().long() != i64).sum()) == 0 and int((i64 == 8).sum()) == 0
+
+
+def test_sample_grid_is_the_quantised_sample_canvas(V):
+    """models/model05.py:200-216 on bytes: an 8x8 grid of quantised samples straight from the sampling kernel."""
+    g = torch.Generator().manual_seed(12)
+    n, H, W, M = 4, 8, 8, 5
+    l = torch.randn(n * n, H, W, 10 * M, generator=g)
+    um = torch.rand(1, n * n, H, W, M, generator=g) * (1 - 2e-5) + 1e-5
+    ul = torch.rand(1, n * n, H, W, 3, M, generator=g) * (1 - 2e-5) + 1e-5
+    d = V.MixtureDiscretizedLogistic(l.to(DEV))
+    canvas = V.sample_grid(d, n, sample_shape=1, u_mix=um.to(DEV), u_log=ul.to(DEV))
+    x01, _ = O.modl_sample_mdl(l, um[0], ul[0])
+    want = V.fill_canvas(O.quantise(x01), n, H, W, 3)
+    assert canvas.dtype == torch.uint8 and canvas.shape == (n * H, n * W, 3)
+    assert torch.equal(canvas.cpu(), want)

@@ -12,7 +12,7 @@ from .mdl_plain import PixelMixtureDiscretizedLogistic, get_mixture_params
 from .mdl_openai import (MixtureDiscretizedLogisticOpenai, discretized_mix_logistic_loss, int_shape,
                          log_prob_from_logits, log_sum_exp, sample_from_discretized_mix_logistic)
 from .mdl_openai_iwae import MixtureDiscretizedLogisticOpenaiIWAE
-from .utils import Dist, DistributionTuple, logmeanexp
+from .utils import Dist, DistributionTuple, fill_canvas, logmeanexp, normalize, sample_grid, write_ppm
 
 __all__ = [
     "DiscretizedLogistic",
@@ -29,6 +29,10 @@ __all__ = [
     "logmeanexp",
     "Dist",
     "DistributionTuple",
+    "fill_canvas",
+    "normalize",
+    "sample_grid",
+    "write_ppm",
     "iwae_loss",
     "elbo_loss",
     "loss_fn",
