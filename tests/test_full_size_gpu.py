@@ -1,0 +1,138 @@
+"""BASELINE.json's full sizes on the GPU: size-independent properties + oracle spot checks (the oracle cannot score these
+shapes whole in seconds).  configs[1] (plain DL), configs[2] (sampler), configs[3] (5000-sample evaluation, one image) and
+the per-GPU shard of configs[4] (64x64x3, 10 mixtures, 16 x 32); configs[0] is in test_modl_gpu.py."""
+import math
+
+import pytest
+import torch
+
+import oracle as O
+from util import GRAD_RTOL, LL_RTOL, relnorm
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def V(built_lib):
+    import vae_mdl_b200
+    return vae_mdl_b200
+
+
+@pytest.fixture(scope="module")
+def F(built_lib):
+    from vae_mdl_b200 import functional
+    return functional
+
+
+def test_config5_shard_properties(F, V):
+    S, B, H, W, M = 16, 32, 64, 64, 10
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    ll64 = F.modl_log_likelihood(params, x_u8, dtype=torch.float64)
+    lp = F.modl_log_prob(params, x_u8)
+    # (a) fused per-image sums == sums of the per-pixel output (float64 accumulation of the same float32 values)
+    assert ((lp.double().sum((-1, -2)) - ll64).abs() / ll64.abs()).max().item() < 1e-12
+    # (b) the fused finish gives the same sums bit for bit, and the IWAE tail of models/loss.py:34-37 on top of them
+    extra = (ll64.mean(0, keepdim=True) - ll64).float() + torch.randn(S, B, device=DEV, generator=gen)
+    ll_f, log_w, lme_b, elbo, g_ll = F.modl_iwae_forward(params, x_u8, extra)
+    assert torch.equal(ll_f, ll64)
+    lw = ll64 + extra.double()
+    want_lme = torch.logsumexp(lw, 0) - math.log(S)
+    assert ((lme_b.double() - want_lme).abs() / want_lme.abs()).max().item() < 1e-6
+    assert abs(elbo.item() - want_lme.mean().item()) <= 1e-6 * abs(want_lme.mean().item())
+    assert relnorm(g_ll, -torch.softmax(lw, 0) / B) < 1e-5
+    assert abs(g_ll.sum().item() + 1.0) < 1e-5                      # the softmax weights of every image sum to one
+    # (c) splitting the batch changes nothing (images are independent): the shard of ranks 0/1 of a 2-GPU run
+    h = B // 2
+    l0, _, _, e0, g0 = F.modl_iwae_forward(params[:, :h].contiguous(), x_u8[:h], extra[:, :h].contiguous(), b_total=B)
+    l1, _, _, e1, g1 = F.modl_iwae_forward(params[:, h:].contiguous(), x_u8[h:], extra[:, h:].contiguous(), b_total=B)
+    assert ((torch.cat([l0, l1], 1) - ll64).abs() / ll64.abs()).max().item() < 1e-12
+    assert abs((e0 + e1).item() - elbo.item()) <= 1e-6 * abs(elbo.item())
+    assert relnorm(torch.cat([g0, g1], 1), g_ll) < 1e-6
+    # (d) gradient: reproducible, linear in the upstream weights, logit gradients of a pixel sum to zero
+    dp = F.modl_backward(params, x_u8, g_image=g_ll)
+    assert torch.equal(dp, F.modl_backward(params, x_u8, g_image=g_ll))
+    assert (F.modl_backward(params, x_u8, g_image=4 * g_ll) - 4 * dp).abs().max().item() < 1e-36
+    assert dp[..., :M].sum(-1).abs().max().item() < 1e-5 * g_ll.abs().max().item()
+    loss, lpxz, dp2 = V.modl_iwae_step(params, x_u8, extra)
+    assert torch.equal(dp2, dp) and torch.equal(lpxz, ll64)
+    # (e) oracle spot checks: two whole images, log-likelihood and gradient
+    for s_i, b_i in [(0, 0), (S - 1, B - 1)]:
+        p64 = params[s_i, b_i].cpu().double()[None].requires_grad_(True)
+        x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
+        want = O.modl_log_prob(p64, x64).sum()
+        assert abs(ll64[s_i, b_i].item() - want.item()) <= LL_RTOL * abs(want.item())
+        (want * g_ll[s_i, b_i].item()).backward()
+        assert relnorm(dp[s_i, b_i], p64.grad[0]) <= GRAD_RTOL
+
+
+def test_config4_one_image_5000_importance_samples(F):
+    """models/model05.py:168-176 for one test image: [5000, 1, 32, 32, 100] parameters, x broadcast over the samples."""
+    S, H, W, M = 5000, 32, 32, 10
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    params = torch.randn(S, 1, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (1, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    ll_f, log_w, lme_b, elbo, g_ll = F.modl_iwae_forward(params, x_u8, None)
+    want = torch.logsumexp(ll_f[:, 0], 0) - math.log(S)
+    assert abs(lme_b[0].item() - want.item()) <= 1e-6 * abs(want.item()) and abs(elbo.item() - want.item()) <= 1e-6 * abs(want.item())
+    # streaming the samples in chunks of 250 (tools / dist.IwaeEvaluator) gives the same per-sample sums
+    chunks = [F.modl_log_likelihood(params[s0:s0 + 250], x_u8, dtype=torch.float64) for s0 in range(0, S, 250)]
+    assert ((torch.cat(chunks, 0) - ll_f).abs() / ll_f.abs()).max().item() < 1e-12
+    # x without its batch dim (models/model05.py:173 passes [H,W,3]) is the same thing
+    assert torch.equal(F.modl_log_likelihood(params, x_u8[0], dtype=torch.float64), ll_f)
+    # oracle spot check: 8 of the 5000 samples
+    idx = torch.tensor([0, 1, 777, 2499, 2500, 4096, 4998, 4999])
+    p64 = params[idx, 0].cpu().double()
+    want8 = O.modl_log_prob(p64, O.normalize_u8(x_u8[0].cpu(), torch.float64)).sum((-1, -2, -3))
+    assert ((ll_f[idx, 0].cpu() - want8).abs() / want8.abs()).max().item() <= LL_RTOL
+    bpd = -lme_b[0].item() / (math.log(2.0) * H * W * 3)
+    assert 8.0 < bpd < 11.0                                        # random parameters: ~9.5 bits/dim
+
+
+def test_config2_plain_dl_full_size(F, V):
+    S, B, H, W = 5, 128, 32, 32
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    both = torch.randn(S, B, H, W, 6, device=DEV, generator=gen)
+    both[..., :3].uniform_(generator=gen)
+    mu, lstd = torch.split(both, 3, dim=-1)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    d = V.DiscretizedLogistic(mu, lstd, low=0.0, high=1.0, levels=256.0)
+    ll64 = d.log_likelihood(x_u8, dtype=torch.float64)
+    lp = d.log_prob(x_u8)
+    # (a lane adds its six element values in float32 before the float64 accumulation: agreement to float32 rounding)
+    assert ((lp.double().sum((-1, -2, -3)) - ll64).abs() / ll64.abs()).max().item() < 1e-7
+    loss, lpxz, dloc, dls = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)
+    assert torch.equal(lpxz, ll64)
+    want = -(torch.logsumexp(ll64, 0) - math.log(S)).mean()
+    assert abs(loss.item() - want.item()) <= 1e-6 * abs(want.item())
+    loss2, _, dloc2, dls2 = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)
+    assert torch.equal(dloc, dloc2) and torch.equal(dls, dls2)
+    for s_i, b_i in [(0, 0), (4, 127)]:
+        b64 = both[s_i, b_i].cpu().double()[None].requires_grad_(True)
+        x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
+        w = O.dlogistic_log_prob(x64, b64[..., :3], b64[..., 3:], 0.0, 1.0, 256.0).sum()
+        assert abs(ll64[s_i, b_i].item() - w.item()) <= LL_RTOL * abs(w.item())
+
+
+def test_config3_sampler_full_size(V):
+    N, H, W, M = 10000, 32, 32, 10
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    l = torch.randn(N, H, W, 10 * M, device=DEV, generator=gen)
+    um = torch.rand(N, H, W, M, device=DEV, generator=gen) * (1 - 2e-5) + 1e-5
+    ul = torch.rand(N, H, W, 3, device=DEV, generator=gen) * (1 - 2e-5) + 1e-5
+    x, xq, idx = V.sample_from_discretized_mix_logistic(l, M, um, ul, return_index=True, return_quantised=True)
+    assert x.shape == (N, H, W, 3) and x.min().item() >= -1.0 and x.max().item() <= 1.0 and idx.max().item() < M
+    # the quantised bytes are the rounded float output except within float32 rounding of a bin boundary
+    q_from_x = torch.round(255.0 * (x.double() * 0.5 + 0.5)).to(torch.uint8)
+    assert (q_from_x != xq).float().mean().item() < 1e-5
+    # same call, same bits
+    x2, xq2, idx2 = V.sample_from_discretized_mix_logistic(l, M, um, ul, return_index=True, return_quantised=True)
+    assert torch.equal(xq, xq2) and torch.equal(idx, idx2) and torch.equal(x, x2)
+    # bit-exact against the float64 oracle on 24 of the 10,000 images
+    pick = torch.linspace(0, N - 1, 24).long()
+    x64, idx64 = O.sample_from_discretized_mix_logistic(l[pick].cpu(), M, um[pick].cpu(), ul[pick].cpu())
+    assert int((idx[pick].cpu().long() != idx64).sum()) == 0
+    assert int((xq[pick].cpu() != O.quantise(x64 * 0.5 + 0.5)).sum()) == 0
+    assert (x[pick].cpu().double() - x64).abs().max().item() < 1e-6
