@@ -31,6 +31,12 @@ struct HostCtx {
   Slot slots[kSlots];
   uint8_t* x = nullptr;
   size_t x_bytes = 0;
+  // whole-batch copies of the small tensors: ONE host transfer each per step instead of three tiny ones per chunk
+  // (a PCIe copy of a few hundred bytes costs ~10 us of queue time, which adds up to ~1 ms over 30 chunks)
+  float* extra_full = nullptr;  // [S, B]
+  float* ll_full = nullptr;     // [S, B]
+  float* lme_full = nullptr;    // [B]
+  size_t extra_full_bytes = 0, ll_full_bytes = 0, lme_full_bytes = 0;
   cudaEvent_t x_ready = nullptr;
 };
 
@@ -82,7 +88,7 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
   const size_t HW = static_cast<size_t>(H) * W;
   const size_t img_bytes = HW * 10 * M * sizeof(float);  // one (s,b) image of parameters
   if (chunk_b <= 0) {
-    const size_t target = 48u << 20;  // ~48 MB of parameters per chunk (tools/tune_e2e.py: best on PCIe Gen5)
+    const size_t target = 64u << 20;  // ~50-64 MB of parameters per chunk (tools/tune_e2e.py: best on PCIe Gen5)
     chunk_b = static_cast<int>(target / (img_bytes * S));
     if (chunk_b < 1) chunk_b = 1;
   }
@@ -90,6 +96,10 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
   const size_t chunk_param_bytes = img_bytes * S * chunk_b;
 
   VAEMDL_TRY(grow(c->x, c->x_bytes, static_cast<size_t>(B) * HW * 3));
+  const size_t sb_bytes = static_cast<size_t>(S) * B * sizeof(float);
+  VAEMDL_TRY(grow(c->extra_full, c->extra_full_bytes, sb_bytes));
+  VAEMDL_TRY(grow(c->ll_full, c->ll_full_bytes, sb_bytes));
+  VAEMDL_TRY(grow(c->lme_full, c->lme_full_bytes, static_cast<size_t>(B) * sizeof(float)));
   for (auto& s : c->slots) {
     VAEMDL_TRY(grow(s.params, s.params_bytes, chunk_param_bytes));
     if (dparams_host) VAEMDL_TRY(grow(s.grads, s.grads_bytes, chunk_param_bytes));
@@ -111,30 +121,37 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
 
   // the observed images: one small copy, every slot stream waits for it
   VAEMDL_TRY(cudaMemcpyAsync(c->x, x_host, static_cast<size_t>(B) * HW * 3, cudaMemcpyHostToDevice, c->slots[0].stream));
+  if (extra_host)
+    VAEMDL_TRY(cudaMemcpyAsync(c->extra_full, extra_host, sb_bytes, cudaMemcpyHostToDevice, c->slots[0].stream));
   VAEMDL_TRY(cudaEventRecord(c->x_ready, c->slots[0].stream));
   for (int k = 1; k < kSlots; ++k) VAEMDL_TRY(cudaStreamWaitEvent(c->slots[k].stream, c->x_ready, 0));
 
   const size_t host_pitch = img_bytes * B;  // bytes between consecutive s in the host tensors
+  // Chunk schedule: the first chunk's upload and the last chunk's download have nothing to overlap with, so the two
+  // ends of the batch travel in half-size chunks.
+  const int edge_b = chunk_b >= 2 ? chunk_b / 2 : chunk_b;
   int ci = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk_b, ++ci) {
+  for (int b0 = 0; b0 < B; ++ci) {
     Slot& s = c->slots[ci % kSlots];
-    const int cb = (B - b0) < chunk_b ? (B - b0) : chunk_b;
+    int want = chunk_b;
+    if (b0 == 0 || B - b0 <= chunk_b) want = edge_b;  // first chunk, and the tail split in two
+    const int cb = (B - b0) < want ? (B - b0) : want;
     const size_t width = img_bytes * cb;
     const long long n_img = static_cast<long long>(S) * cb;
     // [S, B, ...] host  ->  [S, cb, ...] device: S rows of `width` bytes
     VAEMDL_TRY(cudaMemcpy2DAsync(s.params, width, reinterpret_cast<const char*>(params_host) + img_bytes * b0, host_pitch,
                                  width, S, cudaMemcpyHostToDevice, s.stream));
-    if (extra_host)
-      VAEMDL_TRY(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), extra_host + b0, static_cast<size_t>(B) * sizeof(float),
-                                   cb * sizeof(float), S, cudaMemcpyHostToDevice, s.stream));
+    if (extra_host)  // [S, B] -> the chunk's dense [S, cb], device to device
+      VAEMDL_TRY(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), c->extra_full + b0, static_cast<size_t>(B) * sizeof(float),
+                                   cb * sizeof(float), S, cudaMemcpyDeviceToDevice, s.stream));
     // forward + fused finish (per-image sums, log-mean-exp, softmax weights normalised by the WHOLE batch): 2 launches
     int rc = vaemdl_modl_iwae_fwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
                                   VAEMDL_EDGE_MDL, S, cb, B, cb, H, W, M, extra_host ? s.extra : nullptr, s.ll, nullptr,
                                   nullptr, s.lme, nullptr, dparams_host ? s.g_ll : nullptr, s.ws, s.ws_bytes, s.stream);
     if (rc) return rc;
-    VAEMDL_TRY(cudaMemcpy2DAsync(ll_host + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
-                                 cb * sizeof(float), S, cudaMemcpyDeviceToHost, s.stream));
-    VAEMDL_TRY(cudaMemcpyAsync(lme_host + b0, s.lme, cb * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    VAEMDL_TRY(cudaMemcpy2DAsync(c->ll_full + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
+                                 cb * sizeof(float), S, cudaMemcpyDeviceToDevice, s.stream));
+    VAEMDL_TRY(cudaMemcpyAsync(c->lme_full + b0, s.lme, cb * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
     if (dparams_host) {
       rc = vaemdl_modl_bwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
                            VAEMDL_EDGE_MDL, n_img, cb, H, W, M, s.g_ll, nullptr, s.grads, s.stream);
@@ -142,8 +159,13 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
       VAEMDL_TRY(cudaMemcpy2DAsync(reinterpret_cast<char*>(dparams_host) + img_bytes * b0, host_pitch, s.grads, width,
                                    width, S, cudaMemcpyDeviceToHost, s.stream));
     }
+    b0 += cb;
   }
   for (auto& s : c->slots) VAEMDL_TRY(cudaStreamSynchronize(s.stream));
+  VAEMDL_TRY(cudaMemcpyAsync(ll_host, c->ll_full, sb_bytes, cudaMemcpyDeviceToHost, c->slots[0].stream));
+  VAEMDL_TRY(cudaMemcpyAsync(lme_host, c->lme_full, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToHost,
+                             c->slots[0].stream));
+  VAEMDL_TRY(cudaStreamSynchronize(c->slots[0].stream));
   double acc = 0.0;
   for (int b = 0; b < B; ++b) acc += static_cast<double>(lme_host[b]);  // models/loss.py:37 (mean over the batch)
   elbo_host[0] = static_cast<float>(acc / B);
@@ -168,6 +190,9 @@ extern "C" void vaemdl_host_release(void) {
       if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(c->x);
+    cudaFree(c->extra_full);
+    cudaFree(c->ll_full);
+    cudaFree(c->lme_full);
     if (c->x_ready) cudaEventDestroy(c->x_ready);
     delete c;
   }
