@@ -48,7 +48,7 @@ struct ModlArgs {
   int reverse;                // backward only: walk the run from its last tile to its first (the tiles the forward kernel
                               // read last are the ones still in L2)
   int keep_tiles;             // forward: the last keep_tiles tiles of a run are loaded with an L2 evict_last hint
-  int bwd_hint;               // backward: parameter loads and gradient stores carry an L2 evict_first hint
+  int bwd_hint;               // backward: L2 evict_first hint on the parameter loads (bit 0) / gradient stores (bit 1)
   int plain;                  // 1: channel means chained on the component's own means (utils/mdl_plain.py:160-162),
                               // 0: on the observed x (utils/mdl.py:139-145); the fast kernels take this as template AR
   int HW;
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&bars[s], bytes);
         if (BWD) {
-          if (a.bwd_hint)
+          if (a.bwd_hint & 1)
             bulk_g2s_hint(dst, src, bytes, &bars[s], pol_first);
           else
             bulk_g2s(dst, src, bytes, &bars[s]);
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (a.bwd_hint)
+          if (a.bwd_hint & 2)
             bulk_s2g_hint(dst, slot, bytes, pol_first);
           else
             bulk_s2g(dst, slot, bytes);
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
       if (lane == 0) {
         mbar_arrive_expect_tx(bar, bytes);
         if (BWD) {
-          if (a.bwd_hint)
+          if (a.bwd_hint & 1)
             bulk_g2s_hint(slot, src, bytes, bar, pol_first);
           else
             bulk_g2s(slot, src, bytes, bar);
@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (a.bwd_hint)
+          if (a.bwd_hint & 2)
             bulk_s2g_hint(dst, slot, bytes, pol_first);
           else
             bulk_s2g(dst, slot, bytes);
