@@ -87,7 +87,42 @@ def sample_fixture(name, seed, N, H, W, M):
                         q_openai=O.quantise(x * 0.5 + 0.5).numpy(), x01_mdl=x01.numpy(), q_mdl=O.quantise(x01).numpy())
 
 
+def plain_and_latent_fixture(name, seed, S, B, H, W, M, D):
+    """utils/mdl_plain.py log-prob + gradient, its sampler / mean, and the latent-side Normal terms of models/loss.py:28-34."""
+    import torch.distributions as td
+    g = torch.Generator().manual_seed(seed)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    x_u8.view(-1)[::11] = 0
+    x_u8.view(-1)[4::29] = 255
+    params = trained_like(g, S, B, H, W, M)
+    g_image = torch.randn(S, B, generator=g)
+    p64 = params.double().requires_grad_(True)
+    lp = O.mdl_plain_log_prob(p64, O.normalize_u8(x_u8, torch.float64))
+    ll = lp.sum((-1, -2))
+    (ll * g_image.double()).sum().backward()
+    u_mix = torch.rand(S, B, H, W, M, generator=g) * (1 - 2e-5) + 1e-5
+    u_log = torch.rand(S, B, H, W, 3, M, generator=g) * (1 - 2e-5) + 1e-5
+    xs, idx = O.mdl_plain_sample(params, u_mix, u_log)
+    xm, _ = O.mdl_plain_sample(params, u_mix, None)
+    # latent terms: z [S,B,D], q(z|x) = N(q_loc[B,D], q_scale[B,D]), p(z) = N(0,1), beta = 0.7
+    q_loc = torch.randn(B, D, generator=g)
+    q_scale = torch.rand(B, D, generator=g) + 0.5
+    z = q_loc + q_scale * torch.randn(S, B, D, generator=g)
+    z64, ql64, qs64 = z.double().requires_grad_(True), q_loc.double().requires_grad_(True), q_scale.double().requires_grad_(True)
+    lpz = td.Normal(0.0, 1.0).log_prob(z64).sum(-1)
+    lqzx = td.Normal(ql64, qs64).log_prob(z64).sum(-1)
+    extra = 0.7 * (lpz - lqzx)
+    (extra * g_image.double()).sum().backward()
+    np.savez_compressed(
+        os.path.join(HERE, name), params=params.numpy(), x_u8=x_u8.numpy(), g_image=g_image.numpy(),
+        lp=lp.detach().numpy(), ll=ll.detach().numpy(), grad=p64.grad.numpy(), u_mix=u_mix.numpy(), u_log=u_log.numpy(),
+        idx=idx.numpy().astype(np.uint8), q_sample=O.quantise(xs).numpy(), x_sample=xs.numpy(), x_mean=xm.numpy(),
+        z=z.numpy(), q_loc=q_loc.numpy(), q_scale=q_scale.numpy(), lpz=lpz.detach().numpy(), lqzx=lqzx.detach().numpy(),
+        extra=extra.detach().numpy(), dz=z64.grad.numpy(), dq_loc=ql64.grad.numpy(), dq_scale=qs64.grad.numpy())
+
+
 if __name__ == "__main__":
+    plain_and_latent_fixture("plain_m5_latent.npz", 401, 3, 4, 8, 8, 5, 12)
     modl_fixture("modl_m10_randn.npz", 101, 3, 4, 8, 8, 10, "randn")
     modl_fixture("modl_m5_trained.npz", 102, 2, 3, 8, 8, 5, "trained")
     modl_fixture("modl_m30_randn.npz", 103, 2, 2, 8, 4, 30, "randn")

@@ -89,3 +89,33 @@ def test_sample_mean_and_attributes(V):
     assert relnorm(d.loc, loc64) < 1e-6 and relnorm(d.logscale, ls64) < 1e-6
     with pytest.raises(ValueError):
         V.PixelMixtureDiscretizedLogistic(p.to(DEV), low=0.0)
+
+
+def test_golden_plain_mixture_and_latent_terms(V):
+    """tests/golden/plain_m5_latent.npz: trained-like parameters (narrow scales, both edges), sampler, mean, and the
+    latent-side Normal terms with their gradients."""
+    from util import golden
+    from vae_mdl_b200 import functional as F
+    z = golden("plain_m5_latent")
+    M = 5
+    params = torch.from_numpy(z["params"]).to(DEV)
+    x_u8 = torch.from_numpy(z["x_u8"]).to(DEV)
+    d = V.PixelMixtureDiscretizedLogistic(params)
+    ll = d.log_likelihood(x_u8, dtype=torch.float64).cpu()
+    want = torch.from_numpy(z["ll"])
+    assert ((ll - want).abs() / want.abs()).max().item() <= LL_RTOL
+    dp = F.modl_backward(params, x_u8, g_image=torch.from_numpy(z["g_image"]).to(DEV), plain=True)
+    assert_grad_close(dp, z["grad"], M)
+    um, ul = torch.from_numpy(z["u_mix"]).to(DEV), torch.from_numpy(z["u_log"]).to(DEV)
+    x, xq, idx = d.sample(1, u_mix=um[None], u_log=ul[None], return_index=True, return_quantised=True)
+    assert torch.equal(idx[0].cpu(), torch.from_numpy(z["idx"])) and torch.equal(xq[0].cpu(), torch.from_numpy(z["q_sample"]))
+    assert (x[0].cpu().double() - torch.from_numpy(z["x_sample"])).abs().max().item() < 1e-6
+    assert (d.mean(u_mix=um[None]).cpu().double() - torch.from_numpy(z["x_mean"])).abs().max().item() < 1e-6
+    zz, ql, qs = (torch.from_numpy(z[k]).to(DEV) for k in ("z", "q_loc", "q_scale"))
+    terms = [(zz, None, None, 0.7), (zz, ql, qs, -0.7)]
+    extra, sums = F.latent_terms(terms)
+    assert relnorm(extra, torch.from_numpy(z["extra"])) < 1e-6
+    assert relnorm(sums[0], torch.from_numpy(z["lpz"])) < 1e-6 and relnorm(sums[1], torch.from_numpy(z["lqzx"])) < 1e-6
+    dz, dloc, dsc = F.latent_terms_backward(terms, torch.from_numpy(z["g_image"]).to(DEV), share_dz=((0, 1),))
+    assert relnorm(dz[0], torch.from_numpy(z["dz"])) < 1e-5
+    assert relnorm(dloc[1], torch.from_numpy(z["dq_loc"])) < 1e-5 and relnorm(dsc[1], torch.from_numpy(z["dq_scale"])) < 1e-5

@@ -350,3 +350,19 @@ def test_mdl_plain_sample_and_mean():
     # u = 0.5 is a zero logistic draw: the sample equals the mean
     x0, _ = O.mdl_plain_sample(p, um, torch.full_like(ul, 0.5))
     assert torch.allclose(x0, m, atol=1e-15)
+
+
+def test_oracle_reproduces_plain_and_latent_golden():
+    import torch.distributions as td
+    z = np.load(os.path.join(GOLDEN, "plain_m5_latent.npz"))
+    params = torch.from_numpy(z["params"]).double().requires_grad_(True)
+    lp = O.mdl_plain_log_prob(params, O.normalize_u8(torch.from_numpy(z["x_u8"]), torch.float64))
+    assert np.allclose(lp.detach().numpy(), z["lp"], rtol=0, atol=1e-10)
+    (lp.sum((-1, -2)) * torch.from_numpy(z["g_image"]).double()).sum().backward()
+    assert np.allclose(params.grad.numpy(), z["grad"], rtol=1e-9, atol=1e-12)
+    xs, idx = O.mdl_plain_sample(torch.from_numpy(z["params"]), torch.from_numpy(z["u_mix"]), torch.from_numpy(z["u_log"]))
+    assert np.array_equal(idx.numpy().astype(np.uint8), z["idx"]) and np.array_equal(O.quantise(xs).numpy(), z["q_sample"])
+    zz = torch.from_numpy(z["z"]).double()
+    lpz = td.Normal(0.0, 1.0).log_prob(zz).sum(-1)
+    lqzx = td.Normal(torch.from_numpy(z["q_loc"]).double(), torch.from_numpy(z["q_scale"]).double()).log_prob(zz).sum(-1)
+    assert np.allclose((0.7 * (lpz - lqzx)).numpy(), z["extra"], rtol=0, atol=1e-10)
