@@ -1,6 +1,7 @@
 // common.cuh -- PTX wrappers (mbarrier, 1-D TMA bulk copies, MUFU approximations) for sm_100a.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "../../include/vaemdl.h"
@@ -114,8 +115,36 @@ __device__ __forceinline__ void bulk_wait_all() {
 // generic-proxy smem writes -> visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// A kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still draining; it must
+// execute pdl_wait() before touching anything the predecessor wrote (it blocks until the predecessor has completed and
+// its memory is visible).  pdl_trigger() in the predecessor allows the dependent launch to begin early.  Both are no-ops
+// for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- host-side helpers ---------------------------------------------------------------------------
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : static_cast<int>(e); }
+
+// launch `kern<<<grid, block, smem, st>>>(arg)` with the programmatic-stream-serialization attribute (VAEMDL_PDL=0: off)
+template <typename Arg>
+inline cudaError_t launch_pdl(void (*kern)(Arg), unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Arg& arg) {
+  static const bool on = [] {
+    const char* e = getenv("VAEMDL_PDL");
+    return !(e && e[0] == '0');
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
+}
 
 struct DeviceInfo {
   int sm_count;

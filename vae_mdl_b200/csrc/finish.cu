@@ -35,6 +35,8 @@ __device__ __forceinline__ double image_sum(const PartialGeom& g, long long n, b
 __global__ void reduce_partials_kernel(const PartialGeom g, bool small, float* __restrict__ ll_image,
                                        double* __restrict__ ll_image_f64, long long n_img) {
   const long long n = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_wait();     // the partials come from the forward kernel right before this launch
+  pdl_trigger();
   if (n >= n_img) return;
   const double acc = image_sum(g, n, small);
   if (ll_image) ll_image[n] = static_cast<float>(acc);
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(kFinishMaxThreads) finish_kernel(const FinishA
   __shared__ double blk[kFinishMaxThreads / 32];
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();     // the partials come from the forward kernel right before this launch
+  pdl_trigger();  // the gradient kernel may start its prologue; it waits for g_ll itself
   const long long b0 = static_cast<long long>(blockIdx.x) * a.BB;
   const int nb = static_cast<int>((a.B - b0) < a.BB ? (a.B - b0) : a.BB);
   // (1) per-image log-likelihood; consecutive threads take consecutive b of one s
@@ -177,8 +181,8 @@ int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll
     f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
     f.small = small;
     const long long grid = (iw.B + BB - 1) / BB;
-    finish_kernel<<<static_cast<unsigned>(grid), threads, static_cast<size_t>(BB) * iw.S * sizeof(double), st>>>(f);
-    return cuda_rc(cudaGetLastError());
+    return cuda_rc(launch_pdl(finish_kernel, static_cast<unsigned>(grid), static_cast<unsigned>(threads),
+                              static_cast<size_t>(BB) * iw.S * sizeof(double), st, f));
   }
   double* ll64_dst = ll64 ? ll64 : (iwae ? scratch : nullptr);
   reduce_partials_kernel<<<static_cast<unsigned>((n_img + 127) / 128), 128, 0, st>>>(g, small, ll, ll64_dst, n_img);

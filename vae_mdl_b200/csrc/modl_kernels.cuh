@@ -470,6 +470,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   }
   __syncwarp();
   if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  if constexpr (BWD)
+    pdl_wait();     // launched programmatically behind the finish kernel: g_image (and, in general, the parameters) must be complete
+  else
+    pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
 
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
   const bool lane_used = (lane / LPP) < PPT;
@@ -796,6 +800,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
   }
   __syncwarp();
   if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  if constexpr (BWD)
+    pdl_wait();
+  else
+    pdl_trigger();
 
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
   const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
@@ -1273,6 +1281,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
     plan->K = a.K;
     plan->PPT = T::PPT;
   }
+  if (BWD) return cuda_rc(launch_pdl(kern, static_cast<unsigned>(grid), static_cast<unsigned>(warps * 32), smem, st, a));
   kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
   return cuda_rc(cudaGetLastError());
 }
@@ -1335,6 +1344,7 @@ static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
     plan->K = a.K;
     plan->PPT = T::PPT;
   }
+  if (BWD) return cuda_rc(launch_pdl(kern, static_cast<unsigned>(grid), static_cast<unsigned>(warps * 32), smem, st, a));
   kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
   return cuda_rc(cudaGetLastError());
 }
