@@ -120,3 +120,20 @@ def test_fill_canvas_matches_the_reference_loop(tmp_path):
     assert raw.startswith(b"P6\n15 12\n255\n") and raw[len(b"P6\n15 12\n255\n"):] == want.tobytes()
     with pytest.raises(ValueError):
         fill_canvas(img[:4], n, h, w, c)
+
+
+def test_u8_to_unit_recipe_is_exact_for_every_byte():
+    """csrc/common.cuh::u8_to_unit: k * fl(1/255) plus one FMA residual step equals the correctly rounded k / 255.f
+    (utils/data.py:15-16) for all 256 bytes; the bare product does not.  float64 emulates the two FMAs exactly here."""
+    import numpy as np
+    r = np.float32(1.0) / np.float32(255.0)
+    bare = 0
+    for k in range(256):
+        kf = np.float32(k)
+        want = np.float32(kf / np.float32(255.0))
+        q0 = np.float32(kf * r)
+        rem = np.float32(np.float64(kf) - np.float64(q0) * 255.0)
+        q1 = np.float32(np.float64(q0) + np.float64(rem) * np.float64(r))
+        assert q1 == want, k
+        bare += int(q0 != want)
+    assert bare > 0

@@ -330,3 +330,22 @@ def test_no_write_outside_the_callers_buffers(built_lib, S, B, H, W, M):
                       ("lme", lme_buf), ("elbo", el_buf), ("dparams", dp_buf)]:
         assert bool((buf[:G] == -7.0).all()) and bool((buf[-G:] == -7.0).all()), f"guard band of {name} was overwritten"
     assert not bool(torch.isnan(dp).any()) and bool((lp != -7.0).all()) and bool((dp != -7.0).any())
+
+
+def test_every_byte_value_decodes_exactly(F, V):
+    """uint8 x and the float image x/255 (torch division, correctly rounded) give bit-identical results for all 256
+    byte values in every channel -- MoDL and plain DL, element-wise outputs."""
+    M = 10
+    g = torch.Generator().manual_seed(256)
+    k = torch.arange(256, dtype=torch.uint8)
+    x_u8 = torch.stack([k, k.flip(0), (k.int() * 7 % 256).to(torch.uint8)], -1).reshape(1, 16, 16, 3)
+    params = torch.randn(2, 1, 16, 16, 10 * M, generator=g).to(DEV)
+    xd = x_u8.to(DEV)
+    x01 = (x_u8.float() / 255.0).to(DEV)
+    assert torch.equal(F.modl_log_prob(params, xd), F.modl_log_prob(params, x01))
+    p5 = torch.randn(2, 1, 16, 16, 50, generator=g).to(DEV)
+    assert torch.equal(F.modl_log_prob(p5, xd), F.modl_log_prob(p5, x01))
+    both = torch.randn(2, 1, 16, 16, 6, generator=g).to(DEV)
+    mu, ls = torch.split(both, 3, dim=-1)
+    d = V.DiscretizedLogistic(mu, ls, low=0.0, high=1.0, levels=256.0)
+    assert torch.equal(d.log_prob(xd), d.log_prob(x01))

@@ -30,6 +30,17 @@ __device__ __forceinline__ float rcpa(float x) {
   return y;
 }
 
+// ---- uint8 pixel -> float32 / 255 (utils/data.py:15-16), bit-exact in three FMA-pipe instructions ---------------
+// q0 = k * fl(1/255) is off by one ulp for 126 of the 256 byte values; one residual step (rem = k - 255*q0 exactly, by
+// FMA) gives the correctly rounded quotient for all 256 (tests/test_host_logic.py enumerates them against k / 255.f).
+__device__ __forceinline__ float u8_to_unit(unsigned k) {
+  const float kf = static_cast<float>(k);
+  const float r = 1.0f / 255.0f;  // compile-time constant, correctly rounded
+  const float q0 = __fmul_rn(kf, r);
+  const float rem = __fmaf_rn(-q0, 255.0f, kf);
+  return __fmaf_rn(rem, r, q0);
+}
+
 // ---- shared-memory addresses -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

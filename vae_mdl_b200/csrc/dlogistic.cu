@@ -8,6 +8,8 @@
 //   edges  : -log(1+AG)   or   -|mid| - log(A+G)
 // The log-scale is NOT clamped in this class (utils/discretized_logistic.py:38); exp(-ls) is saturated at 3e38 so
 // that x == loc with a vanishing scale gives log 1 = 0 as the reference does instead of inf*0.
+#include <cstdlib>
+
 #include "modl_math.cuh"
 #include "packed.cuh"
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
       }
       float xv;
       if (a.x_u8)
-        xv = __fdiv_rn(static_cast<float>(static_cast<const uint8_t*>(a.x)[xo + c]), 255.0f);
+        xv = u8_to_unit(static_cast<const uint8_t*>(a.x)[xo + c]);
       else
         xv = static_cast<const float*>(a.x)[xo + c];
       const DlOut o = dl_elem<BWD>(xv, a.loc[po], a.logscale[po], a);
@@ -341,9 +343,9 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
       if (a.x_u8) {
         const uint8_t* xp = static_cast<const uint8_t*>(a.x) + xo;  // 6 bytes, 2-byte aligned (xo is a multiple of 6)
         const ushort3 w = *reinterpret_cast<const ushort3*>(xp);
-        xv[0] = pk(__fdiv_rn(static_cast<float>(w.x & 0xff), 255.0f), __fdiv_rn(static_cast<float>(w.y >> 8), 255.0f));
-        xv[1] = pk(__fdiv_rn(static_cast<float>(w.x >> 8), 255.0f), __fdiv_rn(static_cast<float>(w.z & 0xff), 255.0f));
-        xv[2] = pk(__fdiv_rn(static_cast<float>(w.y & 0xff), 255.0f), __fdiv_rn(static_cast<float>(w.z >> 8), 255.0f));
+        xv[0] = pk(u8_to_unit(w.x & 0xff), u8_to_unit(w.y >> 8));
+        xv[1] = pk(u8_to_unit(w.x >> 8), u8_to_unit(w.z & 0xff));
+        xv[2] = pk(u8_to_unit(w.y & 0xff), u8_to_unit(w.z >> 8));
       } else {
         const float2* xp = reinterpret_cast<const float2*>(static_cast<const float*>(a.x) + xo);
         const float2 w0 = xp[0], w1 = xp[1], w2 = xp[2];
@@ -509,7 +511,13 @@ static int dl_launch(DlArgs a, int cpt, int kind, cudaStream_t st, PartialGeom* 
   const int TR = dl_tile_rows(kind);
   const long long n_tiles = (a.n_rows + TR - 1) / TR;
   long long blocks = (n_tiles + 7) / 8;
-  long long cap = static_cast<long long>(di.sm_count) * 8;
+  // a warp's start-up and flush (index divisions, warp reductions) cost about as much as one tile: give every warp a
+  // few tiles rather than spreading a small problem over as many warps as possible
+  static const int per_sm = [] {
+    const char* e = getenv("VAEMDL_DL_BLOCKS_PER_SM");
+    return e ? atoi(e) : 8;
+  }();
+  long long cap = static_cast<long long>(di.sm_count) * (per_sm > 0 ? per_sm : 8);
   if (cap * 8 > kMaxGridWarps) cap = kMaxGridWarps / 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;

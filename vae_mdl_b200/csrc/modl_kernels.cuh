@@ -87,7 +87,7 @@ __device__ __forceinline__ void load_pixel(const ModlArgs& a, long long n, int p
   for (int c = 0; c < 3; ++c) {
     float v;
     if (a.x_u8) {
-      v = __fdiv_rn(static_cast<float>(static_cast<const uint8_t*>(a.x)[xo + c]), 255.0f);  // utils/data.py:15-16
+      v = u8_to_unit(static_cast<const uint8_t*>(a.x)[xo + c]);  // utils/data.py:15-16
     } else {
       v = static_cast<const float*>(a.x)[xo + c];
     }
@@ -443,7 +443,7 @@ __device__ __forceinline__ PixRaw load_pixel_raw(const ModlArgs& a, long long n,
 __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r, Pixel& px) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float v = a.x_u8 ? __fdiv_rn(static_cast<float>(r.v[c]), 255.0f) : __uint_as_float(r.v[c]);  // utils/data.py:15-16
+    float v = a.x_u8 ? u8_to_unit(r.v[c]) : __uint_as_float(r.v[c]);  // utils/data.py:15-16
     if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);                                                  // utils/mdl.py:65
     px.x[c] = v;
     px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
