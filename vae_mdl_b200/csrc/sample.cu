@@ -30,13 +30,23 @@ struct SampleArgs {
   int out_unit;
 };
 
-__global__ void __launch_bounds__(256) modl_sample_kernel(const SampleArgs a) {
+// Per-warp shared-memory slot: [ parameter tile: 32 rows x 10M | u_mix tile: 32 x M | u_log tile: 32 x 3 (x M) ], each
+// brought in by its own 1-D TMA bulk copy on one mbarrier.  The slot is handed back to the TMA engine (next tile) as
+// soon as the lane has picked its component and copied the twelve numbers it still needs into registers, so the
+// float64 part overlaps the next tile's loads.
+__global__ void __launch_bounds__(512) modl_sample_kernel(const SampleArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int M = a.M, ROWF = 10 * M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int TILE_F = 32 * ROWF;
-  float* slot = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * TILE_F;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * TILE_F * 4) + warp;
+  const int UM_F = 32 * M;
+  const int UL_PER = a.variant_mdl ? 3 * M : 3;  // floats of logistic noise per pixel
+  const int UL_F = a.u_log ? 32 * UL_PER : 0;
+  const int WARP_F = TILE_F + UM_F + UL_F;      // all three pieces are multiples of 4 floats
+  float* slot = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
+  float* um_s = slot + TILE_F;
+  float* ul_s = um_s + UM_F;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -45,32 +55,59 @@ __global__ void __launch_bounds__(256) modl_sample_kernel(const SampleArgs a) {
   const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
   const long long tiles_per_rep = (a.n_px + 31) / 32;
   const long long num_tiles = tiles_per_rep * a.n_rep;
-  uint32_t parity = 0;
-  for (long long t = static_cast<long long>(blockIdx.x) * nwarps + warp; t < num_tiles; t += total_warps) {
-    const long long rep = t / tiles_per_rep;
-    const long long tt = t - rep * tiles_per_rep;  // tiles never straddle two repetitions
-    const long long rem = a.n_px - tt * 32;
-    const int rows = rem < 32 ? static_cast<int>(rem) : 32;
-    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
-    const float* src = a.params + tt * TILE_F;
-    if ((bytes & 15u) == 0) {
+
+  struct TileId {
+    long long rep, tt, i0;
+    int rows;
+  };
+  auto locate = [&](long long t) {
+    TileId d;
+    d.rep = t / tiles_per_rep;
+    d.tt = t - d.rep * tiles_per_rep;  // tiles never straddle two repetitions
+    const long long rem = a.n_px - d.tt * 32;
+    d.rows = rem < 32 ? static_cast<int>(rem) : 32;
+    d.i0 = d.rep * a.n_px + d.tt * 32;  // first pixel of the tile in the noise / output tensors
+    return d;
+  };
+  auto issue = [&](const TileId& d) {
+    const uint32_t pb = static_cast<uint32_t>(d.rows) * ROWF * 4u;
+    const uint32_t mb = static_cast<uint32_t>(d.rows) * M * 4u;
+    const uint32_t lb = a.u_log ? static_cast<uint32_t>(d.rows) * UL_PER * 4u : 0u;
+    const float* psrc = a.params + d.tt * TILE_F;
+    const float* msrc = a.u_mix + d.i0 * M;
+    const float* lsrc = a.u_log ? a.u_log + d.i0 * UL_PER : nullptr;
+    const bool bulk = ((pb | mb | lb) & 15u) == 0 && ((reinterpret_cast<uintptr_t>(msrc) | reinterpret_cast<uintptr_t>(lsrc)) & 15u) == 0;
+    if (bulk) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s(slot, src, bytes, bar);
+        mbar_arrive_expect_tx(bar, pb + mb + lb);
+        bulk_g2s(slot, psrc, pb, bar);
+        bulk_g2s(um_s, msrc, mb, bar);
+        if (lb) bulk_g2s(ul_s, lsrc, lb, bar);
       }
-    } else {
-      for (int i = lane; i < rows * ROWF; i += 32) slot[i] = src[i];
+    } else {  // ragged last tile / unaligned noise: plain loads
+      for (int k = lane; k < d.rows * ROWF; k += 32) slot[k] = psrc[k];
+      for (int k = lane; k < d.rows * M; k += 32) um_s[k] = msrc[k];
+      if (a.u_log)
+        for (int k = lane; k < d.rows * UL_PER; k += 32) ul_s[k] = lsrc[k];
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(bar, 0);
     }
-    const bool active = lane < rows;
-    const long long i = rep * a.n_px + tt * 32 + (active ? lane : 0);  // index into the noise / output tensors
+  };
+
+  long long t = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  if (t < num_tiles) issue(locate(t));
+  uint32_t parity = 0;
+  for (; t < num_tiles; t += total_warps) {
+    const TileId d = locate(t);
+    const bool active = lane < d.rows;
+    const int lr = active ? lane : 0;
+    const long long i = d.i0 + lr;
     mbar_wait(bar, parity);
     parity ^= 1;
-    const float* row = slot + (active ? lane : 0) * ROWF;
+    const float* row = slot + lr * ROWF;
     // Gumbel-argmax over the mixture logits (utils/mdl_openai.py:167); first maximum wins
     int sel = 0;
-    const float* um = a.u_mix + i * M;
+    const float* um = um_s + lr * M;
     {
       float best = -INFINITY, second = -INFINITY;
       for (int m = 0; m < M; ++m) {
@@ -95,17 +132,29 @@ __global__ void __launch_bounds__(256) modl_sample_kernel(const SampleArgs a) {
         }
       }
     }
+    // the twelve numbers the float64 part needs, out of shared memory
+    float p_mu[3], p_ls[3], p_k[3], p_u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      p_mu[c] = row[M + c * 3 * M + sel];                                                           // :177
+      p_ls[c] = row[M + c * 3 * M + M + sel];                                                       // :178-180
+      p_k[c] = row[M + c * 3 * M + 2 * M + sel];                                                    // :181
+      p_u[c] = a.u_log ? (a.variant_mdl ? ul_s[(lr * 3 + c) * M + sel] : ul_s[lr * 3 + c]) : 0.5f;
+    }
+    __syncwarp();  // every lane is done with the slot: the next tile may stream in while the float64 math runs
+    if (t + total_warps < num_tiles) issue(locate(t + total_warps));
+
     double xs[3];
     double coef[3];
     double noise_keep[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const double mu = static_cast<double>(row[M + c * 3 * M + sel]);                              // :177
-      const double ls = fmax(static_cast<double>(row[M + c * 3 * M + M + sel]), -7.0);              // :178-180
-      coef[c] = tanh(static_cast<double>(row[M + c * 3 * M + 2 * M + sel]));                        // :181
+      const double mu = static_cast<double>(p_mu[c]);
+      const double ls = fmax(static_cast<double>(p_ls[c]), -7.0);
+      coef[c] = tanh(static_cast<double>(p_k[c]));
       double noise = 0.0;  // u_log == NULL (plain variant only): the selected location itself (utils/mdl_plain.py:104-121)
       if (a.u_log) {
-        const double u = static_cast<double>(a.variant_mdl ? a.u_log[(i * 3 + c) * M + sel] : a.u_log[i * 3 + c]);
+        const double u = static_cast<double>(p_u[c]);
         noise = exp(ls) * log(u / (1.0 - u));                                                       // :185-186 (log u - log(1-u))
       }
       xs[c] = a.variant_plain ? mu : mu + noise;  // plain variant: the noise goes on top of the chained means below
@@ -127,7 +176,6 @@ __global__ void __launch_bounds__(256) modl_sample_kernel(const SampleArgs a) {
       xo[1] = fmin(fmax(l1 + noise_keep[1], -1.0), 1.0);
       xo[2] = fmin(fmax(l2 + noise_keep[2], -1.0), 1.0);
     }
-    __syncwarp();  // every lane is done with the slot before the next bulk copy overwrites it
     if (active) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -168,10 +216,11 @@ extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const
   a.variant_plain = variant == VAEMDL_SAMPLE_PLAIN;
   a.out_unit = out_range == VAEMDL_RANGE_UNIT;
   const DeviceInfo& di = device_info();
-  const size_t tile_b = static_cast<size_t>(32) * 10 * M * 4;
-  int warps = 8;
-  while (warps > 1 && warps * tile_b + warps * 8 > static_cast<size_t>(di.max_smem_optin) / 2) --warps;
-  const size_t smem = warps * tile_b + warps * 8;
+  const size_t ul_per = u_log ? (a.variant_mdl ? 3 * M : 3) : 0;
+  const size_t per_warp = (static_cast<size_t>(32) * 10 * M + 32 * M + 32 * ul_per) * 4 + 8;
+  int warps = 16;  // one CTA per SM, as many warps as shared memory allows
+  while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
   {
     static std::mutex mu;
@@ -189,7 +238,7 @@ extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const
   }
   const long long num_tiles = ((a.n_px + 31) / 32) * n_rep;
   long long grid = (num_tiles + warps - 1) / warps;
-  const long long cap = static_cast<long long>(di.sm_count) * 2;
+  const long long cap = static_cast<long long>(di.sm_count);
   if (grid > cap) grid = cap;
   modl_sample_kernel<<<static_cast<unsigned>(grid), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return cuda_rc(cudaGetLastError());
