@@ -7,14 +7,17 @@
 // models/model05.py:141-145 (see include/vaemdl.h).
 //
 // Data movement.  The parameter tensor is a flat stream of rows (one 40*M-byte row per pixel-sample).  Every warp
-// runs its own pipeline: a 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) brings a tile of PPT rows into the warp's
-// shared-memory slot and signals an mbarrier; each lane then pulls its own row (or its MC-mixture chunk of the row)
-// into registers with conflict-free 128/64-bit shared loads, the slot is re-armed for the warp's next tile right
-// away, and the arithmetic runs out of registers while the next tile streams in.  The backward kernel stages its
-// gradient rows in a second slot and writes them back with a bulk store.  There is no CTA-wide synchronisation.
+// owns a run of consecutive tiles and runs its own pipeline: a 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) brings a
+// tile of PPT rows into the warp's shared-memory slot and signals an mbarrier; each lane reads its own row (or its
+// MC-mixture chunk of the row) with 64-bit shared loads inside a rolled loop over component pairs.  The backward
+// kernel overwrites the row in place with the unscaled gradients, rescales them once the pixel's mixture sum is
+// known and hands the tile back with a bulk store.  Per-image sums stay in registers (float64) along the run and leave
+// the warp once per image (finish.cu adds them up).  There is no CTA-wide synchronisation.
 //
-// Work split.  M = MC * LPP: LPP lanes share a pixel, each owning MC mixtures (M=5: 5x1, M=10: 10x1, M=20: 10x2,
-// M=30: 10x3).  Any other M runs on a plain one-thread-per-pixel kernel (correct, not tuned).
+// Work split.  n_mix 10 / 20 / 30: M = MC * LPP, LPP lanes share a pixel, each owning MC components, two components
+// per packed register (modl_tile_kernel: 10x1, 10x2, 10x3).  n_mix 1..9: one lane owns two pixels, the same component
+// of both per packed register (modl_pp_kernel).  Any other M runs on a plain one-thread-per-pixel kernel (correct,
+// not tuned).  Template parameter AR selects what the green / blue means are chained on (pair_eval).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
