@@ -286,8 +286,46 @@ def test_pixel_pair_kernel_vs_oracle(F, monkeypatch, S, B, H, W, M, force):
         assert relnorm(dp[ok], grad64[ok]) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("S,B,H,W,M", [(2, 2, 8, 8, 11), (1, 3, 5, 7, 12), (2, 1, 9, 9, 13), (1, 2, 8, 8, 16), (2, 2, 6, 7, 18),
+                                        (1, 2, 8, 8, 25), (1, 2, 5, 5, 32), (2, 1, 8, 8, 40), (1, 2, 4, 6, 50), (1, 1, 8, 8, 64),
+                                        (1, 2, 2, 2, 15), (1, 1, 1, 1, 24), (3, 2, 16, 12, 14), (1, 3, 3, 3, 21)])
+@pytest.mark.parametrize("plain", [False, True])
+def test_runtime_tiled_kernel_vs_oracle(F, S, B, H, W, M, plain):
+    """n_mix without its own instantiation runs on modl_rt_kernel (run-time split of a pixel over LPP lanes, uneven and
+    empty component chunks, padding pairs, rotated component order): ragged tiles, tiles straddling images, images
+    smaller than a tile (atomics route), trained-like distribution; both mean chains."""
+    params, x_u8, g = trained_like(900 + 13 * M + H, S, B, H, W, M)
+    x_u8[0, 0, 0] = torch.tensor([0, 255, 0], dtype=torch.uint8)
+    g_image = torch.randn(S, B, generator=g)
+    pd, xd = params.to(DEV), x_u8.to(DEV)
+    if plain:
+        p64 = params.double().requires_grad_(True)
+        lp = O.mdl_plain_log_prob(p64, O.normalize_u8(x_u8, torch.float64))
+        ll64 = lp.sum((-1, -2))
+        (ll64 * g_image.double()).sum().backward()
+        ll64, grad64 = ll64.detach(), p64.grad
+        ll = F.modl_log_likelihood(pd, xd, dtype=torch.float64, plain=True).cpu()
+        assert ((ll - ll64).abs() / ll64.abs()).max().item() <= LL_RTOL
+        dp = F.modl_backward(pd, xd, g_image=g_image.to(DEV), plain=True).cpu().double()
+        assert relnorm(dp, grad64) <= GRAD_RTOL
+        return
+    lp64, ll64, grad64 = oracle_ll_and_grad(params, x_u8, g_image)
+    ok = ~threshold_ambiguous(params.double(), O.normalize_u8(x_u8, torch.float64))
+    assert bool(ok.any()), "pick another seed: every image holds a threshold-ambiguous sub-pixel"
+    ll = F.modl_log_likelihood(pd, xd, dtype=torch.float64).cpu()
+    assert ((ll - ll64).abs() / ll64.abs())[ok].max().item() <= LL_RTOL
+    lp = F.modl_log_prob(pd, xd).cpu().double()
+    assert ((lp - lp64).abs().flatten(2).amax(-1))[ok].max().item() < 5e-5
+    dp = F.modl_backward(pd, xd, g_image=g_image.to(DEV)).cpu().double()
+    if bool(ok.all()):
+        assert_grad_close(dp, grad64, M)
+    else:
+        assert relnorm(dp[ok], grad64[ok]) <= GRAD_RTOL
+
+
 @pytest.mark.parametrize("S,B,H,W,M", [(2, 3, 8, 8, 10), (3, 1, 5, 7, 5), (1, 3, 3, 3, 10), (2, 1, 7, 3, 30), (1, 2, 9, 9, 2),
-                                        (2, 2, 5, 5, 7), (1, 1, 1, 1, 10), (5, 2, 16, 12, 5), (2, 2, 6, 6, 20), (1, 2, 4, 4, 13)])
+                                        (2, 2, 5, 5, 7), (1, 1, 1, 1, 10), (5, 2, 16, 12, 5), (2, 2, 6, 6, 20), (1, 2, 4, 4, 13),
+                                        (2, 2, 7, 5, 11), (1, 3, 6, 6, 16), (2, 1, 5, 9, 25), (1, 2, 3, 5, 64), (1, 1, 9, 9, 8)])
 def test_no_write_outside_the_callers_buffers(built_lib, S, B, H, W, M):
     """Guard words around every output and around the workspace (exactly vaemdl_modl_workspace_bytes long) must survive
     the forward, fused-finish and backward launches on ragged shapes (compute-sanitizer is not available on this pool)."""

@@ -269,7 +269,7 @@ def test_gpu_samplers_match_reference_source(V):
     assert (x1.cpu().double() - t64(rs["x_openai_cls_f64"])).abs().max().item() <= 1e-6
     x2 = V.MixtureDiscretizedLogisticOpenaiIWAE(l).sample(u_mix=u_mix[None], u_log=u_log[None])
     assert (x2.cpu().double() - t64(rs["x01_iwae_cls_f64"])).abs().max().item() <= 1e-6
-    x3, idx3, q3 = V.MixtureDiscretizedLogistic(l).sample(u_mix=u_mix[None], u_log=u_all[None], return_index=True,
+    x3, q3, idx3 = V.MixtureDiscretizedLogistic(l).sample(u_mix=u_mix[None], u_log=u_all[None], return_index=True,
                                                           return_quantised=True)
     assert (x3.cpu().double() - t64(rs["x01_mdl_f64"])).abs().max().item() <= 1e-6
     assert torch.equal(q3.cpu(), q(rs["x01_mdl_f64"]))

@@ -60,6 +60,8 @@ struct ModlArgs {
   int x_unit;       // apply x*2-1
   int edge_openai;  // < -0.999 / > 0.999 instead of <= -1 / >= 1
   int M;
+  // run-time tile geometry (modl_rt_kernel: any n_mix without its own instantiation)
+  int rt_MC, rt_LPP, rt_PPT, rt_rot, rt_warp_f;
 };
 
 struct Pixel {  // one pixel: both halves of a packed register see the same observation
@@ -796,6 +798,11 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* slot = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
   float* aux = slot + TILE_F;
+  // Even n_mix: the row stride 10*M words shares a large power of two with the 32 banks (16-way conflicts at M = 8), so
+  // every group of ROTB lanes walks the components in its own rotated order (<= 2-way for every M; the order of the
+  // per-pixel sum then depends on the lane, the result stays reproducible run to run).
+  constexpr int ROTB = (M % 2 != 0 || M < 2) ? 0 : (M == 8 ? 4 : 8);
+  const int rot0 = ROTB ? (lane / (ROTB ? ROTB : 1)) % M : 0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp;
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -942,13 +949,17 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
     float* auxB = aux + ppB * M;
     mbar_wait(bar, parity);
 
-    f2 lmax = pk(rowA[0], rowB[0]);
+    f2 lmax = pk(rowA[rot0], rowB[rot0]);
 #pragma unroll
-    for (int m = 1; m < M; ++m) lmax = pk(fmaxf(lo(lmax), rowA[m]), fmaxf(hi(lmax), rowB[m]));
+    for (int mi = 1; mi < M; ++mi) {
+      const int m = (mi + rot0 >= M) ? mi + rot0 - M : mi + rot0;
+      lmax = pk(fmaxf(lo(lmax), rowA[m]), fmaxf(hi(lmax), rowB[m]));
+    }
 
     f2 sumW = sp(0.0f), sumWP = sp(0.0f);
 #pragma unroll 1
-    for (int m = 0; m < M; ++m) {
+    for (int mi = 0; mi < M; ++mi) {
+      const int m = (mi + rot0 >= M) ? mi + rot0 - M : mi + rot0;
       const f2 lg = pk(rowA[m], rowB[m]);
       f2 mu[3], sc[3], kp[3];
 #pragma unroll
@@ -1039,7 +1050,8 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
         if (tinyB) modl_pixel_logdomain(growB, M, pxb, a.plain != 0, ltB, llB);
       }
 #pragma unroll 1
-      for (int m = 0; m < M; ++m) {
+      for (int mi = 0; mi < M; ++mi) {
+        const int m = (mi + rot0 >= M) ? mi + rot0 - M : mi + rot0;
         const f2 lg = pk(rowA[m], rowB[m]);
         const f2 W = ex2_2((lg - lmax) * kLog2e);
         const f2 wp = pk(auxA[m], auxB[m]);
@@ -1072,6 +1084,295 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
         }
       }
       // hand the gradient tile to the TMA engine
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+      float* dst = a.dparams + t * TILE_F;
+      if ((bytes & 15u) == 0) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (a.bwd_hint & 2)
+            bulk_s2g_hint(dst, slot, bytes, pol_first);
+          else
+            bulk_s2g(dst, slot, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = slot[q];
+        __syncwarp();
+      }
+      if (it + 1 < t_cnt) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        issue(t + t_dir);
+      }
+    }
+  }
+  if constexpr (BWD) {
+    if (lane == 0) bulk_wait_all<0>();
+  } else {
+    if (a.partial && t_cnt > 0) {
+      const long long n_last = (t_end * PPT < a.n_px ? t_end * PPT - 1 : a.n_px - 1) / a.HW;
+      const double d0 = warp_sum(acc0), d1 = warp_sum(acc1);
+      if (lane == 0) {
+        a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+        if (n_base + 1 <= n_last) a.partial[partial_slot(n_base + 1, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
+      }
+    }
+  }
+}
+
+// ---- the run-time tiled kernel (any n_mix) --------------------------------------------------------------------------------
+// Same pipeline as modl_tile_kernel with one slot per warp, but n_mix and the split of a pixel over lanes are run-time
+// values chosen by the host (rt_plan): LPP lanes share a pixel, lane `sub` of the group owns components
+// [sub*MC, min(M, (sub+1)*MC)), two per packed register; PPT = 32 / LPP pixels per tile (one fewer when PPT * M would be
+// odd: bulk copies need 16-byte multiples).  A lane walks its component pairs in an order rotated by rot * pixel so that
+// the 32 scalar shared-memory loads of one instruction spread over the banks whatever 10 * M is modulo 32.
+__device__ __forceinline__ float group_sum_rt(float v, int base, int LPP) {
+  float s = __shfl_sync(kFull, v, base);
+  for (int j = 1; j < LPP; ++j) s += __shfl_sync(kFull, v, (base + j) & 31);
+  return s;
+}
+__device__ __forceinline__ float group_max_rt(float v, int base, int LPP) {
+  float s = __shfl_sync(kFull, v, base);
+  for (int j = 1; j < LPP; ++j) s = fmaxf(s, __shfl_sync(kFull, v, (base + j) & 31));
+  return s;
+}
+
+// AL: n_mix and MC even -> every component pair sits on an 8-byte boundary and is moved with 64-bit shared accesses
+template <bool BWD, int AR, bool AL>
+__global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
+  const int M = a.M, MC = a.rt_MC, LPP = a.rt_LPP, PPT = a.rt_PPT;
+  const int ROWF = 10 * M, TILE_F = PPT * ROWF, NPAIR = (MC + 1) >> 1;
+  const int WARP_F = a.rt_warp_f;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* slot = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
+  float* aux = slot + TILE_F;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  if constexpr (BWD)
+    pdl_wait();
+  else
+    pdl_trigger();
+
+  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const int p_raw = lane / LPP;
+  const bool lane_used = p_raw < PPT;
+  const int p = lane_used ? p_raw : 0;  // idle lanes shadow pixel 0 (they never write)
+  const int sub = lane - p_raw * LPP;
+  const int gbase = lane - sub;         // first lane of this pixel's group
+  const int m0 = sub * MC;
+  const int m_end = m0 + MC < M ? m0 + MC : M;
+  const int m_safe = m0 < M ? m0 : 0;   // a group's last lane may own nothing (M = 9 over 4 lanes)
+  int rot = (a.rt_rot * p) % NPAIR;
+
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+  const long long t_cnt = t_end - t_begin;
+  const bool rev = BWD && a.reverse;
+  const long long t_first = rev ? t_end - 1 : t_begin;
+  const long long t_dir = rev ? -1 : 1;
+  const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+
+  auto tile_rows = [&](long long t) -> int {
+    const long long rem = a.n_px - t * PPT;
+    return rem < PPT ? static_cast<int>(rem) : PPT;
+  };
+  auto issue = [&](long long t) {
+    const int rows = tile_rows(t);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
+    const float* src = a.params + t * TILE_F;
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, bytes);
+        if (BWD) {
+          if (a.bwd_hint & 1)
+            bulk_g2s_hint(slot, src, bytes, bar, pol_first);
+          else
+            bulk_g2s(slot, src, bytes, bar);
+        } else {
+          if (a.keep_tiles > 0)
+            bulk_g2s_hint(slot, src, bytes, bar, (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
+          else
+            bulk_g2s(slot, src, bytes, bar);
+        }
+      }
+    } else {
+      for (int i = lane; i < rows * ROWF; i += 32) slot[i] = src[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(bar, 0);
+    }
+  };
+  if (t_cnt > 0) issue(t_first);
+
+  const long long step_n = PPT / a.HW;
+  const int step_pix = static_cast<int>(PPT - step_n * a.HW);
+  long long n_own = (t_first * PPT + p) / a.HW;
+  int pix_own = static_cast<int>((t_first * PPT + p) - n_own * a.HW);
+  double acc0 = 0.0, acc1 = 0.0;
+  long long n_base = (t_begin * PPT) / a.HW;
+
+  auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
+                   float& g_out) {
+    const int rows = tile_rows(t);
+    const long long n_first = __shfl_sync(kFull, n_lane, 0);
+    const int pix_first = __shfl_sync(kFull, pix_lane, 0);
+    const bool in = p < rows;
+    const long long n = in ? n_lane : n_first;
+    const int pix = in ? pix_lane : pix_first;
+    raw = load_pixel_raw(a, n, pix);
+    g_out = 0.0f;
+    if constexpr (BWD) {
+      if (a.g_image) g_out = a.g_image[n];
+      if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+    }
+    n_out = n;
+    nfirst_out = n_first;
+  };
+  long long n_cur = 0, nfirst_cur = 0;
+  PixRaw raw_cur{};
+  float g_cur = 0.0f;
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+
+  for (long long it = 0; it < t_cnt; ++it) {
+    const long long t = t_first + it * t_dir;
+    const uint32_t parity = static_cast<uint32_t>(it & 1);
+    const int rows = tile_rows(t);
+    const int pp = p < rows ? p : 0;
+    const bool active = lane_used && (p < rows);
+    const long long i = t * PPT + pp;
+    const long long n = n_cur, n_first = nfirst_cur;
+    const float g = g_cur;
+    Pixel px;
+    decode_pixel(a, raw_cur, px);
+    if (!rev) {
+      n_own += step_n;
+      pix_own += step_pix;
+      if (pix_own >= a.HW) {
+        pix_own -= a.HW;
+        ++n_own;
+      }
+    } else {
+      n_own -= step_n;
+      pix_own -= step_pix;
+      if (pix_own < 0) {
+        pix_own += a.HW;
+        --n_own;
+      }
+    }
+    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+
+    float* rowp = slot + pp * ROWF;
+    float* auxp = aux + pp * M;
+    mbar_wait(bar, parity);
+
+    float lmax = -INFINITY;
+    for (int m = m0; m < m_end; ++m) lmax = fmaxf(lmax, rowp[m]);
+    lmax = group_max_rt(lmax, gbase, LPP);
+
+    f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
+#pragma unroll 1
+    for (int pr = 0; pr < NPAIR; ++pr) {
+      const int prr = pr + rot >= NPAIR ? pr + rot - NPAIR : pr + rot;
+      const int m = m0 + 2 * prr;
+      const bool vlo = m < m_end, vhi = m + 1 < m_end;
+      const int ml = vlo ? m : m_safe, mh = vhi ? m + 1 : ml;
+      f2 lg = ld_pair<AL>(rowp, ml, !vhi);
+      lg = pk(vlo ? lo(lg) : -INFINITY, vhi ? hi(lg) : -INFINITY);  // padding halves get zero weight
+      f2 mu[3], sc[3], kp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* q = rowp + (1 + 3 * c) * M;
+        mu[c] = ld_pair<AL>(q, ml, !vhi);
+        sc[c] = ld_pair<AL>(q, M + ml, !vhi);
+        kp[c] = ld_pair<AL>(q, 2 * M + ml, !vhi);
+      }
+      const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
+      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+      f2 u[9];
+      f2 P;
+      if (narrow)
+        P = pair_eval<true, BWD, Pixel, AR>(px, mu, sc, kp, u);
+      else
+        P = pair_eval<false, BWD, Pixel, AR>(px, mu, sc, kp, u);
+      if (!vlo) P = sp(0.0f);  // a padding pair was evaluated on clamped (backward: possibly overwritten) values
+      sumW2 = sumW2 + W;
+      sumWP2 = fma2(W, P, sumWP2);
+      if constexpr (BWD) {
+        const f2 wp = W * P;
+        if (active && vlo) {  // (AL: a pair is valid or padding as a whole)
+#pragma unroll
+          for (int j = 0; j < 9; ++j) st_pair<AL>(rowp, (1 + j) * M + ml, !vhi, u[j]);
+          st_pair<AL>(auxp, ml, !vhi, wp);
+        }
+      }
+    }
+    const float S = group_sum_rt(lo(sumWP2) + hi(sumWP2), gbase, LPP);
+    const float SW = group_sum_rt(lo(sumW2) + hi(sumW2), gbase, LPP);
+    const bool tiny = !(S > kTinySum);  // also catches NaN
+    const float* grow = a.params + i * ROWF;
+
+    if constexpr (!BWD) {
+      __syncwarp();
+      if (it + 1 < t_cnt) issue(t + t_dir);  // every lane has read its row: re-arm the slot with the warp's next tile
+      float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;
+      if (tiny) {
+        float lt, ll;
+        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+        lp = lt - ll;
+      }
+      const bool owner = active && sub == 0;
+      if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
+      const float val = owner ? lp : 0.0f;
+      if (a.partial) {
+        while (n_base < n_first) {
+          const double done = warp_sum(acc0);
+          if (lane == 0) a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
+        }
+        if (n == n_base)
+          acc0 += static_cast<double>(val);
+        else
+          acc1 += static_cast<double>(val);
+      } else if (a.ll_atomic) {
+        if (owner) atomicAdd(a.ll_atomic + n, static_cast<double>(val));
+      }
+    } else {
+      const float rS = rcpa(S), rSW = rcpa(SW);
+      float lt = 0.f, ll = 0.f;
+      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+#pragma unroll 1
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int prr = pr + rot >= NPAIR ? pr + rot - NPAIR : pr + rot;
+        const int m = m0 + 2 * prr;
+        const bool vlo = m < m_end, vhi = m + 1 < m_end;
+        const int ml = vlo ? m : m_safe, mh = vhi ? m + 1 : ml;
+        const f2 lg = ld_pair<AL>(rowp, ml, !vhi);
+        const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+        const f2 wp = ld_pair<AL>(auxp, ml, !vhi);
+        f2 r = wp * rS;     // posterior responsibility of the component
+        f2 pi = W * rSW;    // softmax(logits)
+        if (tiny) {
+          r = pk(expf(modl_logt(grow, M, ml, px, a.plain != 0) - lt), expf(modl_logt(grow, M, mh, px, a.plain != 0) - lt));
+          pi = pk(expf(grow[ml] - ll), expf(grow[mh] - ll));
+        }
+        const f2 gr = r * g;
+        const f2 dl = (r - pi) * g;
+        if (active && vlo) {
+          st_pair<AL>(rowp, ml, !vhi, dl);
+#pragma unroll
+          for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + ml, !vhi, ld_pair<AL>(rowp, j * M + ml, !vhi) * gr);
+        }
+      }
       const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
       float* dst = a.dparams + t * TILE_F;
       if ((bytes & 15u) == 0) {
@@ -1352,6 +1653,148 @@ static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   return cuda_rc(cudaGetLastError());
 }
 
+// ---- run-time tile geometry for modl_rt_kernel -------------------------------------------------------------------------
+// For a given n_mix pick (LPP, rot): score = lane efficiency / sqrt(mean bank-conflict degree of the scalar parameter loads)
+// * sqrt(min(1, warps that fit / 16)).  Evaluated once per n_mix (a few thousand integer operations) and cached.
+struct RtPlan {
+  int MC = 0, LPP = 0, PPT = 0, rot = 0;
+};
+// score = lane efficiency * MC / (MC + 3) * sqrt(min(1, warps that fit / 16)) / (mean bank-conflict degree)^(1/4):
+// measured on B200 (tools/rt_sweep.py), long component chunks per lane win over many lanes per pixel (the per-tile work of
+// a lane -- logit max, group reductions, log, index bookkeeping -- is amortised over MC components), as long as 16 warps
+// still fit in shared memory.  Evaluated once per (n_mix, direction) and cached.
+static RtPlan rt_plan_compute(int M, bool bwd) {
+  RtPlan best;
+  double best_score = -1.0;
+  for (int LPP = 1; LPP <= 16; ++LPP) {
+    const int MC = (M + LPP - 1) / LPP;
+    if (MC > 13) continue;
+    int PPT = 32 / LPP;
+    if ((PPT * M) & 1) --PPT;  // tile bytes = PPT * 40 * M must be a multiple of 16
+    if (PPT < 1) continue;
+    const int NP = (MC + 1) / 2;
+    const double eff = static_cast<double>(M) / (2.0 * NP * LPP) * (static_cast<double>(PPT) * LPP / 32.0);
+    const double per_warp = (PPT * 10.0 * M + (bwd ? PPT * M : 0)) * 4.0 + 24.0;
+    double occ = 227.0 * 1024.0 / per_warp / 16.0;
+    if (occ > 1.0) occ = 1.0;
+    for (int rot = 0; rot < (NP > 1 ? 4 : 1); ++rot) {
+      long long tot = 0, cnt = 0;
+      for (int pr = 0; pr < NP; ++pr) {
+        for (int half = 0; half < 2; ++half) {
+          // the ten parameter planes of a row are k*M apart: evaluate the first one
+          int per_bank_addr[32][32];
+          int per_bank_n[32] = {0};
+          for (int lane = 0; lane < 32; ++lane) {
+            const int pq = lane / LPP, sub = lane % LPP;
+            if (pq >= PPT) continue;
+            const int m0 = sub * MC, m_end = m0 + MC < M ? m0 + MC : M;
+            const int prr = (pr + rot * pq) % NP;
+            int m = m0 + 2 * prr + half;
+            if (m >= m_end) m = m0 < M ? m0 : 0;
+            const int addr = pq * 10 * M + m;
+            const int bnk = addr & 31;
+            bool seen = false;
+            for (int q = 0; q < per_bank_n[bnk]; ++q) seen = seen || per_bank_addr[bnk][q] == addr;
+            if (!seen) per_bank_addr[bnk][per_bank_n[bnk]++] = addr;
+          }
+          int deg = 1;
+          for (int bnk = 0; bnk < 32; ++bnk) deg = per_bank_n[bnk] > deg ? per_bank_n[bnk] : deg;
+          tot += deg;
+          ++cnt;
+        }
+      }
+      const double conflict = static_cast<double>(tot) / static_cast<double>(cnt);
+      const double score = eff * MC / (MC + 3.0) * sqrt(occ) / sqrt(sqrt(conflict));
+      if (score > best_score) {
+        best_score = score;
+        best = RtPlan{MC, LPP, PPT, rot};
+      }
+    }
+  }
+  return best;
+}
+static RtPlan rt_plan(int M, bool bwd) {
+  const char* env = getenv("VAEMDL_RT");  // "LPP:rot" overrides the choice (tuning sweeps; re-read on every call)
+  int l = 0, r = 0;
+  if (env && sscanf(env, "%d:%d", &l, &r) == 2 && l >= 1 && l <= 32 && (M + l - 1) / l <= 16) {
+    int ppt = 32 / l;
+    if ((ppt * M) & 1) --ppt;
+    if (ppt >= 1) return RtPlan{(M + l - 1) / l, l, ppt, r};
+  }
+  static std::mutex mu;
+  static RtPlan cache[2][VAEMDL_MAX_MIX + 1];
+  std::lock_guard<std::mutex> lock(mu);
+  RtPlan& c = cache[bwd ? 1 : 0][M];
+  if (c.LPP == 0) c = rt_plan_compute(M, bwd);
+  return c;
+}
+
+template <bool BWD, int AR, bool AL>
+static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan* plan);
+
+template <bool BWD, int AR>
+static int launch_rt(ModlArgs a, cudaStream_t st, TilePlan* plan) {
+  const RtPlan rp = rt_plan(a.M, BWD);
+  if (rp.LPP == 0) return VAEMDL_EUNSUPPORTED;
+  static const bool no_al = getenv("VAEMDL_RT_NOAL") != nullptr;  // A/B: scalar shared accesses everywhere
+  const bool al = (a.M % 2 == 0) && (rp.MC % 2 == 0 || rp.LPP == 1) && !no_al;
+  return al ? launch_rt_al<BWD, AR, true>(a, rp, st, plan) : launch_rt_al<BWD, AR, false>(a, rp, st, plan);
+}
+
+template <bool BWD, int AR, bool AL>
+static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan* plan) {
+  a.rt_MC = rp.MC;
+  a.rt_LPP = rp.LPP;
+  a.rt_PPT = rp.PPT;
+  a.rt_rot = rp.rot;
+  const int tile_f = rp.PPT * 10 * a.M;
+  a.rt_warp_f = (tile_f + (BWD ? rp.PPT * a.M : 0) + 3) & ~3;  // every warp's slot stays 16-byte aligned
+  a.num_tiles = (a.n_px + rp.PPT - 1) / rp.PPT;
+  const DeviceInfo& di = device_info();
+  const size_t per_warp = static_cast<size_t>(a.rt_warp_f) * 4 + 8;
+  int warps = tune_shape(BWD, Shape{1, 16}).warps;
+  while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  if (warps * per_warp > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
+  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  const size_t smem = warps * per_warp;
+  auto kern = modl_rt_kernel<BWD, AR, AL>;
+  static std::mutex mu;
+  static int c_dev = -1;
+  static size_t c_smem = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_dev != dev || smem > c_smem) {  // the attribute is a maximum: raise it when a larger footprint shows up
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_rc(e);
+      c_dev = dev;
+      c_smem = smem;
+    }
+  }
+  const long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = di.sm_count;  // persistent, one CTA per SM (__launch_bounds__(512, 1))
+  if (grid > need) grid = need;
+  if (grid * warps > kMaxGridWarps) grid = kMaxGridWarps / warps;
+  if (grid < 1) grid = 1;
+  const long long total_warps = grid * warps;
+  a.tw_base = a.num_tiles / total_warps;
+  a.tw_rem = a.num_tiles % total_warps;
+  a.K = partial_K(a.HW, rp.PPT, a.tw_base);
+  a.small = a.n_px < (1ll << 31) - 64;
+  apply_l2_opt(a, total_warps, static_cast<long long>(tile_f) * 4);
+  if (plan) {
+    plan->total_warps = total_warps;
+    plan->tw_base = a.tw_base;
+    plan->tw_rem = a.tw_rem;
+    plan->K = a.K;
+    plan->PPT = rp.PPT;
+  }
+  if (BWD) return cuda_rc(launch_pdl(kern, static_cast<unsigned>(grid), static_cast<unsigned>(warps * 32), smem, st, a));
+  kern<<<static_cast<unsigned>(grid), warps * 32, smem, st>>>(a);
+  return cuda_rc(cudaGetLastError());
+}
+
 // n_mix 1..9 run on the pixel-pair kernel.  n_mix = 5 also has a component-pair instantiation with 32-row tiles, which
 // is a little faster while the problem is so small that a warp only sees a handful of tiles (measured: 112 vs 117 us
 // per step at 5 x 128 x 32 x 32, 345 vs 314 us backward at 16 x 64 x 64 x 64).
@@ -1389,6 +1832,8 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
     case 30:
       return launch_tiled<10, 3, BWD, AR>(a, st, plan);
     default: {
+      static const bool force_generic = getenv("VAEMDL_GENERIC") != nullptr;  // A/B against the one-thread-per-pixel kernel
+      if (!force_generic) return launch_rt<BWD, AR>(a, st, plan);
       const DeviceInfo& di = device_info();
       long long blocks = (a.n_px + 127) / 128;
       const long long cap = static_cast<long long>(di.sm_count) * 8;
@@ -1410,7 +1855,8 @@ static int tile_ppt(int M, long long n_px) {
     case 30:
       return 10;
     default:
-      return 0;  // generic kernel: atomics
+      if (getenv("VAEMDL_GENERIC")) return 0;  // one-thread-per-pixel kernel: atomics
+      return rt_plan(M, false).PPT;
   }
 }
 
