@@ -1,7 +1,9 @@
 """Op-for-op CPU restatement (torch-CPU tensors) of the reference's observation-model path.
 
-TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  PARITY UNPINNED (no
-golden vectors exist in the reference and TensorFlow cannot run here).
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Pinned against the
+reference's own source executed over ``oracle/tf_shim`` (tests/golden/refsrc_*.npz,
+tests/test_reference_golden.py); TensorFlow itself cannot run here, so TF's
+float32 kernel rounding stays unpinned.
 
 Two flavours of every function, selected by the dtype of the inputs:
 

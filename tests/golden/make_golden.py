@@ -2,8 +2,8 @@
 
 The reference itself (TensorFlow + TensorFlow-Probability) cannot be imported in this image, so these vectors are
 NOT outputs of the reference -- they pin the oracle (any later change to it shows up as a fixture mismatch) and give
-the GPU tests byte-identical inputs on every box.  Parity therefore stays "unpinned" in the sense of the task
-statement; see oracle/__init__.py.
+the GPU tests byte-identical inputs on every box.  The vectors that DO come from the reference's code are the
+refsrc_*.npz files next to these (make_reference_golden.py: same inputs, outputs of the reference's own modules).
 
     python tests/golden/make_golden.py        # rewrites the .npz files
 """
