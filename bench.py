@@ -219,9 +219,16 @@ class ModlStep:
         self.params = self.pool[self.k % len(self.pool)]
 
     def step(self):
+        """One call of vaemdl_modl_iwae_step: a single cooperative launch for small training shapes (BASELINE configs[0]),
+        forward + finish + backward (3 launches) otherwise; self.launches holds what the library enqueued."""
         self.next_input()
-        self.fwd()
-        self.bwd()
+        n = ctypes.c_int(0)
+        rc = self.L.vaemdl_modl_iwae_step(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B, self.b_total,
+                                          self.B, self.H, self.W, self.M, self.extra.data_ptr(), None, self.ll64.data_ptr(),
+                                          None, self.lme.data_ptr(), self.elbo.data_ptr(), self.g_ll.data_ptr(),
+                                          self.dparams.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.st, ctypes.byref(n))
+        assert rc == 0, rc
+        self.launches = n.value
 
 
 def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index):
@@ -360,7 +367,7 @@ def also_workloads(dev, peak):
         nbuf = max(2, -(-3 * L2_BYTES // (S * B * H * W * 40 * M)))
         st = ModlStep(S, B, H, W, M, dev, 7, B, n_buffers=nbuf)
         t = timeit(st.step, 20)
-        out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6,
+        out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6, "launches_per_step": st.launches,
                      "algorithmic_GBs": st.n_px * 120 * M / t / 1e9, "frac_of_hbm_peak": st.n_px * 120 * M / t / 1e9 / peak}
         if name.startswith("cfg1"):
             def on_stream(sp, st=st):

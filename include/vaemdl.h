@@ -113,6 +113,23 @@ VAEMDL_API int vaemdl_modl_iwae_fwd(const float* params, const void* x, int x_dt
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * One IWAE step of the observation model in ONE call: forward, per-image sums, log-mean-exp over importance
+ * samples, batch mean and the parameter gradient of the loss -elbo.
+ * replaces: iwae_loss + tape.gradient restricted to pxz    models/loss.py:26-55 ; models/model05.py:141-145
+ * Same arguments and outputs as vaemdl_modl_iwae_fwd (lme_b and g_ll required here) followed by
+ * vaemdl_modl_bwd(g_image = g_ll) -> dparams [S, B, H, W, 10*M].
+ * For S <= 32, n_mix in {5, 10, 20, 30} and problems of up to a few dozen tiles per warp (the training shapes of
+ * models/model05.py: 5 x 64..128 x 32 x 32) this is ONE cooperative kernel launch -- forward pass, grid barrier, IWAE
+ * finish, grid barrier, backward pass starting on the tile still resident in shared memory; anything else runs the
+ * three launches of the calls above.  *launches (nullable) receives the number of kernel launches that were enqueued.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_iwae_step(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                    const float* extra,
+                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                    float* dparams, void* workspace, size_t workspace_bytes, void* stream, int* launches);
+
+/* ------------------------------------------------------------------------ *
  * Mixture of discretized logistics -- gradient w.r.t. params
  * replaces: tf.GradientTape over the ops above              models/model05.py:141-145
  * The upstream gradient on lp_pixel[n,h,w] is
@@ -143,6 +160,11 @@ VAEMDL_API int vaemdl_modl_plain_iwae_fwd(const float* params, const void* x, in
                     const float* extra,
                     float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
                     void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_plain_iwae_step(const float* params, const void* x, int x_dtype,
+                         int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                         const float* extra,
+                         float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                         float* dparams, void* workspace, size_t workspace_bytes, void* stream, int* launches);
 VAEMDL_API int vaemdl_modl_plain_bwd(const float* params, const void* x, int x_dtype,
                     long long n_img, int x_batch, int H, int W, int M,
                     const float* g_image, const float* g_pixel,

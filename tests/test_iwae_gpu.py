@@ -260,3 +260,51 @@ def test_latent_terms_model06_shapes(V):
     assert relnorm(dloc[1], c1.grad) < 1e-5 and relnorm(dsc[1], c2.grad) < 1e-5
     assert relnorm(dloc[2], d1.grad) < 1e-5 and relnorm(dsc[2], d2.grad) < 1e-5
     assert relnorm(dloc[3], b1.grad) < 1e-5 and relnorm(dsc[3], b2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("S,B,H,W,M,plain", [(5, 8, 32, 32, 10, False), (5, 16, 32, 32, 5, False), (3, 4, 8, 8, 10, False),
+                                              (2, 2, 16, 16, 20, False), (2, 2, 8, 4, 30, False), (1, 3, 5, 7, 10, False),
+                                              (32, 1, 8, 8, 10, False), (4, 3, 9, 9, 5, True), (2, 5, 16, 16, 10, True),
+                                              (3, 200, 8, 8, 10, False)])
+def test_one_launch_step_equals_three_launch_step(built_lib, monkeypatch, S, B, H, W, M, plain):
+    """vaemdl_modl_iwae_step: the cooperative one-launch kernel (forward -> grid barrier -> finish -> grid barrier ->
+    backward on the resident tile) gives bit-identical per-image sums, weights and gradients to forward + finish +
+    backward as three launches, and both match the float64 oracle."""
+    from vae_mdl_b200 import functional as F
+    g = torch.Generator().manual_seed(7000 + S + 3 * B + H + M)
+    params = torch.randn(S, B, H, W, 10 * M, generator=g)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    x_u8.view(-1)[::13] = 0
+    x_u8.view(-1)[5::17] = 255
+    p64 = params.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    lp = O.mdl_plain_log_prob(p64, x64) if plain else O.modl_log_prob(p64, x64)[..., 0]
+    ll64 = lp.sum((-1, -2))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()) + torch.randn(S, B, generator=g).double()
+    log_w = ll64 + extra.float().double()
+    loss64 = -O.logmeanexp(log_w, 0).mean()
+    loss64.backward()
+    pd, xd, ed = params.to(DEV), x_u8.to(DEV), extra.float().to(DEV)
+    monkeypatch.setenv("VAEMDL_FUSED", "1")
+    a = F.modl_iwae_step(pd, xd, ed, plain=plain)
+    torch.cuda.synchronize()
+    assert a[-1] == 1, "the one-launch kernel was not taken"
+    monkeypatch.setenv("VAEMDL_FUSED", "0")
+    b = F.modl_iwae_step(pd, xd, ed, plain=plain)
+    torch.cuda.synchronize()
+    assert b[-1] == 3
+    for name, u, v in zip(("ll64", "log_w", "lme_b", "elbo", "g_ll", "dparams"), a[:-1], b[:-1]):
+        if name == "elbo":
+            assert abs(u.item() - v.item()) <= 1e-6 * abs(v.item())
+        else:
+            assert torch.equal(u, v), f"{name} differs between the one-launch and the three-launch step"
+    assert ((a[0].cpu() - ll64.detach()).abs() / ll64.detach().abs()).max().item() <= 1e-5
+    assert abs(-a[3].item() - loss64.item()) <= 1e-5 * abs(loss64.item())
+    rel = ((a[5].cpu().double() - p64.grad).norm() / p64.grad.norm()).item()
+    assert rel <= 1e-4, rel
+    # sharded batch: b_total > B scales the weights and the loss share
+    monkeypatch.setenv("VAEMDL_FUSED", "1")
+    c = F.modl_iwae_step(pd, xd, ed, b_total=4 * B, plain=plain)
+    assert c[-1] == 1
+    assert torch.allclose(c[4] * 4.0, a[4], rtol=1e-6, atol=0) and abs(c[3].item() * 4.0 - a[3].item()) <= 1e-5 * abs(a[3].item())
+    assert torch.allclose(c[5] * 4.0, a[5], rtol=1e-5, atol=1e-12)

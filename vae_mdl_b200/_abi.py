@@ -42,6 +42,12 @@ PROTOTYPES = {
     "vaemdl_modl_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_iwae_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
+                                      c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "vaemdl_modl_plain_iwae_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
+                                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vaemdl_modl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_plain_fwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,

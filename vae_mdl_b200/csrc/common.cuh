@@ -195,6 +195,29 @@ __device__ __forceinline__ long long partial_slot(long long n, long long w, long
     w_lo = run_of_tile<long long>((n * HW) / PPT, base, rem);
   return n * K + (w - w_lo);
 }
+// image n's sum: the partials of the forward warps whose tile runs touched it -- contiguous, added in warp order
+template <typename I>
+__device__ __forceinline__ double image_sum_t(const PartialGeom& g, long long n64) {
+  const I n = static_cast<I>(n64), HW = static_cast<I>(g.HW), PPT = static_cast<I>(g.PPT);
+  const I base = static_cast<I>(g.tw_base), rem = static_cast<I>(g.tw_rem);
+  const I first = n * HW, last = first + HW - 1;
+  const I w_lo = run_of_tile<I>(first / PPT, base, rem), w_hi = run_of_tile<I>(last / PPT, base, rem);
+  const int cnt = static_cast<int>(w_hi - w_lo) + 1;
+  const double* p = g.partial + n64 * g.K;
+  double acc = 0.0;
+  for (int j0 = 0; j0 < cnt; j0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (j0 + j < cnt) ? p[j0 + j] : 0.0;  // all loads first, then the adds (fixed order)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += v[j];
+  }
+  return acc;
+}
+__device__ __forceinline__ double image_sum(const PartialGeom& g, long long n, bool small) {
+  return small ? image_sum_t<unsigned>(g, n) : image_sum_t<long long>(g, n);
+}
+
 struct IwaeOut {  // outputs of the fused IWAE finish (all nullable); active when S > 0
   int S = 0;
   long long B = 0, B_total = 0;

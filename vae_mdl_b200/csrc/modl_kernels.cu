@@ -37,3 +37,13 @@ extern "C" int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, 
   return modl_bwd_impl<0>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_image, g_pixel, dparams,
                           static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int vaemdl_modl_iwae_step(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
+                                     long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
+                                     float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo,
+                                     float* g_ll, float* dparams, void* workspace, size_t workspace_bytes, void* stream,
+                                     int* launches) {
+  return modl_iwae_step_impl<0>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, dparams, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream), launches);
+}

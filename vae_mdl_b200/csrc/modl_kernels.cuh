@@ -18,6 +18,9 @@
 // per packed register (modl_tile_kernel: 10x1, 10x2, 10x3).  n_mix 1..9: one lane owns two pixels, the same component
 // of both per packed register (modl_pp_kernel).  Any other M runs on a plain one-thread-per-pixel kernel (correct,
 // not tuned).  Template parameter AR selects what the green / blue means are chained on (pair_eval).
+#include <cooperative_groups.h>
+
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -456,29 +459,36 @@ __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r,
   }
 }
 
-template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR>
-__global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
+// FUSED: the forward and the backward pass of one step run inside ONE cooperative kernel (modl_step_kernel): both use
+// the backward shared-memory layout, the mbarrier is initialised once and its phase carries over, the forward pass
+// leaves its last tile in the slot and the (reversed) backward pass starts on it without loading anything.
+template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED>
+__device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem_raw) {
   using T = Tile<MC, LPP>;
   constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F, NPAIR = T::NPAIR;
   constexpr bool AL = T::ALIGNED;
-  constexpr int WARP_F = NSLOT * TILE_F + (BWD ? T::AUX_F : 0);
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int WARP_F = NSLOT * TILE_F + ((BWD || FUSED) ? T::AUX_F : 0);
+  static_assert(!FUSED || NSLOT == 1, "the fused step keeps one slot per warp");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
   float* aux = slots + NSLOT * TILE_F;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp * NSLOT;
 
-  if (lane == 0) {
+  if constexpr (!(FUSED && BWD)) {
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) mbar_init(&bars[s], 1);
-    fence_barrier_init();
+      for (int s = 0; s < NSLOT; ++s) mbar_init(&bars[s], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
-  if constexpr (BWD)
-    pdl_wait();     // launched programmatically behind the finish kernel: g_image (and, in general, the parameters) must be complete
-  else
-    pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
+  if constexpr (!FUSED) {
+    if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+    if constexpr (BWD)
+      pdl_wait();     // launched programmatically behind the finish kernel: g_image (and, in general, the parameters) must be complete
+    else
+      pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
+  }
 
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
   const bool lane_used = (lane / LPP) < PPT;
@@ -528,11 +538,16 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     }
   };
 
-  // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below)
+  // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below);
+  // fused backward: the first tile (the forward pass's last) is already in the slot
+  if constexpr (!(FUSED && BWD)) {
 #pragma unroll
-  for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
-    if (s < t_cnt) issue(t_first + s * t_dir, s);
+    for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
+      if (s < t_cnt) issue(t_first + s * t_dir, s);
+    }
   }
+  // loads this warp's barrier has completed before this pass (fused backward: the whole forward pass but the resident tile)
+  const uint32_t phase0 = (FUSED && BWD) ? static_cast<uint32_t>(t_cnt - 1) : 0u;
 
   // (image, pixel-in-image) of this lane's pixel-sample, advanced incrementally: one 64-bit division per kernel
   const long long step_n = PPT / a.HW;
@@ -571,7 +586,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   for (long long it = 0; it < t_cnt; ++it) {
     const long long t = t_first + it * t_dir;
     const int s = static_cast<int>(it % NSLOT);
-    const uint32_t parity = static_cast<uint32_t>((it / NSLOT) & 1);
+    const uint32_t parity = (phase0 + static_cast<uint32_t>(it / NSLOT)) & 1u;
     const int rows = tile_rows(t);
     const int pp = p < rows ? p : 0;
     const bool active = lane_used && (p < rows);
@@ -601,7 +616,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
     float* slot = slots + s * TILE_F;
     float* rowp = slot + pp * ROWF;
     float* auxp = aux + pp * M;
-    mbar_wait(&bars[s], parity);
+    if (!(FUSED && BWD && it == 0)) mbar_wait(&bars[s], parity);
     if constexpr (BWD && NSLOT > 1) {
       // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
       // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
@@ -757,6 +772,88 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
       }
     }
   }
+}
+
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR>
+__global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  tile_body<MC, LPP, BWD, NSLOT, AR, false>(a, smem_raw);
+}
+
+// ---- one step in one launch: forward -> grid barrier -> per-image sums, log-mean-exp, softmax weights -> grid barrier ->
+// backward.  For training shapes small enough that launch boundaries and pipeline ramps dominate (BASELINE configs[0]:
+// 131 MB of parameters, ~4 tiles per warp): no launch gaps, one ramp instead of three, and each warp's last forward tile
+// is still in shared memory when its reversed backward run starts.  Cooperative launch (all CTAs co-resident).
+struct StepFinish {
+  PartialGeom geom;
+  const float* extra;  // [S,B] nullable
+  float* ll;           // [S,B] nullable
+  double* ll64;        // [S,B] nullable
+  float* log_w;        // [S,B] nullable
+  float* lme_b;        // [B]
+  float* elbo;         // [1] nullable
+  float* g_ll;         // [S,B]
+  double* lme64;       // [B] scratch
+  long long B;
+  int S;  // <= 32: one importance sample per lane
+  float b_norm;
+  bool small;
+};
+struct StepArgs {
+  ModlArgs a;
+  StepFinish f;
+};
+
+// warp `gw` of `total_warps` takes batch elements gw, gw + total_warps, ...: same arithmetic, in the same order, as
+// finish_kernel steps (1) and (2) with S <= 32
+__device__ __forceinline__ void step_finish(const StepFinish& f, long long gw, long long total_warps, int lane) {
+  for (long long b = gw; b < f.B; b += total_warps) {
+    const long long n = static_cast<long long>(lane) * f.B + b;
+    double v = -INFINITY;
+    if (lane < f.S) {
+      const double acc = image_sum(f.geom, n, f.small);
+      if (f.ll) f.ll[n] = static_cast<float>(acc);
+      if (f.ll64) f.ll64[n] = acc;
+      v = acc + (f.extra ? static_cast<double>(f.extra[n]) : 0.0);  // models/loss.py:34
+      if (f.log_w) f.log_w[n] = static_cast<float>(v);
+    }
+    double mx = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));  // utils/utils.py:10
+    const float e = lane < f.S ? expf(static_cast<float>(v - mx)) : 0.0f;
+    float sm = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(kFull, sm, o);
+    const double lme = static_cast<double>(logf(sm / static_cast<float>(f.S))) + mx;  // utils/utils.py:11
+    if (lane == 0) {
+      f.lme_b[b] = static_cast<float>(lme);
+      f.lme64[b] = lme;
+    }
+    if (lane < f.S) f.g_ll[n] = e * (-1.0f / (sm * f.b_norm));  // d(-mean_b lme_b)/d log_w = -softmax_s / B
+  }
+}
+
+template <int MC, int LPP, int AR>
+__global__ void __launch_bounds__(512, 1) modl_step_kernel(const StepArgs sa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = blockDim.x >> 5;
+  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + (threadIdx.x >> 5);
+  const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
+  tile_body<MC, LPP, false, 1, AR, true>(sa.a, smem_raw);
+  __threadfence();
+  grid.sync();
+  step_finish(sa.f, gw, total_warps, lane);
+  __threadfence();
+  grid.sync();
+  if (sa.f.elbo && gw == total_warps - 1) {  // batch mean, fixed order (the last warp owns the shortest run)
+    double t = 0.0;
+    for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
+    t = warp_sum(t);
+    if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+  }
+  tile_body<MC, LPP, true, 1, AR, true>(sa.a, smem_raw);
 }
 
 static __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
@@ -1599,6 +1696,52 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   return launch_tiled_shape<MC, LPP, BWD, 1, 512, AR>(a, sh.warps, st, plan);
 }
 
+// the fused one-launch step (modl_step_kernel): backward shared-memory footprint, cooperative launch
+template <int MC, int LPP, int AR>
+static int launch_step(ModlArgs a, StepFinish f, long long n_img, cudaStream_t st) {
+  using T = Tile<MC, LPP>;
+  a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
+  const DeviceInfo& di = device_info();
+  const size_t per_warp = (static_cast<size_t>(T::TILE_F) + T::AUX_F) * 4 + 8;
+  int warps = 16;
+  while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
+  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  const size_t smem = warps * per_warp;
+  auto kern = modl_step_kernel<MC, LPP, AR>;
+  static std::mutex mu;
+  static int c_dev = -1;
+  static size_t c_smem = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_dev != dev || smem > c_smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_rc(e);
+      c_dev = dev;
+      c_smem = smem;
+    }
+  }
+  const long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = di.sm_count;  // one CTA per SM: every CTA is resident, as the grid barrier requires
+  if (grid > need) grid = need;
+  if (grid * warps > kMaxGridWarps) grid = kMaxGridWarps / warps;
+  if (grid < 1) grid = 1;
+  const long long total_warps = grid * warps;
+  a.tw_base = a.num_tiles / total_warps;
+  a.tw_rem = a.num_tiles % total_warps;
+  a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  if (static_cast<size_t>(n_img) * a.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+  a.reverse = 1;
+  a.keep_tiles = 0;
+  a.bwd_hint = 0;
+  f.geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, T::PPT, a.HW};
+  StepArgs sa{a, f};
+  void* args[] = {&sa};
+  return cuda_rc(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(static_cast<unsigned>(grid)),
+                                             dim3(static_cast<unsigned>(warps * 32)), args, smem, st));
+}
+
 // pixel-pair kernel, n_mix = M (1 <= M <= 9): one slot per warp, as many warps as shared memory allows (<= 16)
 template <int M, bool BWD, int AR>
 static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
@@ -1979,5 +2122,100 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
   iw.g_ll = g_ll;
   return modl_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
                            ll_image, ll_image_f64, iw, workspace, workspace_bytes, st);
+}
+}  // namespace vaemdl
+
+namespace vaemdl {
+// VAEMDL_FUSED = "0": never, "1": whenever the shape is eligible, unset: eligible shapes with at most kFusedMaxTilesPerWarp
+// tiles per warp (where launch boundaries and pipeline ramps are a visible share of the step)
+constexpr long long kFusedMaxTilesPerWarp = 12;  // measured: 101.6 -> 96.6 us at 4.3 tiles per warp, a loss from ~25 on
+static int fused_mode() {
+  const char* e = getenv("VAEMDL_FUSED");
+  if (!e) return -1;
+  return e[0] == '0' ? 0 : 1;
+}
+static bool fused_eligible(int S, long long n_px, int HW, int M) {
+  const int mode = fused_mode();
+  if (mode == 0 || S > 32) return false;
+  if (use_pixel_pairs(M, n_px)) return false;
+  if (M != 5 && M != 10 && M != 20 && M != 30) return false;
+  const int ppt = tile_ppt(M, n_px);
+  if (HW < ppt) return false;
+  static int coop = -1;
+  if (coop < 0) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    coop = v;
+  }
+  if (!coop) return false;
+  if (mode == 1) return true;
+  const long long tiles = (n_px + ppt - 1) / ppt;
+  return tiles <= kFusedMaxTilesPerWarp * device_info().sm_count * 16;
+}
+
+// One IWAE step of the observation model: forward, per-image sums, log-mean-exp, elbo, softmax weights, parameter gradient.
+// One cooperative launch when the shape is eligible, else forward + finish + backward (3 launches).
+template <int AR>
+static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
+                               long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
+                               float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                               float* dparams, void* workspace, size_t workspace_bytes, cudaStream_t st, int* launches) {
+  if (S <= 0 || B <= 0 || B_total < 0 || !lme_b || !g_ll || !dparams) return VAEMDL_EINVAL;
+  const long long n_img = static_cast<long long>(S) * B;
+  int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
+  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(dparams) & 15u) return VAEMDL_EALIGN;
+  const int HW = H * W;
+  const long long n_px = n_img * HW;
+  if (!fused_eligible(S, n_px, HW, M)) {
+    if (launches) *launches = 3;
+    rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st);
+  }
+  const size_t need = vaemdl_modl_workspace_bytes(n_img, H, W);
+  if (!workspace || workspace_bytes < need) return VAEMDL_EWORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
+  char* ws = static_cast<char*>(workspace);
+  ModlArgs a{};
+  a.params = params;
+  a.x = x;
+  a.partial = reinterpret_cast<double*>(ws);
+  a.g_image = g_ll;
+  a.dparams = dparams;
+  a.HW = HW;
+  a.n_px = n_px;
+  a.x_batch = x_batch;
+  a.x_u8 = x_dtype == VAEMDL_X_U8;
+  a.x_unit = x_range == VAEMDL_RANGE_UNIT;
+  a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
+  a.M = M;
+  a.plain = AR;
+  StepFinish f{};
+  f.extra = extra;
+  f.ll = ll_image;
+  f.ll64 = ll_image_f64;
+  f.log_w = log_w;
+  f.lme_b = lme_b;
+  f.elbo = elbo;
+  f.g_ll = g_ll;
+  f.lme64 = reinterpret_cast<double*>(ws + partial_elems(n_img) * sizeof(double));
+  f.B = B;
+  f.S = S;
+  f.b_norm = static_cast<float>(B_total > 0 ? B_total : B);
+  f.small = n_px < (1ll << 31);
+  if (launches) *launches = 1;
+  switch (M) {
+    case 5:
+      return launch_step<5, 1, AR>(a, f, n_img, st);
+    case 10:
+      return launch_step<10, 1, AR>(a, f, n_img, st);
+    case 20:
+      return launch_step<10, 2, AR>(a, f, n_img, st);
+    default:
+      return launch_step<10, 3, AR>(a, f, n_img, st);
+  }
 }
 }  // namespace vaemdl

@@ -5,6 +5,7 @@ stream; PyTorch only owns the buffers.  CPU tensors are rejected (``_abi.require
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional, Tuple
 
@@ -173,6 +174,47 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
                                          ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
                                          ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
     return ll64, log_w, lme_b, elbo, g_ll
+
+
+def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: int = 0,
+                   x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL, plain: bool = False):
+    """Forward + IWAE finish + parameter gradient in ONE call (``vaemdl_modl_iwae_step``): one cooperative kernel launch
+    for the training shapes of models/model05.py, three launches otherwise.  Arguments as ``modl_iwae_forward``.
+    Returns ``(lpxz float64 [S,B], log_w, lme_b [B], elbo [1], g_ll [S,B], dparams, launches)``."""
+    p = dense_f32(params, "parameters")
+    if p.dim() != 5:
+        raise ValueError("parameters must be [S, B, H, W, 10*n_mix]")
+    S, B, H, W, C10 = p.shape
+    M = C10 // 10
+    if C10 != 10 * M or M < 1:
+        raise ValueError(f"last parameter dim must be 10*n_mix, got {C10}")
+    xd, x_dtype, x_batch = _prep_x(x, (H, W, 3), "x")
+    if x_batch not in (1, B):
+        raise ValueError(f"x must hold {B} images (or one), got {x_batch}")
+    ex = dense_f32(extra, "extra").reshape(S, B) if extra is not None else None
+    L = lib()
+    dev = p.device
+    ll64 = torch.empty((S, B), device=dev, dtype=torch.float64)
+    log_w = torch.empty((S, B), device=dev, dtype=torch.float32)
+    lme_b = torch.empty(B, device=dev, dtype=torch.float32)
+    elbo = torch.empty(1, device=dev, dtype=torch.float32)
+    g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
+    dp = torch.empty_like(p)
+    ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
+    ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
+    n_launch = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        if plain:
+            check(L.vaemdl_modl_plain_iwae_step(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex),
+                                                None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(dp),
+                                                ptr(ws), ws_bytes, stream_ptr(dev), ctypes.byref(n_launch)),
+                  "vaemdl_modl_plain_iwae_step")
+        else:
+            check(L.vaemdl_modl_iwae_step(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W,
+                                          M, ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(dp),
+                                          ptr(ws), ws_bytes, stream_ptr(dev), ctypes.byref(n_launch)),
+                  "vaemdl_modl_iwae_step")
+    return ll64, log_w, lme_b, elbo, g_ll, dp, n_launch.value
 
 
 def modl_log_prob(params: torch.Tensor, x: torch.Tensor, x_range: int = _abi.RANGE_UNIT,

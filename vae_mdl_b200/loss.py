@@ -140,9 +140,9 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
 
 def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None, need_grad: bool = True,
                    b_total: int = 0):
-    """The whole observation-model side of one IWAE step in 3 kernel launches, no autograd graph:
-    MoDL forward (tile partial sums, float64) -> fused finish (per-image sums, log-mean-exp, elbo, softmax weights)
-    -> MoDL gradient.
+    """The whole observation-model side of one IWAE step, no autograd graph: MoDL forward (tile partial sums, float64) ->
+    finish (per-image sums, log-mean-exp, elbo, softmax weights) -> MoDL gradient; ONE cooperative kernel launch for the
+    training shapes of models/model05.py (``vaemdl_modl_iwae_step``), three launches otherwise.
 
     ``params [S,B,H,W,10M]``, ``x [B,H,W,3]`` (uint8 or float in [0,1]), ``extra = beta*(lpz-lqzx) [S,B]`` or None.
     ``b_total``: whole-batch size when ``params`` is one rank's batch shard (the returned loss is then this rank's
@@ -150,8 +150,11 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = 
     Returns ``(loss=-elbo [1], lpxz [S,B] float64, dparams or None)`` -- the numbers ``iwae_loss`` + ``backward`` give.
     """
     with torch.no_grad():
-        lpxz, _, _, elbo, g_ll = F.modl_iwae_forward(params, x, extra, b_total)
-        dparams = F.modl_backward(params, x, g_image=g_ll) if need_grad else None
+        if need_grad:  # one call: a single cooperative launch for training shapes, forward -> finish -> gradient otherwise
+            lpxz, _, _, elbo, _, dparams, _ = F.modl_iwae_step(params, x, extra, b_total)
+        else:
+            lpxz, _, _, elbo, _ = F.modl_iwae_forward(params, x, extra, b_total)
+            dparams = None
     return -elbo, lpxz, dparams
 
 
