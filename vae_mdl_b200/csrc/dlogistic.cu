@@ -109,7 +109,8 @@ __device__ __forceinline__ double dl_warp_sum(double v) {
 // One thread per row of CPT channels (CPT = 3 for images, 1 for anything else); one warp = 32 consecutive rows.
 template <int CPT, bool BWD>
 __global__ void __launch_bounds__(256) dl_kernel(const DlArgs a) {
-  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  // runs numbered CTA-minor: the (one tile longer) first tw_rem runs spread evenly over the SMs
+  const long long gw = static_cast<long long>(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int lane = threadIdx.x & 31;
   if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
   // a run of consecutive 32-row tiles per warp: per-image sums stay in registers until the warp leaves the image
@@ -287,7 +288,8 @@ __device__ __forceinline__ DlOut2 dl_elem2(f2 x, f2 loc, f2 ls, const DlArgs& a)
 // IL: loc/logscale are the two halves of one [.., 6] tensor (ld = 6, logscale = loc + 3) and so are dloc/dls.
 template <bool BWD, bool IL>
 __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
-  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  // runs numbered CTA-minor: the (one tile longer) first tw_rem runs spread evenly over the SMs
+  const long long gw = static_cast<long long>(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int lane = threadIdx.x & 31;
   if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
   const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);

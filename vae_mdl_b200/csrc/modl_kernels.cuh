@@ -63,9 +63,17 @@ struct ModlArgs {
   int x_unit;       // apply x*2-1
   int edge_openai;  // < -0.999 / > 0.999 instead of <= -1 / >= 1
   int M;
+  int spread;  // 1: run r belongs to warp (r / #CTAs) of CTA (r % #CTAs), 0: to warp (r % warps) of CTA (r / warps)
   // run-time tile geometry (modl_rt_kernel: any n_mix without its own instantiation)
   int rt_MC, rt_LPP, rt_PPT, rt_rot, rt_warp_f;
 };
+
+// Which run of consecutive tiles a warp owns.  The first tw_rem runs are one tile longer than the rest; numbering the
+// runs CTA-minor spreads those evenly over the SMs (CTA-major puts all of them on the first tw_rem / warps SMs, which
+// then finish a whole tile after the others: 4.3 tiles per warp = 14 % of the kernel at BASELINE configs[0]).
+__device__ __forceinline__ long long run_index(const ModlArgs& a, int warp, int nwarps) {
+  return a.spread ? static_cast<long long>(warp) * gridDim.x + blockIdx.x : static_cast<long long>(blockIdx.x) * nwarps + warp;
+}
 
 struct Pixel {  // one pixel: both halves of a packed register see the same observation
   float x[3];
@@ -490,7 +498,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
   }
 
-  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const long long gw = run_index(a, warp, nwarps);
   const bool lane_used = (lane / LPP) < PPT;
   const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
   const int sub = lane % LPP;
@@ -912,7 +920,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
   else
     pdl_trigger();
 
-  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const long long gw = run_index(a, warp, nwarps);
   const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
   const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
   const long long t_cnt = t_end - t_begin;
@@ -1258,7 +1266,7 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
   else
     pdl_trigger();
 
-  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + warp;
+  const long long gw = run_index(a, warp, nwarps);
   const int p_raw = lane / LPP;
   const bool lane_used = p_raw < PPT;
   const int p = lane_used ? p_raw : 0;  // idle lanes shadow pixel 0 (they never write)
@@ -1949,9 +1957,15 @@ static bool use_pixel_pairs(int M, long long n_px) {
   return n_px >= 64ll * 148 * 16 * 6;
 }
 
+static int spread_runs() {
+  const char* e = getenv("VAEMDL_SPREAD");  // "0": CTA-major run numbering (A/B)
+  return !(e && e[0] == '0');
+}
+
 template <bool BWD, int AR>
 static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   a.plain = AR;
+  a.spread = spread_runs();
   if (use_pixel_pairs(a.M, a.n_px)) {
     switch (a.M) {
       case 1: return launch_pp<1, BWD, AR>(a, st, plan);
@@ -2193,6 +2207,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
   a.plain = AR;
+  a.spread = spread_runs();
   StepFinish f{};
   f.extra = extra;
   f.ll = ll_image;
