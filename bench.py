@@ -379,6 +379,41 @@ def also_workloads(dev, peak):
             out[name]["cuda_graph_us_per_step"] = tg * 1e6
             out[name]["cuda_graph_frac_of_hbm_peak"] = st.n_px * 120 * M / tg / 1e9 / peak
         del st
+    # bfloat16 parameters / gradient at the headline shape: same launches, half the parameter bytes.
+    # NOT the headline (the reference computes in float32); reported to show what the narrower interface costs / buys.
+    try:
+        _, S, B, H, W, M = WORKLOADS[DEFAULT_WORKLOAD]
+        L = ModlStep(1, 1, 8, 8, M, dev, 1, 1).L
+        gen = torch.Generator(device=dev).manual_seed(11)
+        pool = [torch.randn(S, B, H, W, 10 * M, device=dev, generator=gen).bfloat16() for _ in range(3)]
+        xb = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=gen)
+        dpb = torch.empty_like(pool[0])
+        ll64 = torch.empty(S, B, dtype=torch.float64, device=dev)
+        gl, lme, el = torch.empty(S, B, device=dev), torch.empty(B, device=dev), torch.empty(1, device=dev)
+        wsb = L.vaemdl_modl_workspace_bytes(S * B, H, W)
+        ws = torch.empty(wsb // 8 + 1, dtype=torch.float64, device=dev)
+        sp = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        k = [0]
+
+        def bf16_step():
+            k[0] += 1
+            p = pool[k[0] % 3]
+            rc = L.vaemdl_modl_iwae_fwd_bf16(p.data_ptr(), xb.data_ptr(), 1, 0, 0, S, B, B, B, H, W, M, None, None,
+                                             ll64.data_ptr(), None, lme.data_ptr(), el.data_ptr(), gl.data_ptr(), ws.data_ptr(), wsb, sp)
+            assert rc == 0, rc
+            rc = L.vaemdl_modl_bwd_bf16(p.data_ptr(), xb.data_ptr(), 1, 0, 0, S * B, B, H, W, M, gl.data_ptr(), None,
+                                        dpb.data_ptr(), sp)
+            assert rc == 0, rc
+        t = timeit(bf16_step, 20)
+        n_px = S * B * H * W
+        out[DEFAULT_WORKLOAD + "_bf16_params"] = {
+            "px_samples_per_s": n_px / t, "us_per_step": t * 1e6, "launches_per_step": 3,
+            "algorithmic_GBs": n_px * 60 * M / t / 1e9, "frac_of_hbm_peak": n_px * 60 * M / t / 1e9 / peak,
+            "note": "bf16 parameters in, bf16 gradient out (60*M bytes per px-sample), float32 arithmetic; the tile is "
+                    "widened / narrowed in shared memory, which costs more issue slots than the halved DRAM traffic frees"}
+        del pool, dpb
+    except Exception as e:  # pragma: no cover
+        out[DEFAULT_WORKLOAD + "_bf16_params"] = {"error": repr(e)}
     # config 2: plain discretized logistic fwd + IWAE tail + bwd, S=5 x B=128, 32x32x3 (models/model03.py shapes),
     # raw C-ABI calls on preallocated buffers; the un-split [..,6] conv output is read in place (ld = 6)
     S, B, H, W = 5, 128, 32, 32

@@ -144,6 +144,27 @@ VAEMDL_API int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, 
                     float* dparams, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * bfloat16 parameters (the decoder's last conv often runs in bf16: models/model05.py:76-90 under mixed precision)
+ * Same calls as vaemdl_modl_fwd / _iwae_fwd / _bwd with params (and dparams) as bfloat16 [n_img, H, W, 10*M]:
+ * half the DRAM bytes per px-sample.  The tile is widened to float32 in shared memory; every operation, the per-image
+ * float64 sums and the outputs other than dparams are exactly those of the float32 entry points evaluated on the
+ * widened parameters; dparams is rounded to nearest-even once, at the store.  params / dparams 16-byte aligned.
+ * ------------------------------------------------------------------------ */
+VAEMDL_API int vaemdl_modl_fwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    float* lp_pixel, float* ll_image, double* ll_image_f64,
+                    void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_iwae_fwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                    int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                    const float* extra,
+                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                    void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    const float* g_image, const float* g_pixel,
+                    void* dparams_bf16, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Pixel mixture of discretized logistics WITHOUT conditioning on the observed x
  * replaces: PixelMixtureDiscretizedLogistic.log_prob + get_mixture_params   utils/mdl_plain.py:36-66, :124-168
  * Same parameter row, same outputs and workspace as the entry points above; the only difference is the chain of

@@ -50,6 +50,13 @@ PROTOTYPES = {
                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vaemdl_modl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_modl_fwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_iwae_fwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int,
+                                          c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_plain_fwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_plain_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
@@ -137,3 +144,15 @@ def dense_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.data_ptr() % 16:
         t = t.clone(memory_format=torch.contiguous_format)
     return t
+
+
+def dense_param(t: torch.Tensor, name: str):
+    """MoDL parameter tensor as the kernels read it: ``(tensor, is_bf16)``.  bfloat16 stays bfloat16 (the kernels widen it
+    in shared memory); everything else becomes float32.  Contiguous and 16-byte aligned either way."""
+    require_cuda(t, name)
+    if t.dtype != torch.bfloat16:
+        return dense_f32(t, name), False
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t, True

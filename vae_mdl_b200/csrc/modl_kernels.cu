@@ -47,3 +47,29 @@ extern "C" int vaemdl_modl_iwae_step(const float* params, const void* x, int x_d
                                 ll_image_f64, log_w, lme_b, elbo, g_ll, dparams, workspace, workspace_bytes,
                                 static_cast<cudaStream_t>(stream), launches);
 }
+
+// ---- bfloat16 parameters / gradient; x-conditioned class, all arithmetic in float32 ----------------------------
+extern "C" int vaemdl_modl_fwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                                    long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
+                                    double* ll_image_f64, void* workspace, size_t workspace_bytes, void* stream) {
+  return modl_fwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                          lp_pixel, ll_image, ll_image_f64, IwaeOut{}, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int vaemdl_modl_iwae_fwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                                         int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                                         const float* extra, float* ll_image, double* ll_image_f64, float* log_w,
+                                         float* lme_b, float* elbo, float* g_ll, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
+  return modl_iwae_fwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, S, B, B_total,
+                               x_batch, H, W, M, extra, ll_image, ll_image_f64, log_w, lme_b, elbo, g_ll, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream), 1);
+}
+
+extern "C" int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                                    long long n_img, int x_batch, int H, int W, int M, const float* g_image,
+                                    const float* g_pixel, void* dparams_bf16, void* stream) {
+  return modl_bwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                          g_image, g_pixel, static_cast<float*>(dparams_bf16), static_cast<cudaStream_t>(stream), 1);
+}

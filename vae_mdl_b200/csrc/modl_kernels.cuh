@@ -19,6 +19,7 @@
 // of both per packed register (modl_pp_kernel).  Any other M runs on a plain one-thread-per-pixel kernel (correct,
 // not tuned).  Template parameter AR selects what the green / blue means are chained on (pair_eval).
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include <cmath>
 #include <cstdio>
@@ -63,6 +64,7 @@ struct ModlArgs {
   int x_unit;       // apply x*2-1
   int edge_openai;  // < -0.999 / > 0.999 instead of <= -1 / >= 1
   int M;
+  int bf16;    // parameters (and the gradient) are bfloat16 in global memory; all arithmetic stays float32
   int spread;  // 1: run r belongs to warp (r / #CTAs) of CTA (r % #CTAs), 0: to warp (r % warps) of CTA (r / warps)
   // run-time tile geometry (modl_rt_kernel: any n_mix without its own instantiation)
   int rt_MC, rt_LPP, rt_PPT, rt_rot, rt_warp_f;
@@ -73,6 +75,64 @@ struct ModlArgs {
 // then finish a whole tile after the others: 4.3 tiles per warp = 14 % of the kernel at BASELINE configs[0]).
 __device__ __forceinline__ long long run_index(const ModlArgs& a, int warp, int nwarps) {
   return a.spread ? static_cast<long long>(warp) * gridDim.x + blockIdx.x : static_cast<long long>(blockIdx.x) * nwarps + warp;
+}
+
+// ---- bfloat16 parameters (the decoder's conv output arrives in bf16) ------------------------------------------
+// The tile travels as bf16 (half the DRAM bytes) and is widened to float32 IN PLACE in the warp's slot before the compute
+// loop, so nothing downstream changes: the bulk copy lands n bf16 values at byte offset 2n of the slot (= its upper half
+// for a full tile); element i is read at 2n + 2i and written at 4i, front to back, a chunk of 256 elements per step
+// (reads of a step happen before its writes; a step's writes end where the next step's reads begin, at the latest).
+// The backward kernel narrows the float32 gradient tile the same way (round to nearest even) and stores n * 2 bytes.
+__device__ __forceinline__ float bf16_bits_to_f32(unsigned short b) { return __uint_as_float(static_cast<unsigned>(b) << 16); }
+__device__ __forceinline__ unsigned short f32_to_bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+__device__ __forceinline__ void widen_bf16_inplace(float* slot, int n, int lane) {  // n % 8 == 0
+  const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(slot) + 2 * n);  // 4 bf16 per uint2
+  float4* dst = reinterpret_cast<float4*>(slot);
+  const int nq = n >> 2;
+  for (int base = 0; base < nq; base += 64) {
+    const int i0 = base + lane, i1 = base + 32 + lane;
+    uint2 v0 = make_uint2(0u, 0u), v1 = make_uint2(0u, 0u);
+    if (i0 < nq) v0 = src[i0];
+    if (i1 < nq) v1 = src[i1];
+    __syncwarp();
+    if (i0 < nq)
+      dst[i0] = make_float4(__uint_as_float(v0.x << 16), __uint_as_float(v0.x & 0xffff0000u), __uint_as_float(v0.y << 16),
+                            __uint_as_float(v0.y & 0xffff0000u));
+    if (i1 < nq)
+      dst[i1] = make_float4(__uint_as_float(v1.x << 16), __uint_as_float(v1.x & 0xffff0000u), __uint_as_float(v1.y << 16),
+                            __uint_as_float(v1.y & 0xffff0000u));
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void narrow_bf16_inplace(float* slot, int n, int lane) {  // n % 8 == 0
+  const float4* src = reinterpret_cast<const float4*>(slot);
+  uint2* dst = reinterpret_cast<uint2*>(slot);
+  const int nq = n >> 2;
+  for (int base = 0; base < nq; base += 64) {
+    const int i0 = base + lane, i1 = base + 32 + lane;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (i0 < nq) v0 = src[i0];
+    if (i1 < nq) v1 = src[i1];
+    __syncwarp();
+    if (i0 < nq) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v0.x, v0.y), b = __floats2bfloat162_rn(v0.z, v0.w);
+      dst[i0] = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+    }
+    if (i1 < nq) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(v1.x, v1.y), b = __floats2bfloat162_rn(v1.z, v1.w);
+      dst[i1] = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+    }
+    __syncwarp();
+  }
+}
+// parameter `idx` of a row in GLOBAL memory (the rare log-domain fallback reads the row where it lies)
+__device__ __forceinline__ float ld_param(const float* row, int idx, bool bf16) {
+  return bf16 ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(row)[idx]) : row[idx];
+}
+// row `i` of the parameter tensor in global memory
+__device__ __forceinline__ const float* param_row(const ModlArgs& a, long long i, int rowf) {
+  return a.bf16 ? reinterpret_cast<const float*>(reinterpret_cast<const unsigned short*>(a.params) + i * rowf)
+                : a.params + i * rowf;
 }
 
 struct Pixel {  // one pixel: both halves of a packed register see the same observation
@@ -115,38 +175,39 @@ __device__ __forceinline__ void load_pixel(const ModlArgs& a, long long n, int p
 }
 
 // ---- rare fallback: one mixture's  logit + sum_c log f_c  in the log domain, straight from global memory -------
-static __device__ __noinline__ float modl_logt(const float* __restrict__ row, int M, int m, const Pixel& px, bool plain) {
-  const float k0 = tanhf(row[M + 2 * M + m]);
-  const float k1 = tanhf(row[M + 3 * M + 2 * M + m]);
-  const float k2 = tanhf(row[M + 6 * M + 2 * M + m]);
-  float t = row[m];
+static __device__ __noinline__ float modl_logt(const float* __restrict__ row, int M, int m, const Pixel& px, bool plain,
+                                               bool bf16 = false) {
+  const float k0 = tanhf(ld_param(row, M + 2 * M + m, bf16));
+  const float k1 = tanhf(ld_param(row, M + 3 * M + 2 * M + m, bf16));
+  const float k2 = tanhf(ld_param(row, M + 6 * M + 2 * M + m, bf16));
+  float t = ld_param(row, m, bf16);
   float a0 = px.x[0], a1 = px.x[1];  // what the green / blue means are chained on
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float loc = row[M + c * 3 * M + m];
+    float loc = ld_param(row, M + c * 3 * M + m, bf16);
     if (c == 1) loc = loc + k0 * a0;
     if (c == 2) loc = loc + k1 * a0 + k2 * a1;
     if (plain) {  // utils/mdl_plain.py:160-162
       if (c == 0) a0 = loc;
       if (c == 1) a1 = loc;
     }
-    const float ls = fmaxf(row[M + c * 3 * M + M + m], -7.0f);
+    const float ls = fmaxf(ld_param(row, M + c * 3 * M + M + m, bf16), -7.0f);
     t += subpix_logf(px.x[c], px.left[c], px.right[c], loc, ls, kDx, kWidth);
   }
   return t;
 }
 // log sum_m exp(logit_m + sum_c log f)  and  log sum_m exp(logit_m)
 static __device__ __noinline__ void modl_pixel_logdomain(const float* __restrict__ row, int M, const Pixel& px, bool plain,
-                                                  float& lse_t, float& lse_l) {
+                                                  float& lse_t, float& lse_l, bool bf16 = false) {
   float mt = -INFINITY, ml = -INFINITY;
   for (int m = 0; m < M; ++m) {
-    mt = fmaxf(mt, modl_logt(row, M, m, px, plain));
-    ml = fmaxf(ml, row[m]);
+    mt = fmaxf(mt, modl_logt(row, M, m, px, plain, bf16));
+    ml = fmaxf(ml, ld_param(row, m, bf16));
   }
   float st = 0.f, sl = 0.f;
   for (int m = 0; m < M; ++m) {
-    st += expf(modl_logt(row, M, m, px, plain) - mt);
-    sl += expf(row[m] - ml);
+    st += expf(modl_logt(row, M, m, px, plain, bf16) - mt);
+    sl += expf(ld_param(row, m, bf16) - ml);
   }
   lse_t = mt + logf(st);
   lse_l = ml + logf(sl);
@@ -470,13 +531,15 @@ __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r,
 // FUSED: the forward and the backward pass of one step run inside ONE cooperative kernel (modl_step_kernel): both use
 // the backward shared-memory layout, the mbarrier is initialised once and its phase carries over, the forward pass
 // leaves its last tile in the slot and the (reversed) backward pass starts on it without loading anything.
-template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED>
+// PD = 1: bfloat16 parameters / gradient in global memory (widened / narrowed in place in the slot, see widen_bf16_inplace)
+template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED, int PD = 0>
 __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem_raw) {
   using T = Tile<MC, LPP>;
   constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F, NPAIR = T::NPAIR;
   constexpr bool AL = T::ALIGNED;
   constexpr int WARP_F = NSLOT * TILE_F + ((BWD || FUSED) ? T::AUX_F : 0);
   static_assert(!FUSED || NSLOT == 1, "the fused step keeps one slot per warp");
+  static_assert(PD == 0 || (NSLOT == 1 && !FUSED), "bf16 parameters: one slot per warp, three-launch step");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
   float* aux = slots + NSLOT * TILE_F;
@@ -521,9 +584,10 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
   auto issue = [&](long long t, int s) {
     const int rows = tile_rows(t);
-    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
-    const float* src = a.params + t * TILE_F;
-    float* dst = slots + s * TILE_F;
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+    const char* src = reinterpret_cast<const char*>(a.params) + t * TILE_F * (PD ? 2 : 4);
+    float* slot_f = slots + s * TILE_F;
+    char* dst = reinterpret_cast<char*>(slot_f) + (PD ? bytes : 0u);  // bf16 lands behind the room its float32 image needs
     if ((bytes & 15u) == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&bars[s], bytes);
@@ -540,7 +604,8 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
       }
     } else {
-      for (int i = lane; i < rows * ROWF; i += 32) dst[i] = src[i];
+      for (int i = lane; i < rows * ROWF; i += 32)
+        slot_f[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
     }
@@ -625,6 +690,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     float* rowp = slot + pp * ROWF;
     float* auxp = aux + pp * M;
     if (!(FUSED && BWD && it == 0)) mbar_wait(&bars[s], parity);
+    if constexpr (PD != 0) {
+      if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);  // (a ragged tile was widened by its loads)
+    }
     if constexpr (BWD && NSLOT > 1) {
       // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
       // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
@@ -684,9 +752,10 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const float S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
     const float SW = group_sum<LPP>(lo(sumW2) + hi(sumW2), lane);
     const bool tiny = !(S > kTinySum);  // also catches NaN
-    const float* grow = a.params + i * ROWF;
+    const float* grow = param_row(a, i, ROWF);
 
     if constexpr (!BWD) {
+      if constexpr (PD != 0) fence_async_smem();  // the widening wrote the slot through the generic proxy
       __syncwarp();
       {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
         if (it + NSLOT < t_cnt) issue(t + NSLOT * t_dir, s);
@@ -694,7 +763,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
       if (tiny) {
         float lt, ll;
-        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
         lp = lt - ll;
       }
       const bool owner = active && sub == 0;
@@ -720,7 +789,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     } else {
       const float rS = rcpa(S), rSW = rcpa(SW);
       float lt = 0.f, ll = 0.f;
-      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
 #pragma unroll 1
       for (int pr = 0; pr < NPAIR; ++pr) {
         const int m = m0 + 2 * pr;
@@ -731,8 +800,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         f2 r = wp * rS;     // posterior responsibility of the component
         f2 pi = W * rSW;    // softmax(logits)
         if (tiny) {
-          r = pk(expf(modl_logt(grow, M, m, px, a.plain != 0) - lt), single ? 0.0f : expf(modl_logt(grow, M, m + 1, px, a.plain != 0) - lt));
-          pi = pk(expf(grow[m] - ll), single ? 0.0f : expf(grow[m + 1] - ll));
+          r = pk(expf(modl_logt(grow, M, m, px, a.plain != 0, PD != 0) - lt),
+                 single ? 0.0f : expf(modl_logt(grow, M, m + 1, px, a.plain != 0, PD != 0) - lt));
+          pi = pk(expf(ld_param(grow, m, PD != 0) - ll), single ? 0.0f : expf(ld_param(grow, m + 1, PD != 0) - ll));
         }
         const f2 gr = r * g;
         if (active) {
@@ -742,9 +812,13 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
       }
       // hand the gradient tile to the TMA engine
-      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
-      float* dst = a.dparams + t * TILE_F;
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+      char* dst = reinterpret_cast<char*>(a.dparams) + t * TILE_F * (PD ? 2 : 4);
       if ((bytes & 15u) == 0) {
+        if constexpr (PD != 0) {
+          __syncwarp();
+          narrow_bf16_inplace(slot, rows * ROWF, lane);
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -756,7 +830,12 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
       } else {
         __syncwarp();
-        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = slot[q];
+        for (int q = lane; q < rows * ROWF; q += 32) {
+          if (PD)
+            reinterpret_cast<unsigned short*>(dst)[q] = f32_to_bf16_bits(slot[q]);
+          else
+            reinterpret_cast<float*>(dst)[q] = slot[q];
+        }
         __syncwarp();
       }
       if constexpr (NSLOT == 1) {
@@ -782,10 +861,10 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   }
 }
 
-template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR>
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0>
 __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  tile_body<MC, LPP, BWD, NSLOT, AR, false>(a, smem_raw);
+  tile_body<MC, LPP, BWD, NSLOT, AR, false, PD>(a, smem_raw);
 }
 
 // ---- one step in one launch: forward -> grid barrier -> per-image sums, log-mean-exp, softmax weights -> grid barrier ->
@@ -1245,7 +1324,7 @@ __device__ __forceinline__ float group_max_rt(float v, int base, int LPP) {
 }
 
 // AL: n_mix and MC even -> every component pair sits on an 8-byte boundary and is moved with 64-bit shared accesses
-template <bool BWD, int AR, bool AL>
+template <bool BWD, int AR, bool AL, int PD = 0>
 __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
   const int M = a.M, MC = a.rt_MC, LPP = a.rt_LPP, PPT = a.rt_PPT;
   const int ROWF = 10 * M, TILE_F = PPT * ROWF, NPAIR = (MC + 1) >> 1;
@@ -1291,25 +1370,27 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
   };
   auto issue = [&](long long t) {
     const int rows = tile_rows(t);
-    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
-    const float* src = a.params + t * TILE_F;
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+    const char* src = reinterpret_cast<const char*>(a.params) + t * TILE_F * (PD ? 2 : 4);
+    char* land = reinterpret_cast<char*>(slot) + (PD ? bytes : 0u);  // bf16 lands behind the room its float32 image needs
     if ((bytes & 15u) == 0) {
       if (lane == 0) {
         mbar_arrive_expect_tx(bar, bytes);
         if (BWD) {
           if (a.bwd_hint & 1)
-            bulk_g2s_hint(slot, src, bytes, bar, pol_first);
+            bulk_g2s_hint(land, src, bytes, bar, pol_first);
           else
-            bulk_g2s(slot, src, bytes, bar);
+            bulk_g2s(land, src, bytes, bar);
         } else {
           if (a.keep_tiles > 0)
-            bulk_g2s_hint(slot, src, bytes, bar, (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
+            bulk_g2s_hint(land, src, bytes, bar, (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
           else
-            bulk_g2s(slot, src, bytes, bar);
+            bulk_g2s(land, src, bytes, bar);
         }
       }
     } else {
-      for (int i = lane; i < rows * ROWF; i += 32) slot[i] = src[i];
+      for (int i = lane; i < rows * ROWF; i += 32)
+        slot[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(bar, 0);
     }
@@ -1376,6 +1457,9 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
     float* rowp = slot + pp * ROWF;
     float* auxp = aux + pp * M;
     mbar_wait(bar, parity);
+    if constexpr (PD != 0) {
+      if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);
+    }
 
     float lmax = -INFINITY;
     for (int m = m0; m < m_end; ++m) lmax = fmaxf(lmax, rowp[m]);
@@ -1422,15 +1506,16 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
     const float S = group_sum_rt(lo(sumWP2) + hi(sumWP2), gbase, LPP);
     const float SW = group_sum_rt(lo(sumW2) + hi(sumW2), gbase, LPP);
     const bool tiny = !(S > kTinySum);  // also catches NaN
-    const float* grow = a.params + i * ROWF;
+    const float* grow = param_row(a, i, ROWF);
 
     if constexpr (!BWD) {
+      if constexpr (PD != 0) fence_async_smem();
       __syncwarp();
       if (it + 1 < t_cnt) issue(t + t_dir);  // every lane has read its row: re-arm the slot with the warp's next tile
       float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;
       if (tiny) {
         float lt, ll;
-        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
         lp = lt - ll;
       }
       const bool owner = active && sub == 0;
@@ -1454,7 +1539,7 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
     } else {
       const float rS = rcpa(S), rSW = rcpa(SW);
       float lt = 0.f, ll = 0.f;
-      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll);
+      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
 #pragma unroll 1
       for (int pr = 0; pr < NPAIR; ++pr) {
         const int prr = pr + rot >= NPAIR ? pr + rot - NPAIR : pr + rot;
@@ -1467,8 +1552,8 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
         f2 r = wp * rS;     // posterior responsibility of the component
         f2 pi = W * rSW;    // softmax(logits)
         if (tiny) {
-          r = pk(expf(modl_logt(grow, M, ml, px, a.plain != 0) - lt), expf(modl_logt(grow, M, mh, px, a.plain != 0) - lt));
-          pi = pk(expf(grow[ml] - ll), expf(grow[mh] - ll));
+          r = pk(expf(modl_logt(grow, M, ml, px, a.plain != 0, PD != 0) - lt), expf(modl_logt(grow, M, mh, px, a.plain != 0, PD != 0) - lt));
+          pi = pk(expf(ld_param(grow, ml, PD != 0) - ll), expf(ld_param(grow, mh, PD != 0) - ll));
         }
         const f2 gr = r * g;
         const f2 dl = (r - pi) * g;
@@ -1478,9 +1563,13 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
           for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + ml, !vhi, ld_pair<AL>(rowp, j * M + ml, !vhi) * gr);
         }
       }
-      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * 4u;
-      float* dst = a.dparams + t * TILE_F;
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+      char* dst = reinterpret_cast<char*>(a.dparams) + t * TILE_F * (PD ? 2 : 4);
       if ((bytes & 15u) == 0) {
+        if constexpr (PD != 0) {
+          __syncwarp();
+          narrow_bf16_inplace(slot, rows * ROWF, lane);
+        }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -1492,7 +1581,12 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
         }
       } else {
         __syncwarp();
-        for (int q = lane; q < rows * ROWF; q += 32) dst[q] = slot[q];
+        for (int q = lane; q < rows * ROWF; q += 32) {
+          if (PD)
+            reinterpret_cast<unsigned short*>(dst)[q] = f32_to_bf16_bits(slot[q]);
+          else
+            reinterpret_cast<float*>(dst)[q] = slot[q];
+        }
         __syncwarp();
       }
       if (it + 1 < t_cnt) {
@@ -1641,7 +1735,7 @@ struct TilePlan {  // how the forward grid split the tile range: what the per-im
   int K = 0, PPT = 0;
 };
 
-template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR>
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0>
 static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* plan) {
   using T = Tile<MC, LPP>;
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
@@ -1652,7 +1746,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   warps = pick_warps(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
-  auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT, AR>;
+  auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT, AR, PD>;
   // the function attribute and the occupancy query cost several microseconds of host time: once per (device, shape)
   static std::mutex mu;
   static int c_dev = -1, c_warps = -1, c_ctas = 1;
@@ -1682,7 +1776,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
-  apply_l2_opt(a, total_warps, T::TILE_B);
+  apply_l2_opt(a, total_warps, T::TILE_B / (PD ? 2 : 1));
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -1697,6 +1791,12 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
 
 template <int MC, int LPP, bool BWD, int AR>
 static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
+  if (a.bf16) {  // bfloat16 parameters: x-conditioned class only, one slot per warp
+    if constexpr (AR == 0)
+      return launch_tiled_shape<MC, LPP, BWD, 1, 512, 0, 1>(a, tune_shape(BWD, Shape{1, 16}).warps, st, plan);
+    else
+      return VAEMDL_EUNSUPPORTED;
+  }
   // 1 slot x 16 warps: measured best on B200 for every M (profiles/r01_tune_shapes.txt); latency is hidden by the 4
   // warps per scheduler rather than by a second slot per warp
   const Shape sh = tune_shape(BWD, Shape{1, 16});
@@ -1814,14 +1914,15 @@ struct RtPlan {
 // measured on B200 (tools/rt_sweep.py), long component chunks per lane win over many lanes per pixel (the per-tile work of
 // a lane -- logit max, group reductions, log, index bookkeeping -- is amortised over MC components), as long as 16 warps
 // still fit in shared memory.  Evaluated once per (n_mix, direction) and cached.
-static RtPlan rt_plan_compute(int M, bool bwd) {
+static RtPlan rt_plan_compute(int M, bool bwd, bool bf16) {
   RtPlan best;
   double best_score = -1.0;
   for (int LPP = 1; LPP <= 16; ++LPP) {
     const int MC = (M + LPP - 1) / LPP;
     if (MC > 13) continue;
     int PPT = 32 / LPP;
-    if ((PPT * M) & 1) --PPT;  // tile bytes = PPT * 40 * M must be a multiple of 16
+    // tile bytes = PPT * 40 * M (float32) or PPT * 20 * M (bfloat16) must be a multiple of 16
+    while (PPT >= 1 && ((PPT * M) & (bf16 ? 3 : 1))) --PPT;
     if (PPT < 1) continue;
     const int NP = (MC + 1) / 2;
     const double eff = static_cast<double>(M) / (2.0 * NP * LPP) * (static_cast<double>(PPT) * LPP / 32.0);
@@ -1864,35 +1965,41 @@ static RtPlan rt_plan_compute(int M, bool bwd) {
   }
   return best;
 }
-static RtPlan rt_plan(int M, bool bwd) {
+static RtPlan rt_plan(int M, bool bwd, bool bf16 = false) {
   const char* env = getenv("VAEMDL_RT");  // "LPP:rot" overrides the choice (tuning sweeps; re-read on every call)
   int l = 0, r = 0;
   if (env && sscanf(env, "%d:%d", &l, &r) == 2 && l >= 1 && l <= 32 && (M + l - 1) / l <= 16) {
     int ppt = 32 / l;
-    if ((ppt * M) & 1) --ppt;
+    while (ppt >= 1 && ((ppt * M) & (bf16 ? 3 : 1))) --ppt;
     if (ppt >= 1) return RtPlan{(M + l - 1) / l, l, ppt, r};
   }
   static std::mutex mu;
-  static RtPlan cache[2][VAEMDL_MAX_MIX + 1];
+  static RtPlan cache[4][VAEMDL_MAX_MIX + 1];
   std::lock_guard<std::mutex> lock(mu);
-  RtPlan& c = cache[bwd ? 1 : 0][M];
-  if (c.LPP == 0) c = rt_plan_compute(M, bwd);
+  RtPlan& c = cache[(bwd ? 1 : 0) + (bf16 ? 2 : 0)][M];
+  if (c.LPP == 0) c = rt_plan_compute(M, bwd, bf16);
   return c;
 }
 
-template <bool BWD, int AR, bool AL>
+template <bool BWD, int AR, bool AL, int PD>
 static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan* plan);
 
 template <bool BWD, int AR>
 static int launch_rt(ModlArgs a, cudaStream_t st, TilePlan* plan) {
-  const RtPlan rp = rt_plan(a.M, BWD);
+  const RtPlan rp = rt_plan(a.M, BWD, a.bf16 != 0);
   if (rp.LPP == 0) return VAEMDL_EUNSUPPORTED;
   static const bool no_al = getenv("VAEMDL_RT_NOAL") != nullptr;  // A/B: scalar shared accesses everywhere
   const bool al = (a.M % 2 == 0) && (rp.MC % 2 == 0 || rp.LPP == 1) && !no_al;
-  return al ? launch_rt_al<BWD, AR, true>(a, rp, st, plan) : launch_rt_al<BWD, AR, false>(a, rp, st, plan);
+  if (a.bf16) {
+    if constexpr (AR == 0)
+      return al ? launch_rt_al<BWD, 0, true, 1>(a, rp, st, plan) : launch_rt_al<BWD, 0, false, 1>(a, rp, st, plan);
+    else
+      return VAEMDL_EUNSUPPORTED;
+  }
+  return al ? launch_rt_al<BWD, AR, true, 0>(a, rp, st, plan) : launch_rt_al<BWD, AR, false, 0>(a, rp, st, plan);
 }
 
-template <bool BWD, int AR, bool AL>
+template <bool BWD, int AR, bool AL, int PD>
 static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan* plan) {
   a.rt_MC = rp.MC;
   a.rt_LPP = rp.LPP;
@@ -1908,7 +2015,7 @@ static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan*
   if (warps * per_warp > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
   warps = pick_warps(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
-  auto kern = modl_rt_kernel<BWD, AR, AL>;
+  auto kern = modl_rt_kernel<BWD, AR, AL, PD>;
   static std::mutex mu;
   static int c_dev = -1;
   static size_t c_smem = 0;
@@ -1933,7 +2040,7 @@ static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan*
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, rp.PPT, a.tw_base);
   a.small = a.n_px < (1ll << 31) - 64;
-  apply_l2_opt(a, total_warps, static_cast<long long>(tile_f) * 4);
+  apply_l2_opt(a, total_warps, static_cast<long long>(tile_f) * (PD ? 2 : 4));
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -1949,9 +2056,9 @@ static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan*
 // n_mix 1..9 run on the pixel-pair kernel.  n_mix = 5 also has a component-pair instantiation with 32-row tiles, which
 // is a little faster while the problem is so small that a warp only sees a handful of tiles (measured: 112 vs 117 us
 // per step at 5 x 128 x 32 x 32, 345 vs 314 us backward at 16 x 64 x 64 x 64).
-static bool use_pixel_pairs(int M, long long n_px) {
+static bool use_pixel_pairs(int M, long long n_px, bool bf16 = false) {
   const char* env = getenv("VAEMDL_PP");  // "0" / "1" force the choice for n_mix = 5 (A/B measurements, tests)
-  if (M < 1 || M > 9) return false;
+  if (M < 1 || M > 9 || bf16) return false;  // (bfloat16 parameters: tile<5,1> for n_mix = 5, the run-time kernel otherwise)
   if (M != 5) return true;
   if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
   return n_px >= 64ll * 148 * 16 * 6;
@@ -1966,7 +2073,7 @@ template <bool BWD, int AR>
 static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   a.plain = AR;
   a.spread = spread_runs();
-  if (use_pixel_pairs(a.M, a.n_px)) {
+  if (use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
     switch (a.M) {
       case 1: return launch_pp<1, BWD, AR>(a, st, plan);
       case 2: return launch_pp<2, BWD, AR>(a, st, plan);
@@ -1991,6 +2098,7 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
     default: {
       static const bool force_generic = getenv("VAEMDL_GENERIC") != nullptr;  // A/B against the one-thread-per-pixel kernel
       if (!force_generic) return launch_rt<BWD, AR>(a, st, plan);
+      if (a.bf16) return VAEMDL_EUNSUPPORTED;
       const DeviceInfo& di = device_info();
       long long blocks = (a.n_px + 127) / 128;
       const long long cap = static_cast<long long>(di.sm_count) * 8;
@@ -2001,8 +2109,8 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   }
 }
 
-static int tile_ppt(int M, long long n_px) {
-  if (use_pixel_pairs(M, n_px)) return 64;
+static int tile_ppt(int M, long long n_px, bool bf16 = false) {
+  if (use_pixel_pairs(M, n_px, bf16)) return 64;
   switch (M) {
     case 5:
     case 10:
@@ -2013,7 +2121,7 @@ static int tile_ppt(int M, long long n_px) {
       return 10;
     default:
       if (getenv("VAEMDL_GENERIC")) return 0;  // one-thread-per-pixel kernel: atomics
-      return rt_plan(M, false).PPT;
+      return rt_plan(M, false, bf16).PPT;
   }
 }
 
@@ -2037,7 +2145,7 @@ namespace vaemdl {
 template <int AR>
 static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image, double* ll_image_f64,
-                         const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                         const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   const bool iwae = iw.S > 0;
@@ -2055,7 +2163,8 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.x_unit = x_range == VAEMDL_RANGE_UNIT;
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
-  const int ppt = tile_ppt(M, a.n_px);
+  a.bf16 = bf16;
+  const int ppt = tile_ppt(M, a.n_px, bf16 != 0);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
   char* ws = static_cast<char*>(workspace);
   size_t tail_off = 0;
@@ -2097,7 +2206,7 @@ namespace vaemdl {
 template <int AR>
 static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, const float* g_image, const float* g_pixel, float* dparams,
-                         cudaStream_t st) {
+                         cudaStream_t st, int bf16 = 0) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   if (!dparams || (!g_image && !g_pixel)) return VAEMDL_EINVAL;
@@ -2115,6 +2224,7 @@ static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.x_unit = x_range == VAEMDL_RANGE_UNIT;
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
+  a.bf16 = bf16;
   return launch_modl<true, AR>(a, st);
 }
 
@@ -2122,7 +2232,7 @@ template <int AR>
 static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
                               long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
                               float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0) {
   if (S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
   if (elbo && !lme_b) return VAEMDL_EINVAL;
   IwaeOut iw;
@@ -2135,7 +2245,7 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
   iw.elbo = elbo;
   iw.g_ll = g_ll;
   return modl_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
-                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st);
+                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16);
 }
 }  // namespace vaemdl
 

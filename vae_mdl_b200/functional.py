@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _abi
-from ._abi import check, dense_f32, lib, ptr, stream_ptr
+from ._abi import check, dense_f32, dense_param, lib, ptr, stream_ptr
 
 __all__ = [
     "modl_log_prob",
@@ -62,7 +62,9 @@ class _ModlFn(torch.autograd.Function):
     def forward(ctx, params, x, x_range, edge_mode, mode, plain=False):
         # mode: "pixel" -> [..., H, W] ; "image" -> [...] float32 ; "image64" -> [...] float64
         # plain: utils/mdl_plain.py (means chained on the means) instead of utils/mdl.py (chained on the observed x)
-        p = dense_f32(params, "parameters")
+        p, bf16 = dense_param(params, "parameters")
+        if bf16 and plain:
+            raise ValueError("bfloat16 parameters are implemented for the x-conditioned mixture classes only")
         H, W, C10 = p.shape[-3], p.shape[-2], p.shape[-1]
         M = C10 // 10
         if C10 != 10 * M or M < 1:
@@ -90,17 +92,17 @@ class _ModlFn(torch.autograd.Function):
                 check(L.vaemdl_modl_plain_fwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(lp), ptr(ll), ptr(ll64),
                                               ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_plain_fwd")
             else:
-                check(L.vaemdl_modl_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
-                                        ptr(lp), ptr(ll), ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)),
-                      "vaemdl_modl_fwd")
+                fn = L.vaemdl_modl_fwd_bf16 if bf16 else L.vaemdl_modl_fwd
+                check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                         ptr(lp), ptr(ll), ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_fwd")
         ctx.save_for_backward(p, xd)
-        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain)
+        ctx.meta = (x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain, bf16)
         return lp if mode == "pixel" else (ll64 if mode == "image64" else ll)
 
     @staticmethod
     def backward(ctx, g):
         p, xd = ctx.saved_tensors
-        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain = ctx.meta
+        x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, mode, plain, bf16 = ctx.meta
         if g is None:
             return None, None, None, None, None, None
         g = dense_f32(g, "upstream gradient")
@@ -111,16 +113,20 @@ class _ModlFn(torch.autograd.Function):
                 check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(g_image),
                                                   ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
             else:
-                check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
-                                            ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+                fn = lib().vaemdl_modl_bwd_bf16 if bf16 else lib().vaemdl_modl_bwd  # dp has the dtype of p
+                check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                         ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
         return dp, None, None, None, None, None
 
 
 def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch.Tensor] = None,
                   g_pixel: Optional[torch.Tensor] = None, x_range: int = _abi.RANGE_UNIT,
                   edge_mode: int = _abi.EDGE_MDL, plain: bool = False) -> torch.Tensor:
-    """The gradient kernel on its own: d/dparams of sum(g_image * ll_image) + sum(g_pixel * lp_pixel)."""
-    p = dense_f32(params, "parameters")
+    """The gradient kernel on its own: d/dparams of sum(g_image * ll_image) + sum(g_pixel * lp_pixel).
+    bfloat16 parameters give a bfloat16 gradient (float32 arithmetic, one rounding at the store)."""
+    p, bf16 = dense_param(params, "parameters")
+    if bf16 and plain:
+        raise ValueError("bfloat16 parameters are implemented for the x-conditioned mixture classes only")
     H, W, C10 = p.shape[-3:]
     lead = tuple(p.shape[:-3])
     n_img = int(math.prod(lead)) if lead else 1
@@ -134,8 +140,9 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
             check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, ptr(gi), ptr(gp),
                                               ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
         else:
-            check(lib().vaemdl_modl_bwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
-                                        ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
+            fn = lib().vaemdl_modl_bwd_bf16 if bf16 else lib().vaemdl_modl_bwd
+            check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
+                     ptr(gi), ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd")
     return dp
 
 
@@ -144,7 +151,9 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
     """MoDL forward fused with the IWAE tail in TWO launches (``vaemdl_modl_iwae_fwd``): ``params [S,B,H,W,10M]``,
     ``x [B,H,W,3]``, ``extra = beta*(lpz-lqzx) [S,B]`` or None.  Returns ``(lpxz float64 [S,B], log_w, lme_b [B],
     elbo [1], g_ll [S,B])`` with ``g_ll = d(-elbo)/d lpxz`` (models/loss.py:32-37).  Not recorded by autograd."""
-    p = dense_f32(params, "parameters")
+    p, bf16 = dense_param(params, "parameters")
+    if bf16 and plain:
+        raise ValueError("bfloat16 parameters are implemented for the x-conditioned mixture classes only")
     if p.dim() != 5:
         raise ValueError("parameters must be [S, B, H, W, 10*n_mix]")
     S, B, H, W, C10 = p.shape
@@ -170,9 +179,10 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
                                                ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
                                                stream_ptr(dev)), "vaemdl_modl_plain_iwae_fwd")
         else:
-            check(L.vaemdl_modl_iwae_fwd(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
-                                         ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
-                                         ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
+            fn = L.vaemdl_modl_iwae_fwd_bf16 if bf16 else L.vaemdl_modl_iwae_fwd
+            check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
+                     ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
+                     ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
     return ll64, log_w, lme_b, elbo, g_ll
 
 
@@ -181,6 +191,9 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     """Forward + IWAE finish + parameter gradient in ONE call (``vaemdl_modl_iwae_step``): one cooperative kernel launch
     for the training shapes of models/model05.py, three launches otherwise.  Arguments as ``modl_iwae_forward``.
     Returns ``(lpxz float64 [S,B], log_w, lme_b [B], elbo [1], g_ll [S,B], dparams, launches)``."""
+    if params.dtype == torch.bfloat16:  # bfloat16 parameters: forward + finish, then the gradient kernel (3 launches)
+        ll64, log_w, lme_b, elbo, g_ll = modl_iwae_forward(params, x, extra, b_total, x_range, edge_mode, plain)
+        return ll64, log_w, lme_b, elbo, g_ll, modl_backward(params, x, g_image=g_ll, x_range=x_range, edge_mode=edge_mode), 3
     p = dense_f32(params, "parameters")
     if p.dim() != 5:
         raise ValueError("parameters must be [S, B, H, W, 10*n_mix]")
