@@ -136,3 +136,74 @@ def test_config3_sampler_full_size(V):
     assert int((idx[pick].cpu().long() != idx64).sum()) == 0
     assert int((xq[pick].cpu() != O.quantise(x64 * 0.5 + 0.5)).sum()) == 0
     assert (x[pick].cpu().double() - x64).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("M,B", [(16, 20), (12, 27), (40, 8)])
+def test_runtime_tiled_kernel_full_size_properties(F, M, B):
+    """An n_mix without its own instantiation (modl_rt_kernel) at the config-5 image size: per-pixel / per-image
+    consistency, reproducibility, linearity, zero-sum logit gradients, oracle spot checks."""
+    S, H, W = 16, 64, 64
+    gen = torch.Generator(device=DEV).manual_seed(50 + M)
+    params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    ll64 = F.modl_log_likelihood(params, x_u8, dtype=torch.float64)
+    lp = F.modl_log_prob(params, x_u8)
+    assert ((lp.double().sum((-1, -2)) - ll64).abs() / ll64.abs()).max().item() < 1e-12
+    assert torch.equal(ll64, F.modl_log_likelihood(params, x_u8, dtype=torch.float64))
+    g = torch.randn(S, B, device=DEV, generator=gen)
+    dp = F.modl_backward(params, x_u8, g_image=g)
+    assert torch.equal(dp, F.modl_backward(params, x_u8, g_image=g))
+    assert (F.modl_backward(params, x_u8, g_image=4 * g) - 4 * dp).abs().max().item() < 1e-30
+    assert dp[..., :M].sum(-1).abs().max().item() < 2e-5 * g.abs().max().item()
+    for s_i, b_i in [(0, 0), (S - 1, B - 1), (7, B // 2)]:
+        p64 = params[s_i, b_i].cpu().double()[None].requires_grad_(True)
+        x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
+        want = O.modl_log_prob(p64, x64).sum()
+        assert abs(ll64[s_i, b_i].item() - want.item()) <= LL_RTOL * abs(want.item())
+        (want * g[s_i, b_i].item()).backward()
+        assert relnorm(dp[s_i, b_i], p64.grad[0]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("S,B,M", [(5, 64, 10), (5, 128, 5)])
+def test_config1_one_launch_step_full_size(F, V, monkeypatch, S, B, M):
+    """BASELINE configs[0] (and the reference's real default, n_mix 5 x batch 128) through vaemdl_modl_iwae_step: the
+    cooperative one-launch kernel is taken, equals the three-launch route bit for bit, and matches the oracle on whole
+    images picked from both ends of the tensor."""
+    H = W = 32
+    gen = torch.Generator(device=DEV).manual_seed(100 + M)
+    params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    extra = torch.randn(S, B, device=DEV, generator=gen) * 3
+    monkeypatch.delenv("VAEMDL_FUSED", raising=False)
+    a = F.modl_iwae_step(params, x_u8, extra)
+    assert a[-1] == 1
+    monkeypatch.setenv("VAEMDL_FUSED", "0")
+    b = F.modl_iwae_step(params, x_u8, extra)
+    assert b[-1] == 3
+    for u, v in zip(a[:3] + a[4:6], b[:3] + b[4:6]):
+        assert torch.equal(u, v)
+    assert abs(a[3].item() - b[3].item()) <= 1e-6 * abs(b[3].item())
+    ll64, g_ll, dp = a[0], a[4], a[5]
+    lw = ll64 + extra.double()
+    assert relnorm(g_ll, -torch.softmax(lw, 0) / B) < 1e-5
+    for s_i, b_i in [(0, 0), (S - 1, B - 1), (2, B // 3)]:
+        p64 = params[s_i, b_i].cpu().double()[None].requires_grad_(True)
+        x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
+        want = O.modl_log_prob(p64, x64).sum()
+        assert abs(ll64[s_i, b_i].item() - want.item()) <= LL_RTOL * abs(want.item())
+        (want * g_ll[s_i, b_i].item()).backward()
+        assert relnorm(dp[s_i, b_i], p64.grad[0]) <= GRAD_RTOL
+
+
+def test_config5_shard_bf16_parameters(F):
+    """The config-5 shard with bfloat16 parameters: bit-identical sums to the float32 kernels on the widened tensor, the
+    gradient is the float32 gradient rounded once."""
+    S, B, H, W, M = 16, 32, 64, 64, 10
+    gen = torch.Generator(device=DEV).manual_seed(55)
+    pb = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen).bfloat16()
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    g = torch.randn(S, B, device=DEV, generator=gen)
+    wide = pb.float()
+    assert torch.equal(F.modl_log_likelihood(pb, x_u8, dtype=torch.float64), F.modl_log_likelihood(wide, x_u8, dtype=torch.float64))
+    dp = F.modl_backward(pb, x_u8, g_image=g)
+    assert dp.dtype == torch.bfloat16 and torch.equal(dp, F.modl_backward(wide, x_u8, g_image=g).bfloat16())
