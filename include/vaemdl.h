@@ -220,6 +220,18 @@ VAEMDL_API int vaemdl_dlogistic_iwae_fwd(const float* loc, const float* logscale
                          float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* One IWAE step of the plain discretized logistic in ONE call: vaemdl_dlogistic_iwae_fwd + vaemdl_dlogistic_bwd(g_image =
+ * g_ll) (lme_b, g_ll, dloc, dlogscale required).  For image tensors (C = 3, dense [..,3] pairs or the un-split [..,6]
+ * layout), S <= 32 and at most two 64-pixel tiles per resident warp (BASELINE configs[1]: 5 x 128 x 32 x 32 x 3) this is a
+ * single cooperative launch that reads the parameters once and keeps the unscaled derivatives in registers across the
+ * grid barriers; three launches otherwise (the two routes agree to float32 round-off).  *launches: nullable. */
+VAEMDL_API int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscale, int C, int ld,
+                         const void* x, int x_dtype, int S, long long B, long long B_total, int x_batch, long long D,
+                         float low, float high, float levels, const float* extra,
+                         float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                         float* dloc, float* dlogscale, int ld_out,
+                         void* workspace, size_t workspace_bytes, void* stream, int* launches);
+
 /* dloc / dlogscale use the same (C, ld_out) addressing as loc / logscale. */
 VAEMDL_API int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int C, int ld,
                          const void* x, int x_dtype, long long n_img, int x_batch, long long D,

@@ -160,3 +160,52 @@ def test_elementwise_log_prob_and_grad_every_layout(V, shape, split, x_u8):
     (lp * w.to(DEV)).sum().backward()
     assert relnorm(bd.grad[..., :C], b64.grad[..., :C]) < GRAD_RTOL
     assert relnorm(bd.grad[..., C:], b64.grad[..., C:]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("S,B,H,W,interleaved,u8", [(5, 16, 32, 32, True, True), (5, 16, 32, 32, False, False), (3, 4, 8, 8, True, False),
+                                                   (2, 3, 16, 12, False, True), (32, 2, 8, 8, True, True), (1, 1, 8, 8, True, True),
+                                                   (5, 128, 32, 32, True, True), (4, 300, 16, 16, False, True)])
+def test_one_launch_dl_step_equals_three_launch_step(built_lib, monkeypatch, S, B, H, W, interleaved, u8):
+    """vaemdl_dlogistic_iwae_step: the cooperative one-launch kernel (forward with the unscaled derivatives parked in
+    shared memory -> grid barrier -> finish -> grid barrier -> scale and store) agrees with forward + finish + backward
+    as three launches to float32 round-off, and matches the float64 oracle (models/model03.py shapes, both layouts)."""
+    from vae_mdl_b200 import functional as F
+    g = torch.Generator().manual_seed(4100 + S + B + H)
+    both = torch.randn(S, B, H, W, 6, generator=g)
+    both[..., :3] = torch.rand(S, B, H, W, 3, generator=g)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g)
+    x_u8.view(-1)[::13] = 0
+    x_u8.view(-1)[3::19] = 255
+    loc64 = both[..., :3].double().requires_grad_(True)
+    ls64 = both[..., 3:].double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    ll64 = O.dlogistic_log_prob(x64, loc64, ls64, 0.0, 1.0, 256.0).sum((-1, -2, -3))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()) + torch.randn(S, B, generator=g).double()
+    loss64 = -O.logmeanexp(ll64 + extra.float().double(), 0).mean()
+    loss64.backward()
+    bd = both.to(DEV)
+    if interleaved:
+        loc, ls = bd[..., :3], bd[..., 3:]
+    else:
+        loc, ls = bd[..., :3].contiguous(), bd[..., 3:].contiguous()
+    xd = x_u8.to(DEV) if u8 else (x_u8.float() / 255.0).to(DEV)
+    ed = extra.float().to(DEV)
+    monkeypatch.delenv("VAEMDL_FUSED", raising=False)
+    a = F.dlogistic_iwae_step(loc, ls, xd, ed, 0.0, 1.0, 256.0)
+    torch.cuda.synchronize()
+    assert a[-1] == 1, "the one-launch kernel was not taken"
+    monkeypatch.setenv("VAEMDL_FUSED", "0")
+    b = F.dlogistic_iwae_step(loc, ls, xd, ed, 0.0, 1.0, 256.0)
+    torch.cuda.synchronize()
+    assert b[-1] == 3
+    # the one-launch kernel takes the forward value out of the GRADIENT instantiation of the element function (evaluated
+    # once): the compiler contracts a few FMAs differently there, so the two routes agree to float32 round-off, not bit
+    # for bit; the importance weights see the ~1e-4 nat differences of the per-image sums
+    for name, u, v in zip(("ll64", "log_w", "lme_b", "elbo", "g_ll", "dloc", "dls"), a[:-1], b[:-1]):
+        u, v = u.double(), v.double()
+        tol = {"ll64": 1e-7, "log_w": 1e-6, "lme_b": 1e-6, "elbo": 1e-6, "g_ll": 2e-3, "dloc": 2e-3, "dls": 2e-3}[name]
+        assert ((u - v).norm() / v.norm()).item() <= tol, f"{name} differs between the one-launch and the three-launch step"
+    assert ((a[0].cpu() - ll64.detach()).abs() / ll64.detach().abs()).max().item() <= 1e-5
+    assert abs(-a[3].item() - loss64.item()) <= 1e-5 * abs(loss64.item())
+    assert ((a[5].cpu().double() - loc64.grad).norm() / loc64.grad.norm()).item() <= 1e-4
+    assert ((a[6].cpu().double() - ls64.grad).norm() / ls64.grad.norm()).item() <= 1e-4

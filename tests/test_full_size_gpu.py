@@ -104,7 +104,10 @@ def test_config2_plain_dl_full_size(F, V):
     # (a lane adds its six element values in float32 before the float64 accumulation: agreement to float32 rounding)
     assert ((lp.double().sum((-1, -2, -3)) - ll64).abs() / ll64.abs()).max().item() < 1e-7
     loss, lpxz, dloc, dls = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)
-    assert torch.equal(lpxz, ll64)
+    # (the one-launch step takes the forward value out of the gradient instantiation of the element function: float32
+    # round-off apart from the forward kernel's, see tests/test_dlogistic_gpu.py)
+    assert ((lpxz - ll64).abs() / ll64.abs()).max().item() < 1e-7
+    ll64 = lpxz
     want = -(torch.logsumexp(ll64, 0) - math.log(S)).mean()
     assert abs(loss.item() - want.item()) <= 1e-6 * abs(want.item())
     loss2, _, dloc2, dls2 = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)

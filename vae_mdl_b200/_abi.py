@@ -70,6 +70,10 @@ PROTOTYPES = {
     "vaemdl_dlogistic_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_longlong, c_longlong,
                                           c_int, c_longlong, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_dlogistic_iwae_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_longlong, c_longlong,
+                                           c_int, c_longlong, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                           c_size_t, c_void_p, c_void_p]),
     "vaemdl_dlogistic_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_longlong,
                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vaemdl_logmeanexp_fwd": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),

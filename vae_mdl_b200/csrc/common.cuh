@@ -218,6 +218,51 @@ __device__ __forceinline__ double image_sum(const PartialGeom& g, long long n, b
   return small ? image_sum_t<unsigned>(g, n) : image_sum_t<long long>(g, n);
 }
 
+// ---- the IWAE finish inside a cooperative one-launch step (modl_step_kernel, dl_step_kernel) --------------------------------
+struct StepFinish {
+  PartialGeom geom;
+  const float* extra;  // [S,B] nullable
+  float* ll;           // [S,B] nullable
+  double* ll64;        // [S,B] nullable
+  float* log_w;        // [S,B] nullable
+  float* lme_b;        // [B]
+  float* elbo;         // [1] nullable
+  float* g_ll;         // [S,B]
+  double* lme64;       // [B] scratch
+  long long B;
+  int S;  // <= 32: one importance sample per lane
+  float b_norm;
+  bool small;
+};
+// warp `gw` of `total_warps` takes batch elements gw, gw + total_warps, ...: same arithmetic, in the same order, as
+// finish_kernel steps (1) and (2) with S <= 32
+__device__ __forceinline__ void step_finish(const StepFinish& f, long long gw, long long total_warps, int lane) {
+  for (long long b = gw; b < f.B; b += total_warps) {
+    const long long n = static_cast<long long>(lane) * f.B + b;
+    double v = -INFINITY;
+    if (lane < f.S) {
+      const double acc = image_sum(f.geom, n, f.small);
+      if (f.ll) f.ll[n] = static_cast<float>(acc);
+      if (f.ll64) f.ll64[n] = acc;
+      v = acc + (f.extra ? static_cast<double>(f.extra[n]) : 0.0);  // models/loss.py:34
+      if (f.log_w) f.log_w[n] = static_cast<float>(v);
+    }
+    double mx = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));  // utils/utils.py:10
+    const float e = lane < f.S ? expf(static_cast<float>(v - mx)) : 0.0f;
+    float sm = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(kFull, sm, o);
+    const double lme = static_cast<double>(logf(sm / static_cast<float>(f.S))) + mx;  // utils/utils.py:11
+    if (lane == 0) {
+      f.lme_b[b] = static_cast<float>(lme);
+      f.lme64[b] = lme;
+    }
+    if (lane < f.S) f.g_ll[n] = e * (-1.0f / (sm * f.b_norm));  // d(-mean_b lme_b)/d log_w = -softmax_s / B
+  }
+}
+
 struct IwaeOut {  // outputs of the fused IWAE finish (all nullable); active when S > 0
   int S = 0;
   long long B = 0, B_total = 0;

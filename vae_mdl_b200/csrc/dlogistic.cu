@@ -8,7 +8,10 @@
 //   edges  : -log(1+AG)   or   -|mid| - log(A+G)
 // The log-scale is NOT clamped in this class (utils/discretized_logistic.py:38); exp(-ls) is saturated at 3e38 so
 // that x == loc with a vanishing scale gives log 1 = 0 as the reference does instead of inf*0.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
+#include <mutex>
 
 #include "modl_math.cuh"
 #include "packed.cuh"
@@ -285,6 +288,66 @@ __device__ __forceinline__ DlOut2 dl_elem2(f2 x, f2 loc, f2 ls, const DlArgs& a)
   return o;
 }
 
+// this lane's pixel pair (rows r0, r0 + 1): location / log-scale / observation of the three channels, pixel A in the lo
+// halves, pixel B in the hi halves
+template <bool IL>
+__device__ __forceinline__ void dl_pair_load(const DlArgs& a, long long r0, long long xb, long long rpi, long long rr,
+                                             f2 loc[3], f2 ls[3], f2 xv[3]) {
+  if constexpr (IL) {
+    const float4* p = reinterpret_cast<const float4*>(a.loc + r0 * 6);
+    const float4 u0 = p[0], u1 = p[1], u2 = p[2];  // [locA(3) lsA(3) locB(3) lsB(3)]
+    loc[0] = pk(u0.x, u1.z);
+    loc[1] = pk(u0.y, u1.w);
+    loc[2] = pk(u0.z, u2.x);
+    ls[0] = pk(u0.w, u2.y);
+    ls[1] = pk(u1.x, u2.z);
+    ls[2] = pk(u1.y, u2.w);
+  } else {
+    const float2* p = reinterpret_cast<const float2*>(a.loc + r0 * 3);
+    const float2* q = reinterpret_cast<const float2*>(a.logscale + r0 * 3);
+    const float2 u0 = p[0], u1 = p[1], u2 = p[2], v0 = q[0], v1 = q[1], v2 = q[2];  // [A0 A1 | A2 B0 | B1 B2]
+    loc[0] = pk(u0.x, u1.y);
+    loc[1] = pk(u0.y, u2.x);
+    loc[2] = pk(u1.x, u2.y);
+    ls[0] = pk(v0.x, v1.y);
+    ls[1] = pk(v0.y, v2.x);
+    ls[2] = pk(v1.x, v2.y);
+  }
+  const long long xo = (xb * rpi + rr) * 3;
+  if (a.x_u8) {
+    const uint8_t* xp = static_cast<const uint8_t*>(a.x) + xo;  // 6 bytes, 2-byte aligned (xo is a multiple of 6)
+    const ushort3 w = *reinterpret_cast<const ushort3*>(xp);
+    xv[0] = pk(u8_to_unit(w.x & 0xff), u8_to_unit(w.y >> 8));
+    xv[1] = pk(u8_to_unit(w.x >> 8), u8_to_unit(w.z & 0xff));
+    xv[2] = pk(u8_to_unit(w.y & 0xff), u8_to_unit(w.z >> 8));
+  } else {
+    const float2* xp = reinterpret_cast<const float2*>(static_cast<const float*>(a.x) + xo);
+    const float2 w0 = xp[0], w1 = xp[1], w2 = xp[2];
+    xv[0] = pk(w0.x, w1.y);
+    xv[1] = pk(w0.y, w2.x);
+    xv[2] = pk(w1.x, w2.y);
+  }
+}
+
+template <bool IL>
+__device__ __forceinline__ void dl_pair_store(const DlArgs& a, long long r0, const f2 dl[3], const f2 ds[3]) {
+  if constexpr (IL) {
+    float4* out = reinterpret_cast<float4*>(a.dloc + r0 * 6);
+    out[0] = make_float4(lo(dl[0]), lo(dl[1]), lo(dl[2]), lo(ds[0]));
+    out[1] = make_float4(lo(ds[1]), lo(ds[2]), hi(dl[0]), hi(dl[1]));
+    out[2] = make_float4(hi(dl[2]), hi(ds[0]), hi(ds[1]), hi(ds[2]));
+  } else {
+    float2* o1 = reinterpret_cast<float2*>(a.dloc + r0 * 3);
+    float2* o2 = reinterpret_cast<float2*>(a.dls + r0 * 3);
+    o1[0] = make_float2(lo(dl[0]), lo(dl[1]));
+    o1[1] = make_float2(lo(dl[2]), hi(dl[0]));
+    o1[2] = make_float2(hi(dl[1]), hi(dl[2]));
+    o2[0] = make_float2(lo(ds[0]), lo(ds[1]));
+    o2[1] = make_float2(lo(ds[2]), hi(ds[0]));
+    o2[2] = make_float2(hi(ds[1]), hi(ds[2]));
+  }
+}
+
 // IL: loc/logscale are the two halves of one [.., 6] tensor (ld = 6, logscale = loc + 3) and so are dloc/dls.
 template <bool BWD, bool IL>
 __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
@@ -321,40 +384,7 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
     const bool active = r0 < a.n_rows;
     f2 loc[3], ls[3], xv[3];
     if (active) {
-      if constexpr (IL) {
-        const float4* p = reinterpret_cast<const float4*>(a.loc + r0 * 6);
-        const float4 u0 = p[0], u1 = p[1], u2 = p[2];  // [locA(3) lsA(3) locB(3) lsB(3)]
-        loc[0] = pk(u0.x, u1.z);
-        loc[1] = pk(u0.y, u1.w);
-        loc[2] = pk(u0.z, u2.x);
-        ls[0] = pk(u0.w, u2.y);
-        ls[1] = pk(u1.x, u2.z);
-        ls[2] = pk(u1.y, u2.w);
-      } else {
-        const float2* p = reinterpret_cast<const float2*>(a.loc + r0 * 3);
-        const float2* q = reinterpret_cast<const float2*>(a.logscale + r0 * 3);
-        const float2 u0 = p[0], u1 = p[1], u2 = p[2], v0 = q[0], v1 = q[1], v2 = q[2];  // [A0 A1 | A2 B0 | B1 B2]
-        loc[0] = pk(u0.x, u1.y);
-        loc[1] = pk(u0.y, u2.x);
-        loc[2] = pk(u1.x, u2.y);
-        ls[0] = pk(v0.x, v1.y);
-        ls[1] = pk(v0.y, v2.x);
-        ls[2] = pk(v1.x, v2.y);
-      }
-      const long long xo = (xb * rpi + rr) * 3;
-      if (a.x_u8) {
-        const uint8_t* xp = static_cast<const uint8_t*>(a.x) + xo;  // 6 bytes, 2-byte aligned (xo is a multiple of 6)
-        const ushort3 w = *reinterpret_cast<const ushort3*>(xp);
-        xv[0] = pk(u8_to_unit(w.x & 0xff), u8_to_unit(w.y >> 8));
-        xv[1] = pk(u8_to_unit(w.x >> 8), u8_to_unit(w.z & 0xff));
-        xv[2] = pk(u8_to_unit(w.y & 0xff), u8_to_unit(w.z >> 8));
-      } else {
-        const float2* xp = reinterpret_cast<const float2*>(static_cast<const float*>(a.x) + xo);
-        const float2 w0 = xp[0], w1 = xp[1], w2 = xp[2];
-        xv[0] = pk(w0.x, w1.y);
-        xv[1] = pk(w0.y, w2.x);
-        xv[2] = pk(w1.x, w2.y);
-      }
+      dl_pair_load<IL>(a, r0, xb, rpi, rr, loc, ls, xv);
     } else {
 #pragma unroll
       for (int c = 0; c < 3; ++c) loc[c] = ls[c] = xv[c] = sp(0.0f);
@@ -404,21 +434,7 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
         dl[c] = ge[c] * o[c].dloc;
         ds[c] = ge[c] * o[c].dls;
       }
-      if constexpr (IL) {
-        float4* out = reinterpret_cast<float4*>(a.dloc + r0 * 6);
-        out[0] = make_float4(lo(dl[0]), lo(dl[1]), lo(dl[2]), lo(ds[0]));
-        out[1] = make_float4(lo(ds[1]), lo(ds[2]), hi(dl[0]), hi(dl[1]));
-        out[2] = make_float4(hi(dl[2]), hi(ds[0]), hi(ds[1]), hi(ds[2]));
-      } else {
-        float2* o1 = reinterpret_cast<float2*>(a.dloc + r0 * 3);
-        float2* o2 = reinterpret_cast<float2*>(a.dls + r0 * 3);
-        o1[0] = make_float2(lo(dl[0]), lo(dl[1]));
-        o1[1] = make_float2(lo(dl[2]), hi(dl[0]));
-        o1[2] = make_float2(hi(dl[1]), hi(dl[2]));
-        o2[0] = make_float2(lo(ds[0]), lo(ds[1]));
-        o2[1] = make_float2(lo(ds[2]), hi(ds[0]));
-        o2[2] = make_float2(hi(ds[1]), hi(ds[2]));
-      }
+      dl_pair_store<IL>(a, r0, dl, ds);
     }
     // next tile: 64 rows further on
     r0 += 64;
@@ -437,6 +453,129 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
         const double d1 = dl_warp_sum(acc1);
         if (lane == 0) a.partial[partial_slot(n_base + 1, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
       }
+    }
+  }
+}
+
+// ---- one step in one launch (models 03 / 04 / 06: BASELINE configs[1]) ---------------------------------------------------
+// Forward, IWAE finish and gradient of the plain discretized logistic in ONE cooperative kernel.  The shapes this serves
+// are small (S x B x 32 x 32 x 3 with a few hundred images: a handful of 64-pixel tiles per resident warp), so every warp
+// parks the unscaled derivatives of its tiles in shared memory across the two grid barriers: the parameters are read
+// ONCE, the logistic terms are evaluated ONCE, and after the barriers the gradient is one multiply per element.
+// Same formulas and summation order as dl_pair_kernel<false> + finish_kernel + dl_pair_kernel<true>; the forward value comes
+// out of the gradient instantiation of dl_elem2 here, so the two routes agree to float32 round-off (not bit for bit).
+constexpr int kStepKeep = 13;  // floats a lane parks per tile: 6 derivative pairs + the image index of its pixel pair
+struct DlStepArgs {
+  DlArgs a;
+  StepFinish f;
+  int T;  // tiles a warp can park (its run is at most T tiles long)
+};
+
+template <bool IL>
+__global__ void __launch_bounds__(256, 3) dl_step_kernel(const DlStepArgs sa) {
+  extern __shared__ float dl_keep[];  // [warps][T][kStepKeep][32]
+  const DlArgs& a = sa.a;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gw = static_cast<long long>(warp) * gridDim.x + blockIdx.x;
+  const long long total_warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);   // t_end - t_begin <= T
+  const long long rpi = a.rows_per_img;
+  float* keep = dl_keep + static_cast<size_t>(warp) * sa.T * (kStepKeep * 32) + lane;
+  if (t_begin < t_end) {
+    long long n_warp_first, xb;
+    if (a.small) {
+      n_warp_first = static_cast<unsigned>(t_begin * 64) / static_cast<unsigned>(rpi);
+      xb = a.x_batch == 1 ? 0 : static_cast<unsigned>(n_warp_first) % static_cast<unsigned>(a.x_batch);
+    } else {
+      n_warp_first = (t_begin * 64) / rpi;
+      xb = a.x_batch == 1 ? 0 : n_warp_first % a.x_batch;
+    }
+    long long r0 = t_begin * 64 + 2 * lane;
+    long long n = n_warp_first;
+    long long rr = r0 - n * rpi;
+    while (rr >= rpi) {
+      rr -= rpi;
+      ++n;
+      if (a.x_batch != 1 && ++xb == a.x_batch) xb = 0;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    long long n_base = n_warp_first;
+    bool any1 = false;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const bool active = r0 < a.n_rows;
+      f2 loc[3], ls[3], xv[3];
+      if (active) {
+        dl_pair_load<IL>(a, r0, xb, rpi, rr, loc, ls, xv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) loc[c] = ls[c] = xv[c] = sp(0.0f);
+      }
+      float* kp = keep + (t - t_begin) * (kStepKeep * 32);
+      f2 s2 = sp(0.0f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const DlOut2 o = dl_elem2<true>(xv[c], loc[c], ls[c], a);
+        kp[(4 * c + 0) * 32] = lo(o.dloc);
+        kp[(4 * c + 1) * 32] = hi(o.dloc);
+        kp[(4 * c + 2) * 32] = lo(o.dls);
+        kp[(4 * c + 3) * 32] = hi(o.dls);
+        s2 = c == 0 ? o.lp : s2 + o.lp;
+      }
+      kp[12 * 32] = __int_as_float(active ? static_cast<int>(n) : -1);  // (S * B images: far below 2^31)
+      const float val = active ? lo(s2) + hi(s2) : 0.0f;
+      const long long n_first = __shfl_sync(kFull, n, 0);
+      while (n_base < n_first) {
+        const double done = dl_warp_sum(acc0);
+        if (lane == 0) a.partial[partial_slot(n_base, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = done;
+        acc0 = acc1;
+        acc1 = 0.0;
+        ++n_base;
+      }
+      if (n == n_base)
+        acc0 += static_cast<double>(val);
+      else
+        acc1 += static_cast<double>(val);
+      any1 = __any_sync(kFull, active && n != n_base);
+      r0 += 64;
+      rr += 64;
+      while (rr >= rpi) {
+        rr -= rpi;
+        ++n;
+        if (a.x_batch != 1 && ++xb == a.x_batch) xb = 0;
+      }
+    }
+    const double d0 = dl_warp_sum(acc0);
+    if (lane == 0) a.partial[partial_slot(n_base, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+    if (any1) {
+      const double d1 = dl_warp_sum(acc1);
+      if (lane == 0) a.partial[partial_slot(n_base + 1, gw, rpi, 64, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
+    }
+  }
+  __threadfence();
+  grid.sync();
+  step_finish(sa.f, gw, total_warps, lane);
+  __threadfence();
+  grid.sync();
+  if (sa.f.elbo && gw == total_warps - 1) {  // batch mean, fixed order
+    double t = 0.0;
+    for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
+    t = dl_warp_sum(t);
+    if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+  }
+  for (long long t = t_begin; t < t_end; ++t) {
+    const float* kp = keep + (t - t_begin) * (kStepKeep * 32);
+    const int n = __float_as_int(kp[12 * 32]);
+    if (n >= 0) {
+      const f2 ge = sp(sa.f.g_ll[n]);
+      f2 dl[3], ds[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        dl[c] = ge * pk(kp[(4 * c + 0) * 32], kp[(4 * c + 1) * 32]);
+        ds[c] = ge * pk(kp[(4 * c + 2) * 32], kp[(4 * c + 3) * 32]);
+      }
+      dl_pair_store<IL>(a, t * 64 + 2 * lane, dl, ds);
     }
   }
 }
@@ -642,6 +781,112 @@ extern "C" int vaemdl_dlogistic_bwd(const float* loc, const float* logscale, int
   a.dls = dlogscale;
   a.ld_out = ld_out;
   return dl_launch<true>(a, cpt, dl_kind(a, cpt, true), static_cast<cudaStream_t>(stream));
+}
+
+namespace vaemdl {
+constexpr int kStepMaxT = 12;
+// smallest number of parked tiles per warp T for which a grid of resident CTAs covers n_tiles; 0 = not eligible
+static int dl_step_plan(const DlArgs& a, int kind, int S, long long n_tiles, long long* blocks_out) {
+  const char* e = getenv("VAEMDL_FUSED");  // "0": always three launches
+  if (e && e[0] == '0') return 0;
+  if (S > 32 || (kind != 1 && kind != 2) || a.rows_per_img < 64) return 0;
+  static int coop = -1, occ[2][kStepMaxT + 1];
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (coop < 0) {
+      int dev = 0, v = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+      const int max_smem = kStepMaxT * 8 * kStepKeep * 32 * 4;
+      cudaFuncSetAttribute(dl_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      cudaFuncSetAttribute(dl_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      for (int T = 1; T <= kStepMaxT; ++T) {
+        const size_t smem = static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4;
+        occ[0][T] = occ[1][T] = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0][T], dl_step_kernel<true>, 256, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1][T], dl_step_kernel<false>, 256, smem);
+      }
+      coop = v;
+    }
+  }
+  if (!coop) return 0;
+  for (int T = 1; T <= kStepMaxT; ++T) {
+    long long blocks = static_cast<long long>(device_info().sm_count) * occ[kind == 1 ? 0 : 1][T];  // every CTA resident
+    if (blocks * 8 > kMaxGridWarps) blocks = kMaxGridWarps / 8;
+    if (blocks < 1) continue;
+    const long long need = (n_tiles + 7) / 8;
+    if (blocks > need) blocks = need;
+    const long long total_warps = blocks * 8;
+    if ((n_tiles + total_warps - 1) / total_warps <= T) {
+      *blocks_out = blocks;
+      return T;
+    }
+  }
+  return 0;
+}
+}  // namespace vaemdl
+
+/* One IWAE step of the plain discretized logistic in one call (models/model03.py:139-148, models/model06.py): one
+ * cooperative launch for the small image shapes, forward + finish + gradient (3 launches) otherwise. */
+extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscale, int C, int ld, const void* x,
+                                          int x_dtype, int S, long long B, long long B_total, int x_batch, long long D,
+                                          float low, float high, float levels, const float* extra, float* ll_image,
+                                          double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                                          float* dloc, float* dlogscale, int ld_out, void* workspace,
+                                          size_t workspace_bytes, void* stream, int* launches) {
+  if (S <= 0 || B <= 0 || B_total < 0 || !lme_b || !g_ll || !dloc || !dlogscale || ld_out < C) return VAEMDL_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n_img = static_cast<long long>(S) * B;
+  DlArgs a{};
+  int cpt = 1;
+  int rc = dl_fill(a, loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, cpt);
+  if (rc) return rc;
+  a.dloc = dloc;
+  a.dls = dlogscale;
+  a.ld_out = ld_out;
+  const int kind = dl_kind(a, cpt, true);
+  const long long n_tiles = (a.n_rows + 63) / 64;
+  long long blocks = 0;
+  const int T = dl_step_plan(a, kind, S, n_tiles, &blocks);
+  if (T == 0) {
+    if (launches) *launches = 3;
+    rc = vaemdl_dlogistic_iwae_fwd(loc, logscale, C, ld, x, x_dtype, S, B, B_total, x_batch, D, low, high, levels, extra,
+                                   ll_image, ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return vaemdl_dlogistic_bwd(loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, g_ll, nullptr, dloc,
+                                dlogscale, ld_out, stream);
+  }
+  if (!workspace || workspace_bytes < vaemdl_dlogistic_workspace_bytes(n_img, D)) return VAEMDL_EWORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
+  char* ws = static_cast<char*>(workspace);
+  a.partial = reinterpret_cast<double*>(ws);
+  const long long total_warps = blocks * 8;
+  a.tw_base = n_tiles / total_warps;
+  a.tw_rem = n_tiles % total_warps;
+  a.K = partial_K(a.rows_per_img, 64, a.tw_base);
+  if (static_cast<size_t>(n_img) * a.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+  DlStepArgs sa{};
+  sa.a = a;
+  sa.T = T;
+  sa.f.geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, 64, a.rows_per_img};
+  sa.f.extra = extra;
+  sa.f.ll = ll_image;
+  sa.f.ll64 = ll_image_f64;
+  sa.f.log_w = log_w;
+  sa.f.lme_b = lme_b;
+  sa.f.elbo = elbo;
+  sa.f.g_ll = g_ll;
+  sa.f.lme64 = reinterpret_cast<double*>(ws + partial_elems(n_img) * sizeof(double));
+  sa.f.B = B;
+  sa.f.S = S;
+  sa.f.b_norm = static_cast<float>(B_total > 0 ? B_total : B);
+  sa.f.small = n_img * a.rows_per_img < (1ll << 31);
+  if (launches) *launches = 1;
+  void* args[] = {&sa};
+  void* kern = kind == 1 ? reinterpret_cast<void*>(dl_step_kernel<true>) : reinterpret_cast<void*>(dl_step_kernel<false>);
+  return cuda_rc(cudaLaunchCooperativeKernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(256), args,
+                                             static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4, st));
 }
 
 extern "C" int vaemdl_dlogistic_sample(const float* loc, const float* logscale, int C, int ld, const float* u,

@@ -378,6 +378,54 @@ def dlogistic_iwae_forward(loc, logscale, x, extra: Optional[torch.Tensor] = Non
     return ll64, log_w, lme_b, elbo, g_ll
 
 
+def dlogistic_iwae_step(loc, logscale, x, extra: Optional[torch.Tensor] = None, low=-1.0, high=1.0, levels=256.0,
+                        b_total: int = 0, n_event_dims: int = 3):
+    """Plain discretized-logistic forward + IWAE finish + gradient in ONE call (``vaemdl_dlogistic_iwae_step``): a single
+    cooperative kernel launch for the image shapes of models 03/04/06 (the parameters are read once, the unscaled
+    derivatives wait in shared memory for the importance weights), three launches otherwise.  Arguments as
+    ``dlogistic_iwae_forward``.  Returns ``(lpxz float64 [S,B], log_w, lme_b, elbo, g_ll, dloc, dlogscale, launches)``;
+    for the two halves of an un-split ``[..., 2C]`` tensor the two gradients are views of one ``[..., 2C]`` buffer."""
+    if loc.shape != logscale.shape:
+        loc, logscale = torch.broadcast_tensors(loc, logscale)
+    _abi.require_cuda(loc, "loc")
+    if loc.dim() != 2 + n_event_dims:
+        raise ValueError("loc must be [S, B, *event]")
+    locd, lsd, C, ld = _dl_layout(loc, logscale)
+    shape = tuple(loc.shape)
+    S, B = shape[:2]
+    ev = shape[2:]
+    D = int(math.prod(ev))
+    xd, x_dtype, x_batch = _prep_x(x, ev, "x")
+    if x_batch not in (1, B):
+        raise ValueError(f"x must hold {B} images (or one), got {x_batch}")
+    ex = dense_f32(extra, "extra").reshape(S, B) if extra is not None else None
+    L = lib()
+    dev = loc.device
+    ll64 = torch.empty((S, B), device=dev, dtype=torch.float64)
+    log_w = torch.empty((S, B), device=dev, dtype=torch.float32)
+    lme_b = torch.empty(B, device=dev, dtype=torch.float32)
+    elbo = torch.empty(1, device=dev, dtype=torch.float32)
+    g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
+    if ld == 2 * C:
+        both = torch.empty(shape[:-1] + (2 * C,), device=dev, dtype=torch.float32)
+        dloc, dls, ld_out = both[..., :C], both[..., C:], 2 * C
+        p_loc, p_ls = both.data_ptr(), both.data_ptr() + 4 * C
+    else:
+        dloc = torch.empty(shape, device=dev, dtype=torch.float32)
+        dls = torch.empty(shape, device=dev, dtype=torch.float32)
+        ld_out, p_loc, p_ls = C, dloc.data_ptr(), dls.data_ptr()
+    ws_bytes = L.vaemdl_dlogistic_workspace_bytes(S * B, D)
+    ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
+    n_launch = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        check(L.vaemdl_dlogistic_iwae_step(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, S, B, int(b_total), x_batch, D,
+                                           float(low), float(high), float(levels), ptr(ex), None, ptr(ll64), ptr(log_w),
+                                           ptr(lme_b), ptr(elbo), ptr(g_ll), ctypes.c_void_p(p_loc), ctypes.c_void_p(p_ls),
+                                           ld_out, ptr(ws), ws_bytes, stream_ptr(dev), ctypes.byref(n_launch)),
+              "vaemdl_dlogistic_iwae_step")
+    return ll64, log_w, lme_b, elbo, g_ll, dloc, dls, n_launch.value
+
+
 def dlogistic_backward(loc, logscale, x, g_image: torch.Tensor, low=-1.0, high=1.0, levels=256.0, n_event_dims: int = 3):
     """The plain-DL gradient kernel on its own: ``d/d(loc, logscale)`` of ``sum(g_image * ll_image)``.  For the two halves
     of an un-split ``[..., 2C]`` tensor the two gradients are views of one ``[..., 2C]`` buffer."""

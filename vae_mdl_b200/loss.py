@@ -160,12 +160,13 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = 
 
 def dlogistic_iwae_step(loc: torch.Tensor, logscale: torch.Tensor, x: torch.Tensor, extra: torch.Tensor = None,
                         low=-1.0, high=1.0, levels=256.0, need_grad: bool = True, b_total: int = 0):
-    """The plain discretized-logistic counterpart of ``modl_iwae_step`` (models 03/04/06): forward -> fused finish ->
-    gradient, 3 launches.  ``loc``/``logscale [S,B,H,W,3]`` (e.g. the two halves of the ``[..,6]`` conv output,
+    """The plain discretized-logistic counterpart of ``modl_iwae_step`` (models 03/04/06): forward -> finish -> gradient,
+    one cooperative launch for image shapes (``vaemdl_dlogistic_iwae_step``), three launches otherwise.  ``loc``/``logscale [S,B,H,W,3]`` (e.g. the two halves of the ``[..,6]`` conv output,
     models/model03.py:88-91), ``x [B,H,W,3]``.  Returns ``(loss=-elbo [1], lpxz [S,B] float64, dloc, dlogscale)``."""
     with torch.no_grad():
-        lpxz, _, _, elbo, g_ll = F.dlogistic_iwae_forward(loc, logscale, x, extra, low, high, levels, b_total)
-        dloc = dls = None
-        if need_grad:
-            dloc, dls = F.dlogistic_backward(loc, logscale, x, g_ll, low, high, levels)
+        if need_grad:  # one call: a single cooperative launch for the image shapes of models 03/04/06
+            lpxz, _, _, elbo, _, dloc, dls, _ = F.dlogistic_iwae_step(loc, logscale, x, extra, low, high, levels, b_total)
+        else:
+            lpxz, _, _, elbo, _ = F.dlogistic_iwae_forward(loc, logscale, x, extra, low, high, levels, b_total)
+            dloc = dls = None
     return -elbo, lpxz, dloc, dls
