@@ -567,10 +567,35 @@ def run_reference(args, wl):
         "gpu_launches": 0,
         "note": "TensorFlow/TFP are not installable in this image; this is the restated reference (kind=port)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints a version banner when the box
+    exports NCCL_DEBUG=VERSION), so everything that reaches file descriptor 1 from here on is sent to stderr and the
+    JSON line goes to the descriptor stdout had at start-up."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -670,7 +695,7 @@ def main():
             line["iwae_eval_5000is"] = ev
         if also is not None:
             line["also"] = also
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
