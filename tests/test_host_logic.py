@@ -87,6 +87,28 @@ def _worker(rank, world, port, n_images, S, out_dir):
         loss, _, _ = vdist.sharded_modl_iwae_step(fake_step, None, None, log_w[:, lo:hi], B)
         want_loss = -O.logmeanexp(log_w, 0).mean()
         assert abs(loss.item() - want_loss.item()) < 1e-12
+        # sample-sharded step (second row): every rank holds S / world samples of ALL images; the oracle stands
+        # in for the kernels (ll_fn / bwd_fn are plain callables) and the result must equal the unsharded objective
+        S2, B2, H2, W2, M2 = 6, 3, 2, 2, 3
+        p_all = torch.randn(S2, B2, H2, W2, 10 * M2, generator=g, dtype=torch.float64)
+        x01 = torch.randint(0, 256, (B2, H2, W2, 3), generator=g).double() / 255.0
+        extra_all = torch.randn(S2, B2, generator=g, dtype=torch.float64)
+        s_lo, s_hi = vdist.shard_bounds(S2, rank, world)
+
+        def ll_fn(p, x):
+            return O.modl_log_prob(p, x).sum((-1, -2, -3)).detach()
+
+        def bwd_fn(p, x, g_img):
+            q = p.clone().requires_grad_(True)
+            (O.modl_log_prob(q, x).sum((-1, -2, -3)) * g_img.double()).sum().backward()
+            return q.grad
+
+        loss_s, _, dp_s = vdist.sample_sharded_iwae_step(ll_fn, bwd_fn, p_all[s_lo:s_hi], x01, extra_all[s_lo:s_hi], S2)
+        q_all = p_all.clone().requires_grad_(True)
+        full = -O.logmeanexp(O.modl_log_prob(q_all, x01).sum((-1, -2, -3)) + extra_all, 0).mean()
+        full.backward()
+        assert abs(loss_s.item() - full.item()) <= 1e-6 * abs(full.item())
+        assert torch.allclose(dp_s, q_all.grad[s_lo:s_hi], rtol=1e-5, atol=1e-9)   # g_ll passes through float32
         torch.save(llh, os.path.join(out_dir, f"llh{rank}.pt"))
     finally:
         dist.destroy_process_group()

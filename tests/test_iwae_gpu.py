@@ -308,3 +308,21 @@ def test_one_launch_step_equals_three_launch_step(built_lib, monkeypatch, S, B, 
     assert c[-1] == 1
     assert torch.allclose(c[4] * 4.0, a[4], rtol=1e-6, atol=0) and abs(c[3].item() * 4.0 - a[3].item()) <= 1e-5 * abs(a[3].item())
     assert torch.allclose(c[5] * 4.0, a[5], rtol=1e-5, atol=1e-12)
+
+
+def test_sample_sharded_step_single_process(built_lib):
+    """dist.sample_sharded_iwae_step with the real kernels as ll_fn / bwd_fn (world size 1): equals the fused step; the
+    two-rank exchange itself is covered by the gloo test (tests/test_host_logic.py) and tools/nccl_split_s_check.py."""
+    from vae_mdl_b200 import dist as vdist, functional as F
+    S, B, H, W, M = 6, 3, 8, 8, 10
+    g = torch.Generator().manual_seed(606)
+    params = torch.randn(S, B, H, W, 10 * M, generator=g).to(DEV)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).to(DEV)
+    ll = F.modl_log_likelihood(params, x_u8, dtype=torch.float64)
+    extra = (ll.mean(0, keepdim=True) - ll).float() + torch.randn(S, B, generator=g).to(DEV)
+    ref = F.modl_iwae_step(params, x_u8, extra)
+    loss, lpxz, dp = vdist.sample_sharded_iwae_step(lambda p, x: F.modl_log_likelihood(p, x, dtype=torch.float64),
+                                                    lambda p, x, gi: F.modl_backward(p, x, g_image=gi), params, x_u8, extra, S)
+    assert torch.equal(lpxz, ref[0])
+    assert abs(loss.item() + ref[3].item()) <= 1e-6 * abs(ref[3].item())
+    assert relnorm(dp, ref[5]) <= 1e-5

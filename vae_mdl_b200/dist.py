@@ -5,6 +5,10 @@ until the log-mean-exp over samples, and test images are independent of each oth
 
 * training shapes: split the BATCH across ranks -- every rank holds all S samples of its images, so the log-mean-exp
   and its gradient are rank-local; the only exchange is one scalar all-reduce of the partial ELBO sums.
+* training shapes with fewer images than ranks (or to balance): split the IMPORTANCE SAMPLES instead -- every rank holds
+  S / world samples of ALL images; the log-mean-exp over s then needs one exchange of a (max, sum-exp) pair per image
+  (``all_gather`` of ``2 * B`` float64), after which value, ELBO and the softmax weights of the local samples are
+  rank-local again (``sample_sharded_iwae_step``).
 * 5000-sample evaluation (models/model05.py:168-176): images round-robin over ranks, S streamed in chunks into a
   per-image float64 buffer, ONE all-gather of the per-image results at the very end -- no per-image host sync.
 
@@ -19,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["init_from_env", "shard_bounds", "round_robin", "gather_round_robin", "allreduce_sum", "IwaeEvaluator",
-           "sharded_modl_iwae_step"]
+           "sharded_modl_iwae_step", "combine_lme_over_ranks", "sample_sharded_iwae_step"]
 
 
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
@@ -111,3 +115,44 @@ def sharded_modl_iwae_step(step_fn: Callable, params_shard, x_shard, extra_shard
     loss, lpxz, dparams = step_fn(params_shard, x_shard, extra_shard, True, b_total)
     loss = allreduce_sum(loss.clone(), group)
     return loss, lpxz, dparams
+
+
+def combine_lme_over_ranks(log_w_local: torch.Tensor, s_total: int, group=None):
+    """Log-mean-exp over an importance-sample axis that is split across ranks (utils/utils.py:9-11 with the samples of
+    axis 0 spread over the group).  ``log_w_local [S_local, B]`` (float64 recommended).  One ``all_gather`` of ``[2, B]``
+    per rank: the local maximum and the local ``sum_s exp(log_w - max)``.  Returns ``(lme [B], weights [S_local, B])``
+    with ``weights = softmax over ALL ``s_total`` samples, restricted to the local ones`` (what the gradient of the
+    log-mean-exp needs).  Every rank gets bit-identical ``lme`` (the ranks' pairs are combined in rank order)."""
+    mx = log_w_local.amax(0)
+    sm = torch.exp(log_w_local - mx).sum(0)
+    pair = torch.stack([mx, sm])                                                  # [2, B]
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        flat = torch.empty(world * pair.numel(), dtype=pair.dtype, device=pair.device)
+        dist.all_gather_into_tensor(flat, pair.reshape(-1).contiguous(), group=group)
+        allp = flat.reshape((world,) + tuple(pair.shape))
+    else:
+        allp = pair[None]
+    gmax = allp[:, 0].amax(0)
+    gsum = (allp[:, 1] * torch.exp(allp[:, 0] - gmax)).sum(0)                     # rank order: identical everywhere
+    lme = gmax + torch.log(gsum / float(s_total))                                 # utils/utils.py:11
+    weights = torch.exp(log_w_local - gmax) / gsum
+    return lme, weights
+
+
+def sample_sharded_iwae_step(ll_fn: Callable, bwd_fn: Callable, params_shard, x, extra_shard, s_total: int, group=None):
+    """One IWAE observation-model step with the IMPORTANCE SAMPLES split across ranks (second row): this rank
+    holds ``params_shard [S_local, B, H, W, 10M]`` -- its samples of every image -- and ``extra_shard [S_local, B]``.
+
+    ``ll_fn(params, x) -> [S_local, B]`` float64 per-image log-likelihoods (``functional.modl_log_likelihood(...,
+    dtype=torch.float64)``), ``bwd_fn(params, x, g_image) -> dparams`` (``functional.modl_backward``).
+    Returns ``(loss = -elbo, lpxz [S_local, B], dparams_shard)``; the loss is the GLOBAL loss on every rank (no further
+    collective), the gradient is the rank's own slice of the global gradient."""
+    lpxz = ll_fn(params_shard, x)
+    log_w = lpxz.double() + (extra_shard.double() if extra_shard is not None else 0.0)  # models/loss.py:34
+    lme, weights = combine_lme_over_ranks(log_w, s_total, group)
+    B = log_w.shape[1]
+    elbo = lme.mean()                                                             # models/loss.py:37
+    g_ll = (-weights / B).float()                                                 # d(-elbo) / d lpxz
+    dparams = bwd_fn(params_shard, x, g_ll.contiguous())
+    return (-elbo).reshape(1).float(), lpxz, dparams
