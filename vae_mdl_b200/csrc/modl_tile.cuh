@@ -1,0 +1,445 @@
+#pragma once
+// modl_tile.cuh -- the tiled kernel for n_mix = MC * LPP (5, 10, 20, 30) and the one-launch cooperative step built on it.
+// Part of the MoDL kernel family; see modl_kernels.cuh for the overview.
+#include "modl_core.cuh"
+
+namespace vaemdl {
+
+// ---- the tiled kernel -------------------------------------------------------------------------------------------------
+// M = MC * LPP mixtures; LPP lanes share a pixel, each owning MC consecutive components, processed two at a time.
+template <int MC, int LPP>
+struct Tile {
+  static constexpr int M = MC * LPP;
+  static constexpr int PPT = 32 / LPP;  // pixels per warp tile
+  static constexpr int ROWF = 10 * M;
+  static constexpr int TILE_F = PPT * ROWF;
+  static constexpr int TILE_B = TILE_F * 4;
+  static constexpr int AUX_F = PPT * M;  // backward: W*P per (pixel, component)
+  static constexpr int NPAIR = (MC + 1) / 2;
+  static constexpr bool ALIGNED = (M % 2 == 0) && (MC % 2 == 0);  // component pairs sit on 8-byte boundaries
+  static_assert(TILE_B % 16 == 0, "bulk copies need 16-byte multiples");
+};
+
+// a pair of consecutive floats at row[off], row[off+1]; `single`: only row[off] exists (odd MC), both halves get it
+template <bool ALIGNED>
+__device__ __forceinline__ f2 ld_pair(const float* row, int off, bool single) {
+  if constexpr (ALIGNED) {
+    const float2 t = *reinterpret_cast<const float2*>(row + off);
+    return pk(t.x, t.y);
+  } else {
+    const float a = row[off];
+    const float b = single ? a : row[off + 1];
+    return pk(a, b);
+  }
+}
+template <bool ALIGNED>
+__device__ __forceinline__ void st_pair(float* row, int off, bool single, f2 v) {
+  if constexpr (ALIGNED) {
+    *reinterpret_cast<float2*>(row + off) = make_float2(lo(v), hi(v));
+  } else {
+    row[off] = lo(v);
+    if (!single) row[off + 1] = hi(v);
+  }
+}
+
+struct PixRaw {
+  unsigned v[3];
+};
+__device__ __forceinline__ PixRaw load_pixel_raw(const ModlArgs& a, long long n, int pix) {
+  const long long xb = a.x_batch == 1 ? 0 : (n < a.x_batch ? n : n % a.x_batch);
+  const long long xo = (xb * a.HW + pix) * 3;
+  PixRaw r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    r.v[c] = a.x_u8 ? static_cast<unsigned>(static_cast<const uint8_t*>(a.x)[xo + c])
+                    : __float_as_uint(static_cast<const float*>(a.x)[xo + c]);
+  return r;
+}
+__device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r, Pixel& px) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = a.x_u8 ? u8_to_unit(r.v[c]) : __uint_as_float(r.v[c]);  // utils/data.py:15-16
+    if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);                                                  // utils/mdl.py:65
+    px.x[c] = v;
+    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
+    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+  }
+}
+
+// FUSED: the forward and the backward pass of one step run inside ONE cooperative kernel (modl_step_kernel): both use
+// the backward shared-memory layout, the mbarrier is initialised once and its phase carries over, the forward pass
+// leaves its last tile in the slot and the (reversed) backward pass starts on it without loading anything.
+// PD = 1: bfloat16 parameters / gradient in global memory (widened / narrowed in place in the slot, see widen_bf16_inplace)
+template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED, int PD = 0>
+__device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem_raw) {
+  using T = Tile<MC, LPP>;
+  constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F, NPAIR = T::NPAIR;
+  constexpr bool AL = T::ALIGNED;
+  constexpr int WARP_F = NSLOT * TILE_F + ((BWD || FUSED) ? T::AUX_F : 0);
+  static_assert(!FUSED || NSLOT == 1, "the fused step keeps one slot per warp");
+  static_assert(PD == 0 || (NSLOT == 1 && !FUSED), "bf16 parameters: one slot per warp, three-launch step");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
+  float* aux = slots + NSLOT * TILE_F;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp * NSLOT;
+
+  if constexpr (!(FUSED && BWD)) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NSLOT; ++s) mbar_init(&bars[s], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+  }
+  if constexpr (!FUSED) {
+    if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+    if constexpr (BWD)
+      pdl_wait();     // launched programmatically behind the finish kernel: g_image (and, in general, the parameters) must be complete
+    else
+      pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
+  }
+
+  const long long gw = run_index(a, warp, nwarps);
+  const bool lane_used = (lane / LPP) < PPT;
+  const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
+  const int sub = lane % LPP;
+  const int m0 = sub * MC;
+
+  // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
+  // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
+  const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
+  const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
+
+  auto tile_rows = [&](long long t) -> int {
+    const long long rem = a.n_px - t * PPT;
+    return rem < PPT ? static_cast<int>(rem) : PPT;
+  };
+  // bring tile t into slot s (bulk copy when the byte count allows it, plain loads for a ragged tail tile)
+  const long long t_cnt = t_end - t_begin;
+  const bool rev = BWD && a.reverse;
+  const long long t_first = rev ? t_end - 1 : t_begin;
+  const long long t_dir = rev ? -1 : 1;
+  const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
+  auto issue = [&](long long t, int s) {
+    const int rows = tile_rows(t);
+    const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+    const char* src = reinterpret_cast<const char*>(a.params) + t * TILE_F * (PD ? 2 : 4);
+    float* slot_f = slots + s * TILE_F;
+    char* dst = reinterpret_cast<char*>(slot_f) + (PD ? bytes : 0u);  // bf16 lands behind the room its float32 image needs
+    if ((bytes & 15u) == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        if (BWD) {
+          if (a.bwd_hint & 1)
+            bulk_g2s_hint(dst, src, bytes, &bars[s], pol_first);
+          else
+            bulk_g2s(dst, src, bytes, &bars[s]);
+        } else {
+          if (a.keep_tiles > 0)
+            bulk_g2s_hint(dst, src, bytes, &bars[s], (t_end - t) <= a.keep_tiles ? pol_last : pol_first);
+          else
+            bulk_g2s(dst, src, bytes, &bars[s]);
+        }
+      }
+    } else {
+      for (int i = lane; i < rows * ROWF; i += 32)
+        slot_f[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
+    }
+  };
+
+  // forward: every slot is in flight from the start; backward: slots are refilled one tile ahead (see below);
+  // fused backward: the first tile (the forward pass's last) is already in the slot
+  if constexpr (!(FUSED && BWD)) {
+#pragma unroll
+    for (int s = 0; s < (BWD ? 1 : NSLOT); ++s) {
+      if (s < t_cnt) issue(t_first + s * t_dir, s);
+    }
+  }
+  // loads this warp's barrier has completed before this pass (fused backward: the whole forward pass but the resident tile)
+  const uint32_t phase0 = (FUSED && BWD) ? static_cast<uint32_t>(t_cnt - 1) : 0u;
+
+  // (image, pixel-in-image) of this lane's pixel-sample, advanced incrementally: one 64-bit division per kernel
+  const long long step_n = PPT / a.HW;
+  const int step_pix = static_cast<int>(PPT - step_n * a.HW);
+  long long n_own = (t_first * PPT + p) / a.HW;
+  int pix_own = static_cast<int>((t_first * PPT + p) - n_own * a.HW);
+  // float64 running sums of the image the warp is in (acc0, image n_base) and of the next one (acc1), per lane
+  double acc0 = 0.0, acc1 = 0.0;
+  const long long n_warp_first = (t_begin * PPT) / a.HW;
+  long long n_base = n_warp_first;
+
+  // software prefetch of the (L2-resident) pixel and upstream-gradient values one tile ahead
+  auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
+                   float& g_out) {
+    const int rows = tile_rows(t);
+    const long long n_first = __shfl_sync(kFull, n_lane, 0);
+    const int pix_first = __shfl_sync(kFull, pix_lane, 0);
+    const bool in = p < rows;  // lanes past a ragged last tile shadow the tile's first pixel
+    const long long n = in ? n_lane : n_first;
+    const int pix = in ? pix_lane : pix_first;
+    raw = load_pixel_raw(a, n, pix);
+    g_out = 0.0f;
+    if constexpr (BWD) {
+      if (a.g_image) g_out = a.g_image[n];
+      if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+    }
+    n_out = n;
+    nfirst_out = n_first;
+  };
+
+  long long n_cur = 0, nfirst_cur = 0;
+  PixRaw raw_cur{};
+  float g_cur = 0.0f;
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+
+  for (long long it = 0; it < t_cnt; ++it) {
+    const long long t = t_first + it * t_dir;
+    const int s = static_cast<int>(it % NSLOT);
+    const uint32_t parity = (phase0 + static_cast<uint32_t>(it / NSLOT)) & 1u;
+    const int rows = tile_rows(t);
+    const int pp = p < rows ? p : 0;
+    const bool active = lane_used && (p < rows);
+    const long long i = t * PPT + pp;  // this lane's pixel-sample
+    const long long n = n_cur, n_first = nfirst_cur;
+    const float g = g_cur;
+    Pixel px;
+    decode_pixel(a, raw_cur, px);
+    // advance the index and prefetch the next tile's pixel / upstream gradient
+    if (!rev) {
+      n_own += step_n;
+      pix_own += step_pix;
+      if (pix_own >= a.HW) {
+        pix_own -= a.HW;
+        ++n_own;
+      }
+    } else {
+      n_own -= step_n;
+      pix_own -= step_pix;
+      if (pix_own < 0) {
+        pix_own += a.HW;
+        --n_own;
+      }
+    }
+    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+
+    float* slot = slots + s * TILE_F;
+    float* rowp = slot + pp * ROWF;
+    float* auxp = aux + pp * M;
+    if (!(FUSED && BWD && it == 0)) mbar_wait(&bars[s], parity);
+    if constexpr (PD != 0) {
+      if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);  // (a ragged tile was widened by its loads)
+    }
+    if constexpr (BWD && NSLOT > 1) {
+      // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
+      // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
+      if (it + 1 < t_cnt) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        issue(t + t_dir, s ^ 1);
+      }
+    }
+
+    // W_m = exp(logit_m - max logit)
+    float lmax = rowp[m0];
+#pragma unroll
+    for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, rowp[m0 + m]);
+    lmax = group_max<LPP>(lmax, lane);
+
+    f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
+#pragma unroll 1
+    for (int pr = 0; pr < NPAIR; ++pr) {
+      const int m = m0 + 2 * pr;
+      const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+      f2 lg = ld_pair<AL>(rowp, m, single);
+      if (single) lg = pk(lo(lg), -INFINITY);  // the padding half gets zero weight
+      f2 mu[3], sc[3], kp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        mu[c] = ld_pair<AL>(rowp, (1 + 3 * c) * M + m, single);
+        sc[c] = ld_pair<AL>(rowp, (2 + 3 * c) * M + m, single);
+        kp[c] = ld_pair<AL>(rowp, (3 + 3 * c) * M + m, single);
+      }
+      const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
+      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+      f2 u[9];
+      f2 P;
+      if (narrow)
+        P = pair_eval<true, BWD, Pixel, AR>(px, mu, sc, kp, u);
+      else
+        P = pair_eval<false, BWD, Pixel, AR>(px, mu, sc, kp, u);
+      sumW2 = sumW2 + W;
+      sumWP2 = fma2(W, P, sumWP2);
+      if constexpr (BWD) {
+        // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip.
+        // Only lanes that own a real pixel write: shadow lanes (ragged tile, or lanes 30/31 when 3 lanes share a
+        // pixel) would otherwise race with the owner of pixel 0.
+        if (active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          st_pair<AL>(rowp, (1 + 3 * c) * M + m, single, u[3 * c + 0]);
+          st_pair<AL>(rowp, (2 + 3 * c) * M + m, single, u[3 * c + 1]);
+          st_pair<AL>(rowp, (3 + 3 * c) * M + m, single, u[3 * c + 2]);
+        }
+        st_pair<AL>(auxp, m, single, W * P);
+        }
+      }
+    }
+    const float S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
+    const float SW = group_sum<LPP>(lo(sumW2) + hi(sumW2), lane);
+    const bool tiny = !(S > kTinySum);  // also catches NaN
+    const float* grow = param_row(a, i, ROWF);
+
+    if constexpr (!BWD) {
+      if constexpr (PD != 0) fence_async_smem();  // the widening wrote the slot through the generic proxy
+      __syncwarp();
+      {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
+        if (it + NSLOT < t_cnt) issue(t + NSLOT * t_dir, s);
+      }
+      float lp = (lg2_split(S) - lg2_split(SW)) * kLn2;  // utils/mdl.py:78-89 in one step
+      if (tiny) {
+        float lt, ll;
+        modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
+        lp = lt - ll;
+      }
+      const bool owner = active && sub == 0;
+      if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
+      const float val = owner ? lp : 0.0f;
+      if (a.partial) {
+        // float64 from here on: the per-image sums (~ -2e4 nats) feed a softmax over importance samples.
+        // A tile holds pixels of at most two images (HW >= PPT on this route): n_first and n_first + 1.
+        while (n_base < n_first) {  // the warp has left image n_base: its sum leaves the registers (warp-uniform)
+          const double done = warp_sum(acc0);
+          if (lane == 0) a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = done;
+          acc0 = acc1;
+          acc1 = 0.0;
+          ++n_base;
+        }
+        if (n == n_base)
+          acc0 += static_cast<double>(val);
+        else
+          acc1 += static_cast<double>(val);
+      } else if (a.ll_atomic) {
+        if (owner) atomicAdd(a.ll_atomic + n, static_cast<double>(val));
+      }
+    } else {
+      const float rS = rcpa(S), rSW = rcpa(SW);
+      float lt = 0.f, ll = 0.f;
+      if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
+#pragma unroll 1
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int m = m0 + 2 * pr;
+        const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+        f2 lg = ld_pair<AL>(rowp, m, single);
+        const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+        const f2 wp = ld_pair<AL>(auxp, m, single);
+        f2 r = wp * rS;     // posterior responsibility of the component
+        f2 pi = W * rSW;    // softmax(logits)
+        if (tiny) {
+          r = pk(expf(modl_logt(grow, M, m, px, a.plain != 0, PD != 0) - lt),
+                 single ? 0.0f : expf(modl_logt(grow, M, m + 1, px, a.plain != 0, PD != 0) - lt));
+          pi = pk(expf(ld_param(grow, m, PD != 0) - ll), single ? 0.0f : expf(ld_param(grow, m + 1, PD != 0) - ll));
+        }
+        const f2 gr = r * g;
+        if (active) {
+          st_pair<AL>(rowp, m, single, (r - pi) * g);
+#pragma unroll
+          for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + m, single, ld_pair<AL>(rowp, j * M + m, single) * gr);
+        }
+      }
+      // hand the gradient tile to the TMA engine
+      const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
+      char* dst = reinterpret_cast<char*>(a.dparams) + t * TILE_F * (PD ? 2 : 4);
+      if ((bytes & 15u) == 0) {
+        if constexpr (PD != 0) {
+          __syncwarp();
+          narrow_bf16_inplace(slot, rows * ROWF, lane);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (a.bwd_hint & 2)
+            bulk_s2g_hint(dst, slot, bytes, pol_first);
+          else
+            bulk_s2g(dst, slot, bytes);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+        for (int q = lane; q < rows * ROWF; q += 32) {
+          if (PD)
+            reinterpret_cast<unsigned short*>(dst)[q] = f32_to_bf16_bits(slot[q]);
+          else
+            reinterpret_cast<float*>(dst)[q] = slot[q];
+        }
+        __syncwarp();
+      }
+      if constexpr (NSLOT == 1) {
+        if (it + 1 < t_cnt) {
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          issue(t + t_dir, 0);
+        }
+      }
+    }
+  }
+  if constexpr (BWD) {
+    if (lane == 0) bulk_wait_all<0>();
+  } else {
+    if (a.partial && t_begin < t_end) {
+      const long long n_last = (t_end * PPT < a.n_px ? t_end * PPT - 1 : a.n_px - 1) / a.HW;  // image of the warp's last pixel-sample
+      const double d0 = warp_sum(acc0), d1 = warp_sum(acc1);
+      if (lane == 0) {
+        a.partial[partial_slot(n_base, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d0;
+        if (n_base + 1 <= n_last) a.partial[partial_slot(n_base + 1, gw, a.HW, PPT, a.tw_base, a.tw_rem, a.K, a.small)] = d1;
+      }
+    }
+  }
+}
+
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0>
+__global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  tile_body<MC, LPP, BWD, NSLOT, AR, false, PD>(a, smem_raw);
+}
+
+// ---- one step in one launch: forward -> grid barrier -> per-image sums, log-mean-exp, softmax weights -> grid barrier ->
+// backward.  For training shapes small enough that launch boundaries and pipeline ramps dominate (BASELINE configs[0]:
+// 131 MB of parameters, ~4 tiles per warp): no launch gaps, one ramp instead of three, and each warp's last forward tile
+// is still in shared memory when its reversed backward run starts.  Cooperative launch (all CTAs co-resident).
+struct StepArgs {
+  ModlArgs a;
+  StepFinish f;
+};
+
+template <int MC, int LPP, int AR>
+__global__ void __launch_bounds__(512, 1) modl_step_kernel(const StepArgs sa) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = blockDim.x >> 5;
+  const long long gw = static_cast<long long>(blockIdx.x) * nwarps + (threadIdx.x >> 5);
+  const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
+  tile_body<MC, LPP, false, 1, AR, true>(sa.a, smem_raw);
+  __threadfence();
+  grid.sync();
+  step_finish(sa.f, gw, total_warps, lane);
+  __threadfence();
+  grid.sync();
+  if (sa.f.elbo && gw == total_warps - 1) {  // batch mean, fixed order (the last warp owns the shortest run)
+    double t = 0.0;
+    for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
+    t = warp_sum(t);
+    if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+  }
+  tile_body<MC, LPP, true, 1, AR, true>(sa.a, smem_raw);
+}
+
+static __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+
+}  // namespace vaemdl
