@@ -885,8 +885,19 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   if (launches) *launches = 1;
   void* args[] = {&sa};
   void* kern = kind == 1 ? reinterpret_cast<void*>(dl_step_kernel<true>) : reinterpret_cast<void*>(dl_step_kernel<false>);
-  return cuda_rc(cudaLaunchCooperativeKernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(256), args,
-                                             static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4, st));
+  rc = cuda_rc(cudaLaunchCooperativeKernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(256), args,
+                                           static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4, st));
+  if (rc == static_cast<int>(cudaErrorCooperativeLaunchTooLarge) || rc == static_cast<int>(cudaErrorLaunchOutOfResources)) {
+    // the grid cannot be co-resident right now: nothing was enqueued, run the three ordinary launches instead
+    cudaGetLastError();
+    if (launches) *launches = 3;
+    rc = vaemdl_dlogistic_iwae_fwd(loc, logscale, C, ld, x, x_dtype, S, B, B_total, x_batch, D, low, high, levels, extra,
+                                   ll_image, ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    return vaemdl_dlogistic_bwd(loc, logscale, C, ld, x, x_dtype, n_img, x_batch, D, low, high, levels, g_ll, nullptr, dloc,
+                                dlogscale, ld_out, stream);
+  }
+  return rc;
 }
 
 extern "C" int vaemdl_dlogistic_sample(const float* loc, const float* logscale, int C, int ld, const float* u,

@@ -667,13 +667,28 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   if (launches) *launches = 1;
   switch (M) {
     case 5:
-      return launch_step<5, 1, AR>(a, f, n_img, st);
+      rc = launch_step<5, 1, AR>(a, f, n_img, st);
+      break;
     case 10:
-      return launch_step<10, 1, AR>(a, f, n_img, st);
+      rc = launch_step<10, 1, AR>(a, f, n_img, st);
+      break;
     case 20:
-      return launch_step<10, 2, AR>(a, f, n_img, st);
+      rc = launch_step<10, 2, AR>(a, f, n_img, st);
+      break;
     default:
-      return launch_step<10, 3, AR>(a, f, n_img, st);
+      rc = launch_step<10, 3, AR>(a, f, n_img, st);
+      break;
   }
+  if (rc == static_cast<int>(cudaErrorCooperativeLaunchTooLarge) || rc == static_cast<int>(cudaErrorLaunchOutOfResources)) {
+    // the grid cannot be co-resident right now (another context holds SMs, MPS partition, ...): nothing was enqueued,
+    // the step runs as three ordinary launches instead
+    cudaGetLastError();
+    if (launches) *launches = 3;
+    rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st);
+  }
+  return rc;
 }
 }  // namespace vaemdl
