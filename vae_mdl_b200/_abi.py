@@ -129,7 +129,32 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw handle of the current CUDA stream of ``device`` (the fast private accessor when torch has it: this is called
+    for every kernel launch and ``torch.cuda.current_stream`` costs several microseconds)."""
+    try:
+        idx = device.index if isinstance(device, torch.device) and device.index is not None else torch.cuda.current_device()
+        return c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+    except AttributeError:  # pragma: no cover  (older / newer torch without the private accessor)
+        return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def on_device(device):
+    """Context that makes ``device`` current for the C-ABI calls inside it -- a no-op object when it already is (the common
+    case; ``torch.cuda.device`` costs a few microseconds per launch otherwise)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 def require_cuda(t: torch.Tensor, name: str) -> None:

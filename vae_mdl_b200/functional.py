@@ -85,7 +85,7 @@ class _ModlFn(torch.autograd.Function):
                 ll = torch.empty(lead, device=p.device, dtype=torch.float32)
             ws_bytes = L.vaemdl_modl_workspace_bytes(n_img, H, W)
             ws = torch.empty((ws_bytes + 7) // 8, device=p.device, dtype=torch.float64)
-        with torch.cuda.device(p.device):
+        with _abi.on_device(p.device):
             if plain:
                 if x_range != _abi.RANGE_UNIT or edge_mode != _abi.EDGE_MDL:
                     raise ValueError("the plain pixel mixture takes x in [0,1] and the <= -1 / >= 1 edge tests")
@@ -108,7 +108,7 @@ class _ModlFn(torch.autograd.Function):
         g = dense_f32(g, "upstream gradient")
         g_pixel, g_image = (g, None) if mode == "pixel" else (None, g)
         dp = torch.empty_like(p)
-        with torch.cuda.device(p.device):
+        with _abi.on_device(p.device):
             if plain:
                 check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(g_image),
                                                   ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
@@ -135,7 +135,7 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
     gi = dense_f32(g_image, "g_image") if g_image is not None else None
     gp = dense_f32(g_pixel, "g_pixel") if g_pixel is not None else None
     dp = torch.empty_like(p)
-    with torch.cuda.device(p.device):
+    with _abi.on_device(p.device):
         if plain:
             check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, ptr(gi), ptr(gp),
                                               ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
@@ -173,7 +173,7 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
     g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
     ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         if plain:
             check(L.vaemdl_modl_plain_iwae_fwd(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex), None,
                                                ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
@@ -216,7 +216,7 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
     n_launch = ctypes.c_int(0)
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         if plain:
             check(L.vaemdl_modl_plain_iwae_step(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex),
                                                 None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(dp),
@@ -296,7 +296,7 @@ class _DlFn(torch.autograd.Function):
                 ll = torch.empty(lead, device=loc.device, dtype=torch.float32)
             ws_bytes = L.vaemdl_dlogistic_workspace_bytes(n_img, D)
             ws = torch.empty((ws_bytes + 7) // 8, device=loc.device, dtype=torch.float64)
-        with torch.cuda.device(loc.device):
+        with _abi.on_device(loc.device):
             check(L.vaemdl_dlogistic_fwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D,
                                          float(low), float(high), float(levels), ptr(lp), ptr(ll), ptr(ll64), ptr(ws),
                                          ws_bytes, stream_ptr(loc.device)), "vaemdl_dlogistic_fwd")
@@ -323,7 +323,7 @@ class _DlFn(torch.autograd.Function):
             ld_out = C
             p_loc, p_ls = dloc.data_ptr(), dls.data_ptr()
         import ctypes
-        with torch.cuda.device(locd.device):
+        with _abi.on_device(locd.device):
             check(lib().vaemdl_dlogistic_bwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D, low, high,
                                              levels, ptr(g_image), ptr(g_elem), ctypes.c_void_p(p_loc),
                                              ctypes.c_void_p(p_ls), ld_out, stream_ptr(locd.device)),
@@ -370,7 +370,7 @@ def dlogistic_iwae_forward(loc, logscale, x, extra: Optional[torch.Tensor] = Non
     g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
     ws_bytes = L.vaemdl_dlogistic_workspace_bytes(S * B, D)
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         check(L.vaemdl_dlogistic_iwae_fwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, S, B, int(b_total), x_batch, D,
                                           float(low), float(high), float(levels), ptr(ex), None, ptr(ll64), ptr(log_w),
                                           ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes, stream_ptr(dev)),
@@ -417,7 +417,7 @@ def dlogistic_iwae_step(loc, logscale, x, extra: Optional[torch.Tensor] = None, 
     ws_bytes = L.vaemdl_dlogistic_workspace_bytes(S * B, D)
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
     n_launch = ctypes.c_int(0)
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         check(L.vaemdl_dlogistic_iwae_step(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, S, B, int(b_total), x_batch, D,
                                            float(low), float(high), float(levels), ptr(ex), None, ptr(ll64), ptr(log_w),
                                            ptr(lme_b), ptr(elbo), ptr(g_ll), ctypes.c_void_p(p_loc), ctypes.c_void_p(p_ls),
@@ -450,7 +450,7 @@ def dlogistic_backward(loc, logscale, x, g_image: torch.Tensor, low=-1.0, high=1
         dls = torch.empty(shape, device=locd.device, dtype=torch.float32)
         ld_out, p_loc, p_ls = C, dloc.data_ptr(), dls.data_ptr()
     import ctypes
-    with torch.cuda.device(locd.device):
+    with _abi.on_device(locd.device):
         check(lib().vaemdl_dlogistic_bwd(ptr(locd), ptr(lsd), C, ld, ptr(xd), x_dtype, n_img, x_batch, D, float(low),
                                          float(high), float(levels), ptr(gi), None, ctypes.c_void_p(p_loc),
                                          ctypes.c_void_p(p_ls), ld_out, stream_ptr(locd.device)), "vaemdl_dlogistic_bwd")
@@ -467,7 +467,7 @@ class _LmeFn(torch.autograd.Function):
         out = torch.empty(B, device=log_w2d.device, dtype=torch.float32)
         L = lib()
         fn = L.vaemdl_logmeanexp_fwd_f64 if log_w2d.dtype == torch.float64 else L.vaemdl_logmeanexp_fwd
-        with torch.cuda.device(log_w2d.device):
+        with _abi.on_device(log_w2d.device):
             check(fn(ptr(log_w2d), S, B, ptr(out), stream_ptr(log_w2d.device)), "vaemdl_logmeanexp_fwd")
         ctx.save_for_backward(log_w2d)
         return out
@@ -480,7 +480,7 @@ class _LmeFn(torch.autograd.Function):
         d = torch.empty(log_w2d.shape, device=log_w2d.device, dtype=torch.float32)
         L = lib()
         fn = L.vaemdl_logmeanexp_bwd_f64 if log_w2d.dtype == torch.float64 else L.vaemdl_logmeanexp_bwd
-        with torch.cuda.device(log_w2d.device):
+        with _abi.on_device(log_w2d.device):
             check(fn(ptr(log_w2d), ptr(g), S, B, ptr(d), stream_ptr(log_w2d.device)), "vaemdl_logmeanexp_bwd")
         return d.to(log_w2d.dtype)
 
@@ -515,7 +515,7 @@ def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: i
     elbo = torch.empty(1, device=ll.device, dtype=torch.float32)
     g_ll = torch.empty((S, B), device=ll.device, dtype=torch.float32)
     is64 = ll.dtype == torch.float64
-    with torch.cuda.device(ll.device):
+    with _abi.on_device(ll.device):
         check(lib().vaemdl_iwae_tail(None if is64 else ptr(ll), ptr(ll) if is64 else None, ptr(ex), S, B, int(b_total), ptr(log_w),
                                      ptr(lme_b), ptr(elbo), ptr(g_ll), stream_ptr(ll.device)), "vaemdl_iwae_tail")
     return log_w, lme_b, elbo, g_ll
@@ -551,7 +551,7 @@ def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, 
     x = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.float32)
     xq = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.uint8) if want_quantised else None
     idx = torch.empty(out_lead + (H, W), device=p.device, dtype=torch.uint8) if want_index else None
-    with torch.cuda.device(p.device):
+    with _abi.on_device(p.device):
         check(lib().vaemdl_modl_sample(ptr(p), ptr(um), ptr(ul), variant, out_range, n_rep, n_img, H, W, M, ptr(x),
                                        ptr(xq), ptr(idx), stream_ptr(p.device)), "vaemdl_modl_sample")
     outs = [x]
@@ -574,7 +574,7 @@ def dlogistic_sample(loc: torch.Tensor, logscale: torch.Tensor, u: torch.Tensor,
         raise ValueError("u must have shape [n..., *loc.shape]")
     out = torch.empty(ud.shape, device=loc.device, dtype=torch.float32)
     reps = ud.numel() // n_param
-    with torch.cuda.device(loc.device):
+    with _abi.on_device(loc.device):
         for r in range(reps):  # leading sample dims re-use the same parameters
             import ctypes
             off = r * n_param * 4
@@ -627,7 +627,7 @@ def latent_terms(terms, extra_in: Optional[torch.Tensor] = None):
     extra = torch.empty((S, B), device=dev, dtype=torch.float32)
     sums = torch.empty((len(terms), S, B), device=dev, dtype=torch.float32)
     ex = dense_f32(extra_in, "extra_in") if extra_in is not None else None
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         check(lib().vaemdl_latent_terms_fwd(arr, len(terms), S, B, ptr(ex), ptr(extra), ptr(sums), stream_ptr(dev)),
               "vaemdl_latent_terms_fwd")
     return extra, sums
@@ -649,7 +649,7 @@ def latent_terms_backward(terms, g_extra: torch.Tensor, share_dz=()):
     dsc = [torch.empty_like(k[2]) if k[2] is not None else None for k in keep]
     PP = ctypes.c_void_p * n
     mk = lambda lst: PP(*[t.data_ptr() if t is not None else None for t in lst])  # noqa: E731
-    with torch.cuda.device(dev):
+    with _abi.on_device(dev):
         check(lib().vaemdl_latent_terms_bwd(arr, n, S, B, ptr(g), mk(dz), mk(dloc), mk(dsc), stream_ptr(dev)),
               "vaemdl_latent_terms_bwd")
     shared = {j for _, j in share_dz}

@@ -76,11 +76,11 @@ def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
         kind, meta, p0, p1 = pxz._iwae_spec()
         loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, [(z, pz.loc, pz.scale, beta),      # :34
                                                                         (z, qzx.loc, qzx.scale, -beta)])
-        iwae_elbo = -loss.detach()
+        neg_elbo = loss.detach()
         lpz, lqzx = sums[0], sums[1]
         n_dims = float(math.prod(x.shape[1:]))                              # :42
-        return loss, {"iwae_elbo": iwae_elbo, "bpd": -iwae_elbo / (math.log(2.0) * n_dims), "lpxz": lpxz, "lqzx": lqzx,
-                      "lpz": lpz, "kl": -torch.mean(lpz - lqzx, dim=0)}
+        return loss, {"iwae_elbo": -neg_elbo, "bpd": neg_elbo * (1.0 / (math.log(2.0) * n_dims)), "lpxz": lpxz,  # :43
+                      "lqzx": lqzx, "lpz": lpz, "kl": torch.mean(lqzx - lpz, dim=0)}                                # :46
     lpz = torch.sum(pz.log_prob(z), dim=_axes(pz))                      # :28
     lqzx = torch.sum(qzx.log_prob(z), dim=_axes(qzx))                   # :30
     lpxz = _lpxz(pxz, x)                                                # :32
