@@ -83,8 +83,9 @@ VAEMDL_API const char* vaemdl_strerror(int code);
  * lp_pixel [n_img, H, W]   nullable -- per-pixel log-prob (what log_prob() returns, minus the trailing 1)
  * ll_image [n_img]         nullable -- sum over H,W of lp_pixel
  * ll_image_f64 [n_img]     nullable -- the same sum in float64.  The per-pixel values are float32, but they are
- *                          accumulated in float64 (fixed order for M in {5,10,20,30} and H*W >= 32, float64 atomics
- *                          otherwise): |ll| ~ 2e4 nats has a float32 ulp of 2e-3, which would go straight into the
+ *                          accumulated in float64 (fixed order whenever an image holds at least one tile of pixels --
+ *                          64 for n_mix 1..9, at most 32 otherwise -- float64 atomics for smaller images):
+ *                          |ll| ~ 2e4 nats has a float32 ulp of 2e-3, which would go straight into the
  *                          softmax over importance samples of the IWAE gradient.  Feed this to vaemdl_iwae_tail.
  * workspace: 8-byte aligned, at least vaemdl_modl_workspace_bytes(n_img, H, W) bytes (used when a sum is requested)
  * ------------------------------------------------------------------------ */
@@ -96,8 +97,8 @@ VAEMDL_API int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, 
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ *
- * MoDL forward fused with the IWAE tail: TWO launches (forward, finish) when S <= 512 and M in {5,10,20,30},
- * otherwise forward + per-image reduce + IWAE tail, for
+ * MoDL forward fused with the IWAE tail: TWO launches (forward, finish) when S <= 512 and an image holds at least one
+ * tile of pixels, otherwise forward + per-image reduce + IWAE tail, for
  *     lpxz = reduce_sum(pxz.log_prob(x), [-1,-2,-3])                    models/loss.py:32
  *     log_w = lpxz + extra ; lme_b = logmeanexp(log_w, axis=0)          models/loss.py:34-37, utils/utils.py:9-11
  *     elbo = sum_b lme_b / B_total ; g_ll = d(-elbo)/d lpxz = -softmax_s(log_w) / B_total
