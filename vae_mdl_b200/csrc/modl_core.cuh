@@ -361,8 +361,17 @@ __device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub
   o.den = den;
   if constexpr (BWD) {
     const f2 omA2 = (sp(1.0f) - A) * opA;
-    f2 nm = neg_sign_of_2(sel_2(il, ih, G * omA2, omA2), mid);
-    f2 nh = sel_2(il, ih, (h * -1.0f) * num_n, sp(0.0f));
+    // "value in the CDF-difference branch, 0 in the low-probability branch" as a multiplication by a 0/1 mask on the
+    // packed pipe: a select of a packed value costs the compiler four predicated moves (they were a quarter of the
+    // backward loop), the mask two compares.  Every masked quantity is finite (h <= e^7 / 255), so x * 0 is 0.
+    const f2 mi = pk(il ? 1.0f : 0.0f, ih ? 1.0f : 0.0f);
+    f2 gsel;  // G in the CDF-difference branch, 1 in the low-probability branch
+    if constexpr (NARROW)
+      gsel = sel_2(il, ih, G, sp(1.0f));
+    else
+      gsel = fma2(mi, omG * -1.0f, 1.0f);  // mi = 1: 1 - omG, the very expression G was formed with
+    f2 nm = neg_sign_of_2(gsel * omA2, mid);
+    f2 nh = mi * ((h * -1.0f) * num_n);
     const f2 h2 = h * h;
     f2 hc = fma2(h2, 2.0f / 945.0f, -1.0f / 45.0f);
     hc = fma2(h2, hc, 1.0f / 3.0f);
@@ -371,8 +380,8 @@ __device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub
       const f2 e = h * fma2(G, G, 1.0f) * rcp_2(rest_n);
       hc = sel_2(nl, nh_, e, hc);
     }
-    f2 c0 = sel_2(il, ih, hc, sp(0.0f));
-    f2 dir = sel_2(il, ih, sp(0.0f), sp(-1.0f));
+    f2 c0 = mi * hc;
+    f2 dir = mi + -1.0f;
     if (el || eh) {
       const f2 t = sel_2(ool, ooh, AG, G);
       nm = sel_2(el, eh, pk(e.ll ? lo(t) : -lo(t), e.lh ? hi(t) : -hi(t)), nm);
@@ -433,8 +442,8 @@ __device__ __forceinline__ f2 pair_eval(const PX& px, const f2 mu[3], const f2 s
       const f2 Dm = f[c].nm * rd[c];
       dloc[c] = (f[c].inv * -1.0f) * Dm;
       f2 dls = (f[c].dir - f[c].c0) - fma2(f[c].mid, Dm, f[c].nh * rd[c]);
-      // tf.maximum(logscale, -7): the gradient reaches logscale iff logscale >= -7
-      dls = sel_2(lo(s[c]) >= -7.0f, hi(s[c]) >= -7.0f, dls, sp(0.0f));
+      // tf.maximum(logscale, -7): the gradient reaches logscale iff logscale >= -7 (0/1 mask, see subpix2)
+      dls = dls * pk(lo(s[c]) >= -7.0f ? 1.0f : 0.0f, hi(s[c]) >= -7.0f ? 1.0f : 0.0f);
       u[3 * c + 0] = dloc[c];
       u[3 * c + 1] = dls;
     }
