@@ -86,3 +86,34 @@ def test_random_shapes_plain_dl(built_lib, S, B, H, W, M, interleaved, u8, seed)
     assert ((out[0].cpu() - ll64.detach()).abs() / ll64.detach().abs().clamp_min(1e-3)).max().item() <= LL_RTOL
     assert abs(-out[3].item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
     assert relnorm(out[5], loc64.grad) <= GRAD_RTOL and relnorm(out[6], ls64.grad) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("M", [3, 5, 10, 12, 16, 25])
+def test_broadcast_single_image_against_many_samples(built_lib, M):
+    """models/model05.py:173: x WITHOUT a batch dim scored against [S, 1, H, W, 10M] parameters (x_batch = 1), every
+    kernel family; the IWAE-class wrapper and the float-x path give the same numbers."""
+    from vae_mdl_b200 import functional as F
+    import vae_mdl_b200 as V
+    S, H, W = 37, 9, 7
+    params, x_u8, g = trained_like(4200 + M, S, 1, H, W, M)
+    x1 = x_u8[0]                                             # [H, W, 3]
+    p64 = params.double()
+    x64 = O.normalize_u8(x1, torch.float32).double()
+    lp = O.modl_log_prob(p64, x64)[..., 0]                   # broadcasting x over S and the batch dim of 1
+    ll64 = lp.sum((-1, -2))
+    ok = ~threshold_ambiguous(p64, x64[None])
+    if not bool(ok.any()):
+        pytest.skip("threshold-ambiguous draw")
+    pd = params.to(DEV)
+    ll_a = F.modl_log_likelihood(pd, x1.to(DEV), dtype=torch.float64).cpu()
+    ll_b = F.modl_log_likelihood(pd, O.normalize_u8(x1, torch.float32).to(DEV), dtype=torch.float64).cpu()
+    assert torch.equal(ll_a, ll_b)
+    assert ((ll_a - ll64).abs() / ll64.abs().clamp_min(1e-3))[ok].max().item() <= LL_RTOL
+    out = V.MixtureDiscretizedLogistic(pd).log_prob(O.normalize_u8(x1, torch.float32).to(DEV))
+    assert list(out.shape) == [S, 1, H, W, 1]
+    assert (((out[..., 0].cpu().double() - lp).abs() - 1e-6 * lp.abs()).flatten(2).amax(-1))[ok].max().item() < 5e-5
+    g_image = torch.randn(S, 1, generator=g)
+    q = p64.clone().requires_grad_(True)
+    (O.modl_log_prob(q, x64)[..., 0].sum((-1, -2)) * g_image.double()).sum().backward()
+    dp = F.modl_backward(pd, x1.to(DEV), g_image=g_image.to(DEV)).cpu().double()
+    assert relnorm(dp[ok], q.grad[ok]) <= GRAD_RTOL
