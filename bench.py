@@ -40,6 +40,7 @@ WORKLOADS = {
     "cfg1": ("modl", 5, 64, 32, 32, 10),
     "cfg1_m5": ("modl", 5, 128, 32, 32, 5),
     "cfg5_64_m5": ("modl", 16, 64, 64, 64, 5),
+    "cfg5_64_m20": ("modl", 16, 32, 64, 64, 20),
 }
 DEFAULT_WORKLOAD = "cfg5_64_m10"
 L2_BYTES = 126 * 1024 * 1024
@@ -195,23 +196,28 @@ class ModlStep:
         self.g_ll = torch.empty(S, B, device=dev)
         self.lme = torch.empty(B, device=dev)
         self.elbo = torch.empty(1, device=dev)
-        self.ws_bytes = self.L.vaemdl_modl_workspace_bytes(S * B, H, W)
+        self.ws_bytes = self.L.vaemdl_modl_step_workspace_bytes(S * B, H, W)
         self.ws = torch.empty(self.ws_bytes // 8 + 1, dtype=torch.float64, device=dev)
+        # (mixture sum, logit normaliser) per pixel-sample: written by the forward kernel, read by the backward kernel,
+        # which then scales every gradient in the pass that forms it (what vaemdl_modl_iwae_step does internally)
+        self.stats = torch.empty(S * B * H * W * 2, dtype=torch.float32, device=dev)
         self.stream = torch.cuda.current_stream(dev)
         self.st = ctypes.c_void_p(self.stream.cuda_stream)
         self.n_px = S * B * H * W
 
     def fwd(self):
         # forward kernel + fused finish kernel: lpxz (float64), log-mean-exp, elbo, g_ll = d(-elbo)/d lpxz
-        rc = self.L.vaemdl_modl_iwae_fwd(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B, self.b_total,
-                                         self.B, self.H, self.W, self.M, self.extra.data_ptr(), None,
-                                         self.ll64.data_ptr(), None, self.lme.data_ptr(), self.elbo.data_ptr(),
-                                         self.g_ll.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.st)
+        rc = self.L.vaemdl_modl_iwae_fwd_stats(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B,
+                                               self.b_total, self.B, self.H, self.W, self.M, self.extra.data_ptr(), None,
+                                               self.ll64.data_ptr(), None, self.lme.data_ptr(), self.elbo.data_ptr(),
+                                               self.g_ll.data_ptr(), self.stats.data_ptr(), self.ws.data_ptr(),
+                                               self.ws_bytes, self.st)
         assert rc == 0, rc
 
     def bwd(self):
-        rc = self.L.vaemdl_modl_bwd(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S * self.B, self.B, self.H,
-                                    self.W, self.M, self.g_ll.data_ptr(), None, self.dparams.data_ptr(), self.st)
+        rc = self.L.vaemdl_modl_bwd_stats(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S * self.B, self.B,
+                                          self.H, self.W, self.M, self.g_ll.data_ptr(), None, self.stats.data_ptr(),
+                                          self.dparams.data_ptr(), self.st)
         assert rc == 0, rc
 
     def next_input(self):

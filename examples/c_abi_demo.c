@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
   double* d_ll64;
   uint8_t* d_x;
   void* d_ws;
-  const size_t ws_bytes = vaemdl_modl_workspace_bytes(n_img, H, W);
+  const size_t ws_bytes = vaemdl_modl_step_workspace_bytes(n_img, H, W);
   CK(cudaMalloc((void**)&d_params, n_param * sizeof(float)));
   CK(cudaMalloc((void**)&d_dparams, n_param * sizeof(float)));
   CK(cudaMalloc((void**)&d_x, n_x));

@@ -124,6 +124,12 @@ VAEMDL_API int vaemdl_modl_iwae_fwd(const float* params, const void* x, int x_dt
  * finish, grid barrier, backward pass starting on the tile still resident in shared memory; anything else runs the
  * three launches of the calls above.  *launches (nullable) receives the number of kernel launches that were enqueued.
  * ------------------------------------------------------------------------ */
+/* workspace for vaemdl_modl_iwae_step: the forward workspace plus one (mixture sum, logit normaliser) float pair per
+ * pixel-sample, which the forward pass leaves for the backward pass so that the gradient of a component is scaled in the
+ * same pass that forms it (n_mix in {5, 10, 20, 30}; with a buffer of only vaemdl_modl_workspace_bytes the step still
+ * runs, with the two-pass gradient kernel). */
+VAEMDL_API size_t vaemdl_modl_step_workspace_bytes(long long n_img, int H, int W);
+
 VAEMDL_API int vaemdl_modl_iwae_step(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
                     int S, long long B, long long B_total, int x_batch, int H, int W, int M,
                     const float* extra,
@@ -142,6 +148,19 @@ VAEMDL_API int vaemdl_modl_iwae_step(const float* params, const void* x, int x_d
 VAEMDL_API int vaemdl_modl_bwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
                     long long n_img, int x_batch, int H, int W, int M,
                     const float* g_image, const float* g_pixel,
+                    float* dparams, void* stream);
+
+/* The two halves of vaemdl_modl_iwae_step as separate calls: pix_stats [n_img*H*W*2] floats (8-byte aligned) is written
+ * by the forward call and read by the backward call on the SAME params / x (n_mix in {5, 10, 20, 30}: one-pass gradient;
+ * any other n_mix ignores it and forms the sums again).  pix_stats = NULL: exactly vaemdl_modl_iwae_fwd / vaemdl_modl_bwd. */
+VAEMDL_API int vaemdl_modl_iwae_fwd_stats(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                    const float* extra,
+                    float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                    float* pix_stats, void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_bwd_stats(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                    long long n_img, int x_batch, int H, int W, int M,
+                    const float* g_image, const float* g_pixel, const float* pix_stats,
                     float* dparams, void* stream);
 
 /* ------------------------------------------------------------------------ *

@@ -30,6 +30,9 @@ struct ModlArgs {
   const float* g_image;  // nullable
   const float* g_pixel;  // nullable
   float* dparams;
+  float2* pix_stats;  // [n_px] nullable: (mixture sum S, logit normaliser SW) of every pixel-sample.  The forward kernel
+                      // writes them when given; a backward kernel instantiated with ST reads them and scales its gradients
+                      // in the same pass that forms them (no second pass over the row, no aux strip)
   unsigned* zero_me;  // nullable: a word the forward kernel clears for the fused finish kernel that follows it
   long long n_px;  // n_img * H * W
   long long num_tiles;

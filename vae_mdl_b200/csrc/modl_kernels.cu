@@ -15,6 +15,12 @@ extern "C" size_t vaemdl_modl_workspace_bytes(long long n_img, int H, int W) {
   return partial_elems(n_img) * sizeof(double) + static_cast<size_t>(n_img) * sizeof(double) + 256;
 }
 
+extern "C" size_t vaemdl_modl_step_workspace_bytes(long long n_img, int H, int W) {
+  if (n_img <= 0 || H <= 0 || W <= 0) return 0;
+  // the forward workspace + one (mixture sum, logit normaliser) pair per pixel-sample for the one-pass gradient
+  return vaemdl_modl_workspace_bytes(n_img, H, W) + static_cast<size_t>(n_img) * H * W * sizeof(float2);
+}
+
 extern "C" int vaemdl_modl_fwd(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
                                long long n_img, int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image,
                                double* ll_image_f64, void* workspace, size_t workspace_bytes, void* stream) {
@@ -72,4 +78,22 @@ extern "C" int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int 
                                     const float* g_pixel, void* dparams_bf16, void* stream) {
   return modl_bwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
                           g_image, g_pixel, static_cast<float*>(dparams_bf16), static_cast<cudaStream_t>(stream), 1);
+}
+
+// ---- forward / backward as two calls that share the per-pixel mixture sums (what vaemdl_modl_iwae_step does inside) -----------
+extern "C" int vaemdl_modl_iwae_fwd_stats(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
+                                          long long B, long long B_total, int x_batch, int H, int W, int M,
+                                          const float* extra, float* ll_image, double* ll_image_f64, float* log_w,
+                                          float* lme_b, float* elbo, float* g_ll, float* pix_stats, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  return modl_iwae_fwd_impl<0>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
+                               ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream), 0, pix_stats);
+}
+
+extern "C" int vaemdl_modl_bwd_stats(const float* params, const void* x, int x_dtype, int x_range, int edge_mode,
+                                     long long n_img, int x_batch, int H, int W, int M, const float* g_image,
+                                     const float* g_pixel, const float* pix_stats, float* dparams, void* stream) {
+  return modl_bwd_impl<0>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_image, g_pixel, dparams,
+                          static_cast<cudaStream_t>(stream), 0, pix_stats);
 }

@@ -68,18 +68,18 @@ struct TilePlan {  // how the forward grid split the tile range: what the per-im
   int K = 0, PPT = 0;
 };
 
-template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0>
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0, bool ST = false>
 static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* plan) {
   using T = Tile<MC, LPP>;
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
   const DeviceInfo& di = device_info();
-  const size_t per_warp = (static_cast<size_t>(NSLOT) * T::TILE_F + (BWD ? T::AUX_F : 0)) * 4 + NSLOT * 8;
+  const size_t per_warp = (static_cast<size_t>(NSLOT) * T::TILE_F + ((BWD && !ST) ? T::AUX_F : 0) + (ST ? 2 * T::PPT : 0)) * 4 + NSLOT * 8;
   if (warps > MAXT / 32) warps = MAXT / 32;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
   warps = pick_warps(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
-  auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT, AR, PD>;
+  auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT, AR, PD, ST>;
   // the function attribute and the occupancy query cost several microseconds of host time: once per (device, shape)
   static std::mutex mu;
   static int c_dev = -1, c_warps = -1, c_ctas = 1;
@@ -134,6 +134,9 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   // warps per scheduler rather than by a second slot per warp
   const Shape sh = tune_shape(BWD, Shape{1, 16});
   if (AR == 0 && sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256, 0>(a, sh.warps, st, plan);  // tuning only
+  if constexpr (BWD) {
+    if (a.pix_stats) return launch_tiled_shape<MC, LPP, true, 1, 512, AR, 0, true>(a, sh.warps, st, plan);  // one-pass gradient
+  }
   return launch_tiled_shape<MC, LPP, BWD, 1, 512, AR>(a, sh.warps, st, plan);
 }
 
@@ -143,7 +146,7 @@ static int launch_step(ModlArgs a, StepFinish f, long long n_img, cudaStream_t s
   using T = Tile<MC, LPP>;
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
   const DeviceInfo& di = device_info();
-  const size_t per_warp = (static_cast<size_t>(T::TILE_F) + T::AUX_F) * 4 + 8;
+  const size_t per_warp = (static_cast<size_t>(T::TILE_F) + 2 * T::PPT) * 4 + 8;  // (ST: the tile's (S, SW) pairs, no aux strip)
   int warps = 16;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
   warps = pick_warps(a.num_tiles, di.sm_count, warps);
@@ -402,10 +405,27 @@ static int spread_runs() {
   return !(e && e[0] == '0');
 }
 
+// Which separately launched kernels exchange per-pixel mixture sums between the forward and the backward pass
+// (ModlArgs::pix_stats -> one-pass gradient).  Measured on B200 (tools/fused_probe.py, VAEMDL_NO_STATS A/B): n_mix = 30 gains
+// 1-8 % and n_mix = 5 (32-row tiles) 4 %, n_mix = 10 / 20 LOSE 6-8 % -- with the second pass gone the warps spend 23 % of
+// their samples waiting for the next tile instead of 10 % -- so those keep the two-pass kernel.  VAEMDL_STATS=all / none
+// overrides (A/B).  The one-launch step (modl_step_kernel) always exchanges the sums.
+static bool stats_off() {
+  const char* e = getenv("VAEMDL_STATS");
+  return getenv("VAEMDL_NO_STATS") != nullptr || (e && e[0] == 'n');
+}
+static bool stats_supported(int M, long long n_px, bool bf16) {
+  if (stats_off() || bf16 || use_pixel_pairs(M, n_px, bf16)) return false;
+  const char* e = getenv("VAEMDL_STATS");
+  if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
+  return M == 5 || M == 30;
+}
+
 template <bool BWD, int AR>
 static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   a.plain = AR;
   a.spread = spread_runs();
+  if (!stats_supported(a.M, a.n_px, a.bf16 != 0)) a.pix_stats = nullptr;
   if (use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
     switch (a.M) {
       case 1: return launch_pp<1, BWD, AR>(a, st, plan);
@@ -478,7 +498,8 @@ namespace vaemdl {
 template <int AR>
 static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image, double* ll_image_f64,
-                         const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0) {
+                         const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0,
+                         float* pix_stats = nullptr) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   const bool iwae = iw.S > 0;
@@ -497,6 +518,7 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
   a.bf16 = bf16;
+  a.pix_stats = reinterpret_cast<float2*>(pix_stats);
   const int ppt = tile_ppt(M, a.n_px, bf16 != 0);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
   char* ws = static_cast<char*>(workspace);
@@ -539,7 +561,7 @@ namespace vaemdl {
 template <int AR>
 static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, const float* g_image, const float* g_pixel, float* dparams,
-                         cudaStream_t st, int bf16 = 0) {
+                         cudaStream_t st, int bf16 = 0, const float* pix_stats = nullptr) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   if (!dparams || (!g_image && !g_pixel)) return VAEMDL_EINVAL;
@@ -558,6 +580,8 @@ static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.edge_openai = edge_mode == VAEMDL_EDGE_OPENAI;
   a.M = M;
   a.bf16 = bf16;
+  a.pix_stats = reinterpret_cast<float2*>(const_cast<float*>(pix_stats));
+  if (pix_stats && (reinterpret_cast<uintptr_t>(pix_stats) & 7u)) return VAEMDL_EALIGN;
   return launch_modl<true, AR>(a, st);
 }
 
@@ -565,8 +589,10 @@ template <int AR>
 static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
                               long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
                               float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
-                              void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0) {
+                              void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0,
+                              float* pix_stats = nullptr) {
   if (S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
+  if (pix_stats && (reinterpret_cast<uintptr_t>(pix_stats) & 7u)) return VAEMDL_EALIGN;
   if (elbo && !lme_b) return VAEMDL_EINVAL;
   IwaeOut iw;
   iw.S = S;
@@ -578,7 +604,7 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
   iw.elbo = elbo;
   iw.g_ll = g_ll;
   return modl_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
-                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16);
+                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16, pix_stats);
 }
 }  // namespace vaemdl
 
@@ -625,17 +651,24 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   if (reinterpret_cast<uintptr_t>(dparams) & 15u) return VAEMDL_EALIGN;
   const int HW = H * W;
   const long long n_px = n_img * HW;
-  if (!fused_eligible(S, n_px, HW, M)) {
-    if (launches) *launches = 3;
-    rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
-                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st);
-    if (rc) return rc;
-    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st);
-  }
   const size_t need = vaemdl_modl_workspace_bytes(n_img, H, W);
   if (!workspace || workspace_bytes < need) return VAEMDL_EWORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
   char* ws = static_cast<char*>(workspace);
+  // per-pixel mixture sums handed from the forward to the backward pass (one-pass gradient): behind the forward
+  // workspace, when the caller sized the buffer with vaemdl_modl_step_workspace_bytes and the kernels support it
+  const bool room = workspace_bytes >= need + static_cast<size_t>(n_px) * sizeof(float2);
+  const bool fused = room && !stats_off() && fused_eligible(S, n_px, HW, M);  // (implies n_mix in {5, 10, 20, 30})
+  float* stats = nullptr;
+  if (room && (fused || stats_supported(M, n_px, false))) stats = reinterpret_cast<float*>(ws + need);
+  if (!fused) {
+    if (launches) *launches = 3;
+    rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats);
+    if (rc) return rc;
+    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st, 0,
+                             stats);
+  }
   ModlArgs a{};
   a.params = params;
   a.x = x;
@@ -651,6 +684,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   a.M = M;
   a.plain = AR;
   a.spread = spread_runs();
+  a.pix_stats = reinterpret_cast<float2*>(stats);
   StepFinish f{};
   f.extra = extra;
   f.ll = ll_image;
@@ -685,9 +719,10 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
     cudaGetLastError();
     if (launches) *launches = 3;
     rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
-                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st);
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats);
     if (rc) return rc;
-    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st);
+    return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st, 0,
+                             stats);
   }
   return rc;
 }

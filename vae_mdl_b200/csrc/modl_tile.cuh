@@ -70,17 +70,22 @@ __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r,
 // the backward shared-memory layout, the mbarrier is initialised once and its phase carries over, the forward pass
 // leaves its last tile in the slot and the (reversed) backward pass starts on it without loading anything.
 // PD = 1: bfloat16 parameters / gradient in global memory (widened / narrowed in place in the slot, see widen_bf16_inplace)
-template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED, int PD = 0>
+// ST: the backward pass takes every pixel's mixture sums from a.pix_stats (written by the forward pass of the same step)
+// instead of forming them itself: the gradient of a component is scaled as soon as it is computed -- one pass over the
+// row, no aux strip.  (The forward body of a FUSED step is instantiated with the same ST: both share the slot layout.)
+template <int MC, int LPP, bool BWD, int NSLOT, int AR, bool FUSED, int PD = 0, bool ST = false>
 __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem_raw) {
   using T = Tile<MC, LPP>;
   constexpr int M = T::M, PPT = T::PPT, ROWF = T::ROWF, TILE_F = T::TILE_F, NPAIR = T::NPAIR;
   constexpr bool AL = T::ALIGNED;
-  constexpr int WARP_F = NSLOT * TILE_F + ((BWD || FUSED) ? T::AUX_F : 0);
+  // ST: instead of the aux strip the slot is followed by the tile's (S, SW) pairs, which travel with the tile (bulk copy)
+  constexpr int STAT_F = 2 * PPT;
+  constexpr int WARP_F = NSLOT * TILE_F + (((BWD || FUSED) && !ST) ? T::AUX_F : 0) + (ST ? STAT_F : 0);
   static_assert(!FUSED || NSLOT == 1, "the fused step keeps one slot per warp");
   static_assert(PD == 0 || (NSLOT == 1 && !FUSED), "bf16 parameters: one slot per warp, three-launch step");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
-  float* aux = slots + NSLOT * TILE_F;
+  float* aux = slots + NSLOT * TILE_F;   // (ST: the tile's (S, SW) pairs live here)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp * NSLOT;
 
   if constexpr (!(FUSED && BWD)) {
@@ -126,9 +131,11 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const char* src = reinterpret_cast<const char*>(a.params) + t * TILE_F * (PD ? 2 : 4);
     float* slot_f = slots + s * TILE_F;
     char* dst = reinterpret_cast<char*>(slot_f) + (PD ? bytes : 0u);  // bf16 lands behind the room its float32 image needs
-    if ((bytes & 15u) == 0) {
+    [[maybe_unused]] const uint32_t sbytes = static_cast<uint32_t>(rows) * 8u;  // the tile's (S, SW) pairs (BWD && ST)
+    if ((bytes & 15u) == 0 && (!(BWD && ST) || (sbytes & 15u) == 0)) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(&bars[s], bytes);
+        mbar_arrive_expect_tx(&bars[s], bytes + ((BWD && ST) ? sbytes : 0u));
+        if constexpr (BWD && ST) bulk_g2s(aux, a.pix_stats + t * PPT, sbytes, &bars[s]);
         if (BWD) {
           if (a.bwd_hint & 1)
             bulk_g2s_hint(dst, src, bytes, &bars[s], pol_first);
@@ -144,6 +151,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     } else {
       for (int i = lane; i < rows * ROWF; i += 32)
         slot_f[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+      if constexpr (BWD && ST) {
+        if (lane < rows) reinterpret_cast<float2*>(aux)[lane] = a.pix_stats[t * PPT + lane];
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
     }
@@ -172,7 +182,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
 
   // software prefetch of the (L2-resident) pixel and upstream-gradient values one tile ahead
   auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
-                   float& g_out) {
+                   float& g_out, float2& st_out) {
     const int rows = tile_rows(t);
     const long long n_first = __shfl_sync(kFull, n_lane, 0);
     const int pix_first = __shfl_sync(kFull, pix_lane, 0);
@@ -185,6 +195,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       if (a.g_image) g_out = a.g_image[n];
       if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
     }
+    (void)st_out;
     n_out = n;
     nfirst_out = n_first;
   };
@@ -192,7 +203,8 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   long long n_cur = 0, nfirst_cur = 0;
   PixRaw raw_cur{};
   float g_cur = 0.0f;
-  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+  float2 st_cur = make_float2(1.0f, 1.0f);
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
 
   for (long long it = 0; it < t_cnt; ++it) {
     const long long t = t_first + it * t_dir;
@@ -204,6 +216,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const long long i = t * PPT + pp;  // this lane's pixel-sample
     const long long n = n_cur, n_first = nfirst_cur;
     const float g = g_cur;
+    const float2 st = st_cur;
     Pixel px;
     decode_pixel(a, raw_cur, px);
     // advance the index and prefetch the next tile's pixel / upstream gradient
@@ -222,12 +235,18 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         --n_own;
       }
     }
-    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur);
+    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
 
     float* slot = slots + s * TILE_F;
     float* rowp = slot + pp * ROWF;
     float* auxp = aux + pp * M;
     if (!(FUSED && BWD && it == 0)) mbar_wait(&bars[s], parity);
+    if constexpr (FUSED && BWD && ST) {
+      if (it == 0) {  // the resident tile was not loaded by this pass: fetch its (S, SW) pairs by hand
+        if (lane < rows) reinterpret_cast<float2*>(aux)[lane] = a.pix_stats[t * PPT + lane];
+        __syncwarp();
+      }
+    }
     if constexpr (PD != 0) {
       if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);  // (a ragged tile was widened by its loads)
     }
@@ -247,6 +266,17 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, rowp[m0 + m]);
     lmax = group_max<LPP>(lmax, lane);
 
+    // ST backward: the pixel's sums come from the forward pass
+    [[maybe_unused]] float st_rS = 0.f, st_rSW = 0.f, st_lt = 0.f, st_ll = 0.f;
+    [[maybe_unused]] bool st_tiny = false;
+    if constexpr (BWD && ST) {
+      const float2 stp = reinterpret_cast<const float2*>(aux)[pp];  // arrived with the tile
+      (void)st;
+      st_rS = rcpa(stp.x);
+      st_rSW = rcpa(stp.y);
+      st_tiny = !(stp.x > kTinySum);  // the linear-domain sum left the float32 range (or is NaN): log-domain responsibilities
+      if (st_tiny) modl_pixel_logdomain(param_row(a, i, ROWF), M, px, a.plain != 0, st_lt, st_ll, PD != 0);
+    }
     f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
 #pragma unroll 1
     for (int pr = 0; pr < NPAIR; ++pr) {
@@ -270,9 +300,26 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         P = pair_eval<true, BWD, Pixel, AR>(px, mu, sc, kp, u);
       else
         P = pair_eval<false, BWD, Pixel, AR>(px, mu, sc, kp, u);
+      if constexpr (BWD && ST) {
+        f2 r = (W * P) * st_rS;   // posterior responsibility of the component
+        f2 pi = W * st_rSW;       // softmax(logits)
+        if (st_tiny) {
+          const float* grow_t = param_row(a, i, ROWF);
+          r = pk(expf(modl_logt(grow_t, M, m, px, a.plain != 0, PD != 0) - st_lt),
+                 single ? 0.0f : expf(modl_logt(grow_t, M, m + 1, px, a.plain != 0, PD != 0) - st_lt));
+          pi = pk(expf(ld_param(grow_t, m, PD != 0) - st_ll), single ? 0.0f : expf(ld_param(grow_t, m + 1, PD != 0) - st_ll));
+        }
+        const f2 gr = r * g;
+        if (active) {  // final gradients overwrite the component's parameters in place
+          st_pair<AL>(rowp, m, single, (r - pi) * g);
+#pragma unroll
+          for (int j = 0; j < 9; ++j) st_pair<AL>(rowp, (1 + j) * M + m, single, u[j] * gr);
+        }
+      } else {
       sumW2 = sumW2 + W;
       sumWP2 = fma2(W, P, sumWP2);
-      if constexpr (BWD) {
+      }
+      if constexpr (BWD && !ST) {
         // unscaled gradients overwrite the component's parameters in place; W*P goes to the aux strip.
         // Only lanes that own a real pixel write: shadow lanes (ragged tile, or lanes 30/31 when 3 lanes share a
         // pixel) would otherwise race with the owner of pixel 0.
@@ -287,9 +334,12 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
       }
     }
-    const float S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
-    const float SW = group_sum<LPP>(lo(sumW2) + hi(sumW2), lane);
-    const bool tiny = !(S > kTinySum);  // also catches NaN
+    float S = 1.0f, SW = 1.0f;
+    if constexpr (!(BWD && ST)) {
+      S = group_sum<LPP>(lo(sumWP2) + hi(sumWP2), lane);
+      SW = group_sum<LPP>(lo(sumW2) + hi(sumW2), lane);
+    }
+    [[maybe_unused]] const bool tiny = !(S > kTinySum);  // also catches NaN
     const float* grow = param_row(a, i, ROWF);
 
     if constexpr (!BWD) {
@@ -305,6 +355,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         lp = lt - ll;
       }
       const bool owner = active && sub == 0;
+      if (a.pix_stats && owner) a.pix_stats[i] = make_float2(S, SW);
       if (a.lp_pixel && owner) a.lp_pixel[i] = lp;
       const float val = owner ? lp : 0.0f;
       if (a.partial) {
@@ -325,6 +376,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         if (owner) atomicAdd(a.ll_atomic + n, static_cast<double>(val));
       }
     } else {
+      if constexpr (!ST) {
       const float rS = rcpa(S), rSW = rcpa(SW);
       float lt = 0.f, ll = 0.f;
       if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
@@ -348,6 +400,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
 #pragma unroll
           for (int j = 1; j < 10; ++j) st_pair<AL>(rowp, j * M + m, single, ld_pair<AL>(rowp, j * M + m, single) * gr);
         }
+      }
       }
       // hand the gradient tile to the TMA engine
       const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
@@ -399,10 +452,10 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   }
 }
 
-template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0>
+template <int MC, int LPP, bool BWD, int NSLOT, int MAXT, int AR, int PD = 0, bool ST = false>
 __global__ void __launch_bounds__(MAXT, 1) modl_tile_kernel(const ModlArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  tile_body<MC, LPP, BWD, NSLOT, AR, false, PD>(a, smem_raw);
+  tile_body<MC, LPP, BWD, NSLOT, AR, false, PD, ST>(a, smem_raw);
 }
 
 // ---- one step in one launch: forward -> grid barrier -> per-image sums, log-mean-exp, softmax weights -> grid barrier ->
@@ -422,19 +475,20 @@ __global__ void __launch_bounds__(512, 1) modl_step_kernel(const StepArgs sa) {
   const long long nwarps = blockDim.x >> 5;
   const long long gw = static_cast<long long>(blockIdx.x) * nwarps + (threadIdx.x >> 5);
   const long long total_warps = static_cast<long long>(gridDim.x) * nwarps;
-  tile_body<MC, LPP, false, 1, AR, true>(sa.a, smem_raw);
+  tile_body<MC, LPP, false, 1, AR, true, 0, true>(sa.a, smem_raw);   // writes a.pix_stats
   __threadfence();
   grid.sync();
   step_finish(sa.f, gw, total_warps, lane);
   __threadfence();
   grid.sync();
+  asm volatile("fence.proxy.async;" ::: "memory");  // the forward pass's (S, SW) pairs are about to be read by bulk copies
   if (sa.f.elbo && gw == total_warps - 1) {  // batch mean, fixed order (the last warp owns the shortest run)
     double t = 0.0;
     for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
     t = warp_sum(t);
     if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
   }
-  tile_body<MC, LPP, true, 1, AR, true>(sa.a, smem_raw);
+  tile_body<MC, LPP, true, 1, AR, true, 0, true>(sa.a, smem_raw);    // one-pass gradient from a.pix_stats
 }
 
 static __global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {

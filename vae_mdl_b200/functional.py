@@ -121,7 +121,8 @@ class _ModlFn(torch.autograd.Function):
 
 def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch.Tensor] = None,
                   g_pixel: Optional[torch.Tensor] = None, x_range: int = _abi.RANGE_UNIT,
-                  edge_mode: int = _abi.EDGE_MDL, plain: bool = False) -> torch.Tensor:
+                  edge_mode: int = _abi.EDGE_MDL, plain: bool = False,
+                  pix_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The gradient kernel on its own: d/dparams of sum(g_image * ll_image) + sum(g_pixel * lp_pixel).
     bfloat16 parameters give a bfloat16 gradient (float32 arithmetic, one rounding at the store)."""
     p, bf16 = dense_param(params, "parameters")
@@ -139,6 +140,11 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
         if plain:
             check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, ptr(gi), ptr(gp),
                                               ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
+        elif pix_stats is not None and not bf16:
+            # the per-pixel mixture sums of the forward call on the same parameters: one-pass gradient kernel
+            check(lib().vaemdl_modl_bwd_stats(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
+                                              ptr(gi), ptr(gp), ptr(pix_stats), ptr(dp), stream_ptr(p.device)),
+                  "vaemdl_modl_bwd_stats")
         else:
             fn = lib().vaemdl_modl_bwd_bf16 if bf16 else lib().vaemdl_modl_bwd
             check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
@@ -147,7 +153,8 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
 
 
 def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: int = 0,
-                      x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL, plain: bool = False):
+                      x_range: int = _abi.RANGE_UNIT, edge_mode: int = _abi.EDGE_MDL, plain: bool = False,
+                      want_stats: bool = False):
     """MoDL forward fused with the IWAE tail in TWO launches (``vaemdl_modl_iwae_fwd``): ``params [S,B,H,W,10M]``,
     ``x [B,H,W,3]``, ``extra = beta*(lpz-lqzx) [S,B]`` or None.  Returns ``(lpxz float64 [S,B], log_w, lme_b [B],
     elbo [1], g_ll [S,B])`` with ``g_ll = d(-elbo)/d lpxz`` (models/loss.py:32-37).  Not recorded by autograd."""
@@ -179,10 +186,20 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
                                                ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
                                                stream_ptr(dev)), "vaemdl_modl_plain_iwae_fwd")
         else:
+            if want_stats and not bf16:
+                # leaves every pixel's (mixture sum, logit normaliser) for modl_backward(pix_stats=...): one-pass gradient
+                stats = torch.empty((S, B, H, W, 2), device=dev, dtype=torch.float32)
+                check(L.vaemdl_modl_iwae_fwd_stats(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch,
+                                                   H, W, M, ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo),
+                                                   ptr(g_ll), ptr(stats), ptr(ws), ws_bytes, stream_ptr(dev)),
+                      "vaemdl_modl_iwae_fwd_stats")
+                return ll64, log_w, lme_b, elbo, g_ll, stats
             fn = L.vaemdl_modl_iwae_fwd_bf16 if bf16 else L.vaemdl_modl_iwae_fwd
             check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
                      ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws),
                      ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd")
+    if want_stats:
+        return ll64, log_w, lme_b, elbo, g_ll, None
     return ll64, log_w, lme_b, elbo, g_ll
 
 
@@ -213,7 +230,7 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     elbo = torch.empty(1, device=dev, dtype=torch.float32)
     g_ll = torch.empty((S, B), device=dev, dtype=torch.float32)
     dp = torch.empty_like(p)
-    ws_bytes = L.vaemdl_modl_workspace_bytes(S * B, H, W)
+    ws_bytes = L.vaemdl_modl_step_workspace_bytes(S * B, H, W)   # incl. the per-pixel sums the two passes share
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
     n_launch = ctypes.c_int(0)
     with _abi.on_device(dev):
@@ -687,15 +704,21 @@ class _FusedIwaeFn(torch.autograd.Function):
                 expanded += [le, se]
                 terms.append((zs[zi], le, se, w))
         extra, sums = latent_terms(terms)
+        stats = None
         if kind == "modl":
-            ll64, log_w, lme_b, elbo, g_ll = modl_iwae_forward(p0, x, extra, 0, meta["x_range"], meta["edge_mode"],
-                                                               meta["plain"])
+            # n_mix 5 / 30: the forward kernel leaves the per-pixel mixture sums for a one-pass gradient kernel (the
+            # library ignores them for any other n_mix, so they are not even allocated then)
+            want = bool(ctx.needs_input_grad[5]) and p0.shape[-1] in (50, 300) and not meta["plain"]
+            out = modl_iwae_forward(p0, x, extra, 0, meta["x_range"], meta["edge_mode"], meta["plain"], want_stats=want)
+            ll64, log_w, lme_b, elbo, g_ll = out[:5]
+            stats = out[5] if want else None
         else:
             ll64, log_w, lme_b, elbo, g_ll = dlogistic_iwae_forward(p0, p1, x, extra, meta["low"], meta["high"],
                                                                     meta["levels"])
         ctx.kind, ctx.meta_, ctx.term_meta, ctx.n_z = kind, meta, term_meta, n_z
         ctx.raw_shapes = [t.shape for t in raw]
         ctx.has_p1 = p1 is not None
+        ctx.pix_stats = stats   # (not an input or output of the function: plain attribute)
         ctx.save_for_backward(x, p0, p1 if p1 is not None else p0, g_ll, *zs, *expanded)
         lpxz = ll64.float()
         loss = -elbo.reshape(())
@@ -713,7 +736,7 @@ class _FusedIwaeFn(torch.autograd.Function):
         if ctx.kind == "modl":
             if ctx.needs_input_grad[5]:
                 dp0 = modl_backward(p0, x, g_image=g, x_range=meta["x_range"], edge_mode=meta["edge_mode"],
-                                    plain=meta["plain"])
+                                    plain=meta["plain"], pix_stats=None if meta["plain"] else ctx.pix_stats)
         elif ctx.needs_input_grad[5] or ctx.needs_input_grad[6]:
             dp0, dp1 = dlogistic_backward(p0, p1, x, g, meta["low"], meta["high"], meta["levels"])
         n_t = len(ctx.needs_input_grad) - 7
