@@ -237,30 +237,45 @@ class ModlStep:
         self.launches = n.value
 
 
+PROBE_EVERY = 4  # every 4th timed step carries the per-kernel CUDA events
+
+
 def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index):
-    """Timed region: barrier + sync, K steps with CUDA events around every kernel group, sync + barrier."""
+    """Timed region: barrier + sync, K steps, sync + barrier; ONE pair of CUDA events brackets all K steps (`value`).
+    Every PROBE_EVERY-th step also records an event between the forward + finish launches and the backward launch --
+    the per-kernel durations `roofline` is computed from come out of the same timed region.  (An event record between two
+    launches ends the programmatic dependent-launch chain there, which costs that step ~2 %: hence not on every step.)"""
     for _ in range(warmup):
         step.step()
     torch.cuda.synchronize(dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    probes = [k for k in range(steps) if k % PROBE_EVERY == 0]
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in probes}
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
     torch.cuda.synchronize(dev)
     with ClockSampler(sampler_index) as clk:
         t0 = time.perf_counter()
+        e_begin.record(step.stream)
         for k in range(steps):
             step.next_input()
-            ev[k][0].record(step.stream)
-            step.fwd()
-            ev[k][1].record(step.stream)
-            step.bwd()
-            ev[k][2].record(step.stream)
+            if k in ev:
+                ev[k][0].record(step.stream)
+                step.fwd()
+                ev[k][1].record(step.stream)
+                step.bwd()
+                ev[k][2].record(step.stream)
+            else:
+                step.fwd()
+                step.bwd()
+        e_end.record(step.stream)
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
     barrier(world)
-    total_ms = ev[0][0].elapsed_time(ev[-1][2])
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
-    return {"total_ms": total_ms, "wall_ms": wall * 1e3, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "clocks": clk.summary()}
+    total_ms = e_begin.elapsed_time(e_end)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev.values()) / len(ev)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev.values()) / len(ev)
+    return {"total_ms": total_ms, "wall_ms": wall * 1e3, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "clocks": clk.summary(),
+            "probed_steps": len(ev)}
 
 
 def run_e2e(S, B, H, W, M, steps, warmup, world, dev, seed):
@@ -694,7 +709,8 @@ def main():
                        "step": "modl_fwd (tile partials, float64) -> fused finish (per-image ll, log-mean-exp, elbo, softmax weights) -> modl_bwd; inputs resident in HBM"},
             "clocks": res["clocks"], "e2e": e2e, "gpu_launches": ModlStep.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_ms": {"fwd_plus_finish": res["fwd_ms"], "bwd": res["bwd_ms"]},
+            "kernel_ms": {"fwd_plus_finish": res["fwd_ms"], "bwd": res["bwd_ms"], "probed_steps": res["probed_steps"],
+                          "how": "CUDA events around the two launch groups on every 4th step of the timed region"},
             "elbo_check": {"device": elbo_device, "e2e": elbo_e2e},
         }
         if ev is not None:
