@@ -214,3 +214,23 @@ def test_config5_shard_bf16_parameters(F):
     assert torch.equal(F.modl_log_likelihood(pb, x_u8, dtype=torch.float64), F.modl_log_likelihood(wide, x_u8, dtype=torch.float64))
     dp = F.modl_backward(pb, x_u8, g_image=g)
     assert dp.dtype == torch.bfloat16 and torch.equal(dp, F.modl_backward(wide, x_u8, g_image=g).bfloat16())
+
+
+@pytest.mark.parametrize("S,B,H,W,M,reps", [(5, 64, 32, 32, 10, 200), (5, 128, 32, 32, 5, 100), (16, 32, 64, 64, 10, 30),
+                                             (16, 16, 64, 64, 30, 15)])
+def test_soak_bitwise_reproducible_under_back_to_back_steps(F, S, B, H, W, M, reps):
+    """The same step enqueued back to back `reps` times without host synchronisation (one-launch cooperative kernel for the
+    small shapes, three launches with and without the handed-over mixture sums for the large ones): every repetition must
+    reproduce the first bit for bit -- a race between warps, grid barriers or reused workspace would show up here."""
+    gen = torch.Generator(device=DEV).manual_seed(900 + M)
+    params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    extra = torch.randn(S, B, device=DEV, generator=gen)
+    first = F.modl_iwae_step(params, x_u8, extra)
+    ref_ll, ref_g, ref_dp, ref_elbo = first[0].clone(), first[4].clone(), first[5].clone(), first[3].clone()
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    for _ in range(reps):
+        out = F.modl_iwae_step(params, x_u8, extra)
+        bad += (out[0] != ref_ll).sum() + (out[4] != ref_g).sum() + (out[5] != ref_dp).sum() + (out[3] != ref_elbo).sum()
+    assert int(bad.item()) == 0
+    assert not bool(torch.isnan(ref_dp).any())
