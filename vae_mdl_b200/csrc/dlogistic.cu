@@ -464,6 +464,8 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
 // ONCE, the logistic terms are evaluated ONCE, and after the barriers the gradient is one multiply per element.
 // Same formulas and summation order as dl_pair_kernel<false> + finish_kernel + dl_pair_kernel<true>; the forward value comes
 // out of the gradient instantiation of dl_elem2 here, so the two routes agree to float32 round-off (not bit for bit).
+constexpr int kStepWarps = 24;  // warps per CTA of the one-launch step: one 768-thread CTA per SM (a third of the CTAs of
+                                // 256-thread blocks at the two grid barriers, the same number of warps)
 constexpr int kStepKeep = 13;  // floats a lane parks per tile: 6 derivative pairs + the image index of its pixel pair
 struct DlStepArgs {
   DlArgs a;
@@ -472,7 +474,7 @@ struct DlStepArgs {
 };
 
 template <bool IL>
-__global__ void __launch_bounds__(256, 3) dl_step_kernel(const DlStepArgs sa) {
+__global__ void __launch_bounds__(kStepWarps * 32, 1) dl_step_kernel(const DlStepArgs sa) {
   extern __shared__ float dl_keep[];  // [warps][T][kStepKeep][32]
   const DlArgs& a = sa.a;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
@@ -798,14 +800,15 @@ static int dl_step_plan(const DlArgs& a, int kind, int S, long long n_tiles, lon
       int dev = 0, v = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
-      const int max_smem = kStepMaxT * 8 * kStepKeep * 32 * 4;
+      const int max_smem = device_info().max_smem_optin;
       cudaFuncSetAttribute(dl_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       cudaFuncSetAttribute(dl_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
       for (int T = 1; T <= kStepMaxT; ++T) {
-        const size_t smem = static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4;
+        const size_t smem = static_cast<size_t>(T) * kStepWarps * kStepKeep * 32 * 4;
         occ[0][T] = occ[1][T] = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0][T], dl_step_kernel<true>, 256, smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1][T], dl_step_kernel<false>, 256, smem);
+        if (smem > static_cast<size_t>(max_smem)) continue;  // more parked tiles than shared memory holds
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0][T], dl_step_kernel<true>, kStepWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1][T], dl_step_kernel<false>, kStepWarps * 32, smem);
       }
       coop = v;
     }
@@ -813,11 +816,11 @@ static int dl_step_plan(const DlArgs& a, int kind, int S, long long n_tiles, lon
   if (!coop) return 0;
   for (int T = 1; T <= kStepMaxT; ++T) {
     long long blocks = static_cast<long long>(device_info().sm_count) * occ[kind == 1 ? 0 : 1][T];  // every CTA resident
-    if (blocks * 8 > kMaxGridWarps) blocks = kMaxGridWarps / 8;
+    if (blocks * kStepWarps > kMaxGridWarps) blocks = kMaxGridWarps / kStepWarps;
     if (blocks < 1) continue;
-    const long long need = (n_tiles + 7) / 8;
+    const long long need = (n_tiles + kStepWarps - 1) / kStepWarps;
     if (blocks > need) blocks = need;
-    const long long total_warps = blocks * 8;
+    const long long total_warps = blocks * kStepWarps;
     if ((n_tiles + total_warps - 1) / total_warps <= T) {
       *blocks_out = blocks;
       return T;
@@ -861,7 +864,7 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   if (reinterpret_cast<uintptr_t>(workspace) & 7u) return VAEMDL_EALIGN;
   char* ws = static_cast<char*>(workspace);
   a.partial = reinterpret_cast<double*>(ws);
-  const long long total_warps = blocks * 8;
+  const long long total_warps = blocks * kStepWarps;
   a.tw_base = n_tiles / total_warps;
   a.tw_rem = n_tiles % total_warps;
   a.K = partial_K(a.rows_per_img, 64, a.tw_base);
@@ -885,8 +888,8 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   if (launches) *launches = 1;
   void* args[] = {&sa};
   void* kern = kind == 1 ? reinterpret_cast<void*>(dl_step_kernel<true>) : reinterpret_cast<void*>(dl_step_kernel<false>);
-  rc = cuda_rc(cudaLaunchCooperativeKernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(256), args,
-                                           static_cast<size_t>(T) * 8 * kStepKeep * 32 * 4, st));
+  rc = cuda_rc(cudaLaunchCooperativeKernel(kern, dim3(static_cast<unsigned>(blocks)), dim3(kStepWarps * 32), args,
+                                           static_cast<size_t>(T) * kStepWarps * kStepKeep * 32 * 4, st));
   if (rc == static_cast<int>(cudaErrorCooperativeLaunchTooLarge) || rc == static_cast<int>(cudaErrorLaunchOutOfResources)) {
     // the grid cannot be co-resident right now: nothing was enqueued, run the three ordinary launches instead
     cudaGetLastError();
