@@ -328,6 +328,9 @@ VAEMDL_API int vaemdl_modl_sample(const float* params, const float* u_mix, const
                        long long n_rep, long long n_img, int H, int W, int M,
                        float* x_out, uint8_t* x_q, uint8_t* idx, void* stream);
 
+/* Plain discretized-logistic sampler (utils/discretized_logistic.py:80-85; models/model06.py:166 calls it on every
+ * forward pass): x_out[e] = clip(loc + exp(logscale) * (log u - log(1 - u)), low, high), float32 arithmetic with the
+ * accurate logf / log1pf / expf (|error| < ~3e-7 on unclipped values).  loc / logscale addressed as base[(e / C) * ld + e % C]. */
 VAEMDL_API int vaemdl_dlogistic_sample(const float* loc, const float* logscale, int C, int ld, const float* u,
                             long long n_elem, float low, float high, float* x_out, void* stream);
 

@@ -587,19 +587,59 @@ __global__ void dl_cast_kernel(const double* __restrict__ in, float* __restrict_
   if (i < n) out[i] = static_cast<float>(in[i]);
 }
 
-// sampler: clip(loc + exp(ls) * (log u - log(1-u)), low, high) in float64   (utils/discretized_logistic.py:80-85)
+// sampler: clip(loc + exp(ls) * (log u - log(1-u)), low, high)   (utils/discretized_logistic.py:80-85)
+// float32 with the accurate logf / log1pf / expf (the reference's own precision): whenever the result is not clipped,
+// |exp(ls) * eps| <= |high - low| + |loc|, so one-ulp errors in eps and exp(ls) stay below ~3e-7 absolute -- float64
+// transcendentals made this kernel FP64-pipe-bound at a quarter of the HBM roofline (models/model06.py:166 draws x on
+// every forward pass).  Four elements per thread and iteration keep enough loads in flight.
 __global__ void dl_sample_kernel(const float* __restrict__ loc, const float* __restrict__ logscale, int C, int ld,
                                  const float* __restrict__ u, long long n_elem, float low, float high,
                                  float* __restrict__ out) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_elem; e += stride) {
-    const long long row = e / C;
-    const long long po = row * ld + (e - row * C);
-    const double uu = static_cast<double>(u[e]);
-    const double eps = log(uu) - log(1.0 - uu);
-    double v = static_cast<double>(loc[po]) + exp(static_cast<double>(logscale[po])) * eps;
-    v = fmin(fmax(v, static_cast<double>(low)), static_cast<double>(high));
-    out[e] = static_cast<float>(v);
+  const long long e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (long long base = e0; base < n_elem; base += 4 * stride) {
+    float uu[4], lc[4], ls[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long e = base + k * stride;
+      uu[k] = 0.5f;
+      lc[k] = ls[k] = 0.0f;
+      if (e < n_elem) {
+        const long long row = e / C;
+        const long long po = row * ld + (e - row * C);
+        uu[k] = u[e];
+        lc[k] = loc[po];
+        ls[k] = logscale[po];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long e = base + k * stride;
+      const float eps = logf(uu[k]) - log1pf(-uu[k]);
+      const float v = fminf(fmaxf(fmaf(expf(ls[k]), eps, lc[k]), low), high);
+      if (e < n_elem) out[e] = v;
+    }
+  }
+}
+
+// image tensors (C = 3): one thread per pixel, no index division; loc / logscale rows are ld floats apart
+__global__ void dl_sample3_kernel(const float* __restrict__ loc, const float* __restrict__ logscale, int ld,
+                                  const float* __restrict__ u, long long n_rows, float low, float high,
+                                  float* __restrict__ out) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    float uu[3], lc[3], ls[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uu[c] = u[r * 3 + c];
+      lc[c] = loc[r * ld + c];
+      ls[c] = logscale[r * ld + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float eps = logf(uu[c]) - log1pf(-uu[c]);
+      out[r * 3 + c] = fminf(fmaxf(fmaf(expf(ls[c]), eps, lc[c]), low), high);
+    }
   }
 }
 
@@ -907,8 +947,18 @@ extern "C" int vaemdl_dlogistic_sample(const float* loc, const float* logscale, 
                                        long long n_elem, float low, float high, float* x_out, void* stream) {
   if (!loc || !logscale || !u || !x_out || C <= 0 || ld < C || n_elem <= 0) return VAEMDL_EINVAL;
   const DeviceInfo& di = device_info();
-  long long blocks = (n_elem + 255) / 256;
+  if (C == 3 && n_elem % 3 == 0) {
+    const long long n_rows = n_elem / 3;
+    long long rb = (n_rows + 255) / 256;
+    const long long rcap = static_cast<long long>(di.sm_count) * 32;
+    if (rb > rcap) rb = rcap;
+    dl_sample3_kernel<<<static_cast<unsigned>(rb), 256, 0, static_cast<cudaStream_t>(stream)>>>(loc, logscale, ld, u, n_rows,
+                                                                                              low, high, x_out);
+    return cuda_rc(cudaGetLastError());
+  }
+  long long blocks = (n_elem + 4 * 256 - 1) / (4 * 256);
   const long long cap = static_cast<long long>(di.sm_count) * 16;
+  if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
   dl_sample_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(loc, logscale, C, ld, u,
                                                                                                n_elem, low, high, x_out);
