@@ -350,7 +350,7 @@ __device__ __forceinline__ void dl_pair_store(const DlArgs& a, long long r0, con
 
 // IL: loc/logscale are the two halves of one [.., 6] tensor (ld = 6, logscale = loc + 3) and so are dloc/dls.
 template <bool BWD, bool IL>
-__global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
+__global__ void __launch_bounds__(256, 3) dl_pair_kernel(const DlArgs a) {
   // runs numbered CTA-minor: the (one tile longer) first tw_rem runs spread evenly over the SMs
   const long long gw = static_cast<long long>(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -380,14 +380,31 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
   double acc0 = 0.0, acc1 = 0.0;
   long long n_base = n_warp_first;
   bool any1 = false;  // some row of the current tile belongs to image n_base + 1 (warp-uniform)
-  for (long long t = t_begin; t < t_end; ++t) {
-    const bool active = r0 < a.n_rows;
-    f2 loc[3], ls[3], xv[3];
-    if (active) {
-      dl_pair_load<IL>(a, r0, xb, rpi, rr, loc, ls, xv);
-    } else {
+  // the loads of tile t + 1 are issued before tile t is evaluated: a tile is only 48 bytes per lane, so without this
+  // every warp sat on its own load latency (26 % + 15 % of the stall samples on the first uses of the loaded values)
+  bool active = r0 < a.n_rows;
+  f2 loc[3], ls[3], xv[3];
+  if (active) {
+    dl_pair_load<IL>(a, r0, xb, rpi, rr, loc, ls, xv);
+  } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) loc[c] = ls[c] = xv[c] = sp(0.0f);
+    for (int c = 0; c < 3; ++c) loc[c] = ls[c] = xv[c] = sp(0.0f);
+  }
+  for (long long t = t_begin; t < t_end; ++t) {
+    // next tile: 64 rows further on
+    long long r0n = r0 + 64, rrn = rr + 64, nn = n, xbn = xb;
+    while (rrn >= rpi) {
+      rrn -= rpi;
+      ++nn;
+      if (a.x_batch != 1 && ++xbn == a.x_batch) xbn = 0;
+    }
+    bool nact = false;
+    f2 nloc[3], nls[3], nxv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) nloc[c] = nls[c] = nxv[c] = sp(0.0f);
+    if (t + 1 < t_end) {
+      nact = r0n < a.n_rows;
+      if (nact) dl_pair_load<IL>(a, r0n, xbn, rpi, rrn, nloc, nls, nxv);
     }
     DlOut2 o[3];
 #pragma unroll
@@ -436,13 +453,16 @@ __global__ void __launch_bounds__(256) dl_pair_kernel(const DlArgs a) {
       }
       dl_pair_store<IL>(a, r0, dl, ds);
     }
-    // next tile: 64 rows further on
-    r0 += 64;
-    rr += 64;
-    while (rr >= rpi) {
-      rr -= rpi;
-      ++n;
-      if (a.x_batch != 1 && ++xb == a.x_batch) xb = 0;
+    r0 = r0n;
+    rr = rrn;
+    n = nn;
+    xb = xbn;
+    active = nact;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      loc[c] = nloc[c];
+      ls[c] = nls[c];
+      xv[c] = nxv[c];
     }
   }
   if constexpr (!BWD) {
@@ -698,9 +718,11 @@ static int dl_launch(DlArgs a, int cpt, int kind, cudaStream_t st, PartialGeom* 
   // few tiles rather than spreading a small problem over as many warps as possible
   static const int per_sm = [] {
     const char* e = getenv("VAEMDL_DL_BLOCKS_PER_SM");
-    return e ? atoi(e) : 8;
+    return e ? atoi(e) : 0;
   }();
-  long long cap = static_cast<long long>(di.sm_count) * (per_sm > 0 ? per_sm : 8);
+  // pixel-pair kernels: 80 registers -> 3 resident CTAs per SM, and a fully resident grid measured best (162 vs 197 us
+  // forward at 16 x 256 x 64 x 64 with 8 CTAs per SM, i.e. 2.7 waves)
+  long long cap = static_cast<long long>(di.sm_count) * (per_sm > 0 ? per_sm : (kind ? 3 : 8));
   if (cap * 8 > kMaxGridWarps) cap = kMaxGridWarps / 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
