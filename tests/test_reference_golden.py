@@ -45,6 +45,16 @@ def test_fixtures_reproduce_from_the_reference_source():
     assert "reproduce bit for bit" in r.stdout
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference is only mounted in the build container")
+def test_oracle_matches_reference_source_on_random_cases():
+    """tests/golden/fuzz_reference.py: 40 random shapes / n_mix / scales / (low, high, levels), values and gradients, the
+    oracle against the reference's own modules executed over oracle/tf_shim (in a subprocess: it puts the reference on
+    sys.path)."""
+    r = subprocess.run([sys.executable, os.path.join(GOLDEN, "fuzz_reference.py"), "40", "20261018"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("name,M", MODL)
 def test_oracle_matches_reference_source_modl_f64(name, M):
     fx, rs = golden(name), refsrc(name)
