@@ -240,9 +240,13 @@ __device__ __forceinline__ DlOut2 dl_elem2(f2 x, f2 loc, f2 ls, const DlArgs& a)
   const bool il = lo(lhs) > lo(thr), ih = hi(lhs) > hi(thr);  // prob > 1e-5 (:64)
   const bool el = ll_ || rl_, eh = lh_ || rh_;
   const bool ol = (ll_ == pl), oh = (lh_ == ph);
+  // 0/1 masks on the packed pipe instead of selects wherever one side is zero (a select of a packed value costs the
+  // compiler four predicated moves; these kernels are issue-bound).  Masked quantities are finite.
+  const f2 mi = pk(il ? 1.0f : 0.0f, ih ? 1.0f : 0.0f);  // 1 in the CDF-difference branch
+  const f2 nmi = sp(1.0f) - mi;                          // 1 in the low-probability branch
   f2 nu = sel_2(il, ih, rest_n, sp(1.0f));
   f2 de = sel_2(il, ih, den_n, opA * opA);
-  f2 cst = sel_2(il, ih, sp(0.0f), sp(a.ln_width) - ls);
+  f2 cst = nmi * (sp(a.ln_width) - ls);
   f2 use_mid = am;
   if (el || eh) {
     const f2 de_e = sel_2(ol, oh, opAG, ApG);
@@ -268,10 +272,13 @@ __device__ __forceinline__ DlOut2 dl_elem2(f2 x, f2 loc, f2 ls, const DlArgs& a)
       }
     }
     f2 den = de;  // the same denominators serve the derivatives
-    f2 nm = neg_sign_of_2(sel_2(il, ih, G * omA2, omA2), mid);
-    f2 nh = sel_2(il, ih, (h * -1.0f) * lhs, sp(0.0f));
-    f2 c0 = sel_2(il, ih, hc, sp(0.0f));
-    f2 dir = sel_2(il, ih, sp(0.0f), sp(-1.0f));
+    // G in the CDF-difference branch, 1 in the low-probability branch (1 - mi * omG is the expression G was formed with
+    // unless a lane took the exact exp(-h))
+    const f2 gsel = narrow ? sel_2(il, ih, G, sp(1.0f)) : fma2(mi, omG * -1.0f, 1.0f);
+    f2 nm = neg_sign_of_2(gsel * omA2, mid);
+    f2 nh = mi * ((h * -1.0f) * lhs);
+    f2 c0 = mi * hc;
+    f2 dir = mi + -1.0f;
     if (el || eh) {
       const f2 t = sel_2(ol, oh, AG, G);
       const f2 nm_e = pk(ll_ ? lo(t) : -lo(t), lh_ ? hi(t) : -hi(t));
