@@ -6,7 +6,14 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input that is already resident in HBM:
 MoDL per-image log-likelihood (forward kernel) -> fused IWAE tail (log-mean-exp over importance samples, ELBO,
-softmax weights) -> MoDL parameter gradient (backward kernel).  Rank 0 prints ONE JSON line.
+softmax weights) -> MoDL parameter gradient (backward kernel); at N > 1 the step also carries the path's one collective
+(the scalar all-reduce of the ELBO shares, vae_mdl_b200/dist.py::sharded_modl_iwae_step).  Rank 0 prints ONE JSON line.
+
+Besides the K timed steps the line carries: `value_sustained` (the same step back to back for >= 3 s, clocks recorded),
+`configs0` / `configs0_ref_default` (BASELINE configs[0] and the reference's real default shape, each with its own
+roofline block), `sample_split` (the step with the importance samples, not the batch, spread over the ranks),
+`iwae_eval_5000is` (BASELINE configs[3], 512 images per GPU), `e2e` (host buffers through the C ABI) and `elbo_check`
+(the e2e arm's inputs pushed through the device arm: a failed comparison fails the run).
 
 Headline workload (BASELINE.json configs[4], the largest MoDL fwd+bwd configuration, per-GPU shard):
     64x64x3 images, 10 mixtures, 16 importance samples, 32 images per GPU  (= batch 256 over 8 GPUs), weak scaling.
@@ -240,13 +247,45 @@ class ModlStep:
 PROBE_EVERY = 4  # every 4th timed step carries the per-kernel CUDA events
 
 
+def allreduce_elbo(step, world):
+    """The path's one collective at N > 1 (models/loss.py:37 over a batch split across ranks): every rank's additive
+    share of the ELBO -> the global value, on the stream the kernels run on."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(step.elbo, op=dist.ReduceOp.SUM)
+
+
+def run_sustained(step: ModlStep, seconds, ms_per_step, world, dev, sampler_index):
+    """The same step back to back for >= `seconds` (no per-kernel probes, no host sync inside): what the kernels deliver
+    once the GPU has warmed up and settled on its sustained clocks.  The step count is fixed up front from the short
+    run's time per step, so every rank enqueues the same number of steps."""
+    n = max(10, int(math.ceil(seconds * 1e3 / ms_per_step * 1.08)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    torch.cuda.synchronize(dev)
+    with ClockSampler(sampler_index, period_s=0.01) as clk:
+        e0.record(step.stream)
+        for _ in range(n):
+            step.next_input()
+            step.fwd()
+            step.bwd()
+            allreduce_elbo(step, world)
+        e1.record(step.stream)
+        torch.cuda.synchronize(dev)
+    barrier(world)
+    return {"steps": n, "total_ms": e0.elapsed_time(e1), "clocks": clk.summary()}
+
+
 def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index):
     """Timed region: barrier + sync, K steps, sync + barrier; ONE pair of CUDA events brackets all K steps (`value`).
     Every PROBE_EVERY-th step also records an event between the forward + finish launches and the backward launch --
     the per-kernel durations `roofline` is computed from come out of the same timed region.  (An event record between two
     launches ends the programmatic dependent-launch chain there, which costs that step ~2 %: hence not on every step.)"""
     for _ in range(warmup):
-        step.step()
+        step.next_input()
+        step.fwd()
+        step.bwd()
+        allreduce_elbo(step, world)
     torch.cuda.synchronize(dev)
     probes = [k for k in range(steps) if k % PROBE_EVERY == 0]
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in probes}
@@ -267,6 +306,7 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
             else:
                 step.fwd()
                 step.bwd()
+            allreduce_elbo(step, world)
         e_end.record(step.stream)
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
@@ -311,10 +351,43 @@ def run_e2e(S, B, H, W, M, steps, warmup, world, dev, seed):
     L.vaemdl_host_release()
     h2d = params.numel() * 4 + x.numel() + extra.numel() * 4
     d2h = dparams.numel() * 4 + ll.numel() * 4 + lme.numel() * 4
-    return dt, h2d, d2h, float(elbo.item())
+    check = elbo_check(L, S, B, H, W, M, dev, params, x, extra, dparams, ll, float(elbo.item()))
+    return dt, h2d, d2h, check
 
 
-def run_eval(world, rank, dev, peak, n_local=48, S=5000, H=32, W=32, M=10):
+def elbo_check(L, S, B, H, W, M, dev, params_h, x_h, extra_h, dparams_h, ll_h, elbo_host):
+    """The SAME inputs through both arms: the host-buffer arm's pinned tensors are copied to the device and pushed through
+    the device-resident entry point (vaemdl_modl_iwae_step, same batch normaliser); ELBO, per-image log-likelihoods and
+    the gradient must agree.  Raises (the bench fails) when they do not."""
+    p = params_h.to(dev)
+    xd = x_h.to(dev)
+    ex = extra_h.to(dev)
+    dp = torch.empty_like(p)
+    ll64 = torch.empty(S, B, dtype=torch.float64, device=dev)
+    g_ll, lme, el = torch.empty(S, B, device=dev), torch.empty(B, device=dev), torch.empty(1, device=dev)
+    wsb = L.vaemdl_modl_step_workspace_bytes(S * B, H, W)
+    ws = torch.empty(wsb // 8 + 1, dtype=torch.float64, device=dev)
+    n = ctypes.c_int(0)
+    rc = L.vaemdl_modl_iwae_step(p.data_ptr(), xd.data_ptr(), 1, 0, 0, S, B, B, B, H, W, M, ex.data_ptr(), None,
+                                 ll64.data_ptr(), None, lme.data_ptr(), el.data_ptr(), g_ll.data_ptr(), dp.data_ptr(),
+                                 ws.data_ptr(), wsb, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream), ctypes.byref(n))
+    assert rc == 0, rc
+    torch.cuda.synchronize(dev)
+    elbo_dev = float(el.item())
+    rel_elbo = abs(elbo_dev - elbo_host) / abs(elbo_dev)
+    rel_ll = float(((ll_h.to(dev).double() - ll64).abs() / ll64.abs()).max().item())
+    # the host arm cuts the batch into chunks and runs the two-pass gradient kernel on each; same arithmetic per pixel
+    rel_grad = float(((dparams_h.to(dev) - dp).norm() / dp.norm()).item())
+    out = {"device": elbo_dev, "e2e": elbo_host, "rel_elbo": rel_elbo, "rel_ll_max": rel_ll, "rel_grad": rel_grad,
+           "tolerance": {"elbo": 1e-5, "ll": 1e-5, "grad": 1e-4}, "same_inputs": True,
+           "how": "the e2e arm's pinned host tensors copied to the device and run through vaemdl_modl_iwae_step"}
+    out["ok"] = bool(rel_elbo <= 1e-5 and rel_ll <= 1e-5 and rel_grad <= 1e-4)
+    if not out["ok"]:
+        raise RuntimeError(f"elbo_check failed: {out}")
+    return out
+
+
+def run_eval(world, rank, dev, peak, n_local=512, S=5000, H=32, W=32, M=10):
     """BASELINE configs[3]: test-set IWAE evaluation with 5000 importance samples (models/model05.py:168-176), images
     round-robin over ranks (vae_mdl_b200/dist.py).  Per image: ONE forward launch over the [5000,1,32,32,10M] decoder
     output (2.05 GB at M=10) + ONE finish launch (per-sample sums, log-mean-exp) writing llh[i]; no host sync until the
@@ -337,7 +410,10 @@ def run_eval(world, rank, dev, peak, n_local=48, S=5000, H=32, W=32, M=10):
             assert rc == 0, rc
         return vdist.gather_round_robin(llh, n_local * world)
 
-    sweep()
+    for i in range(8):  # warm-up: a few images, not the whole sweep
+        rc = L.vaemdl_modl_iwae_fwd(pool[i & 1].data_ptr(), xs[i].data_ptr(), 1, 0, 0, S, 1, 0, 1, H, W, M, None, None,
+                                    None, None, llh[i:].data_ptr(), None, None, ws.data_ptr(), ws_bytes, st)
+        assert rc == 0, rc
     torch.cuda.synchronize(dev)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -354,6 +430,140 @@ def run_eval(world, rank, dev, peak, n_local=48, S=5000, H=32, W=32, M=10):
             "frac_of_hbm_peak_per_gpu": n_local * S * H * W * 40 * M / t / 1e9 / peak,
             "full_test_set_26032_images_s": 26032 / (n_total / t), "bpd_of_synthetic_params": bpd,
             "launches_per_image": 2, "collective": "one all_gather of the per-image results at the end"}
+
+
+def traffic_from_profiles(key, field):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json);
+    None when no capture of that workload has been committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key, {}).get(field)
+    except Exception:
+        return None
+
+
+def run_small_shape(name, world, dev, peak, steps=60, warm=6):
+    """BASELINE configs[0] (`cfg1`: model05 MoDL loss, 10 mixtures, batch 64 x 5 importance samples, 32x32x3) and the
+    reference's real default (`cfg1_m5`: n_mix 5, batch 128; models/model05.py:60, utils/data.py:20) through
+    vaemdl_modl_iwae_step: ONE cooperative launch per step (forward, IWAE finish, gradient).  Inputs rotate over enough
+    buffers that a step's parameters were last touched > 3 x L2 bytes ago.  At N > 1 every rank runs its own batch shard
+    and the step carries the ELBO all-reduce.  The one kernel IS the step, so its roofline comes from the step time."""
+    _, S, B, H, W, M = WORKLOADS[name]
+    nbuf = max(2, -(-3 * L2_BYTES // (S * B * H * W * 40 * M)))
+    st = ModlStep(S, B, H, W, M, dev, 7 + int(os.environ.get("RANK", "0")), B * world, n_buffers=nbuf)
+    for _ in range(warm):
+        st.step()
+        allreduce_elbo(st, world)
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st.stream)
+    for _ in range(steps):
+        st.step()
+        allreduce_elbo(st, world)
+    e1.record(st.stream)
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    t = max_over_ranks(e0.elapsed_time(e1), world, dev) * 1e-3 / steps
+    alg = st.n_px * 120 * M
+    out = {"workload": name, "config": {"S": S, "B_per_gpu": B, "H": H, "W": W, "n_mix": M,
+                                        "input_rotation": f"{nbuf} parameter tensors ({nbuf * st.n_px * 40 * M / 2**20:.0f} MiB) take turns"},
+           "metric": "MoDL fwd+bwd px-samples/s", "value": world * st.n_px / t, "unit": "px-samples/s", "n_gpus": world,
+           "steps": steps, "us_per_step": t * 1e6, "launches_per_step": st.launches,
+           "roofline": {"bound": "hbm", "kernel": "modl_step_kernel (one cooperative launch: forward + IWAE finish + gradient)"
+                        if st.launches == 1 else "forward + finish + gradient launches",
+                        "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
+                        "traffic": traffic_from_profiles(name, "modl_step_dram_bytes_per_launch"),
+                        "algorithmic_bytes_per_launch": alg}}
+    if world == 1:
+        def on_stream(sp):
+            keep, st.st = st.st, sp
+            for _ in range(len(st.pool)):  # one graph = one pass over every buffer of the rotation
+                st.step()
+            st.st = keep
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            on_stream(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(20):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tg = e0.elapsed_time(e1) * 1e-3 / 20 / len(st.pool)
+        out["cuda_graph_us_per_step"] = tg * 1e6
+        out["cuda_graph_frac_of_hbm_peak"] = alg / tg / 1e9 / peak
+    del st
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sample_split(S_total, B_per_gpu, H, W, M, steps, warm, world, rank, dev, peak):
+    """The step with the IMPORTANCE SAMPLES, not the batch, spread over the ranks (SURVEY 8e second row;
+    vae_mdl_b200/dist.py::sample_sharded_iwae_step): every rank holds S_total / world samples of ALL B_per_gpu * world
+    images -- the same pixel-samples per GPU as the batch split -- and the log-mean-exp over s needs one exchange per
+    step: an all_gather of the (max, sum exp) pair of every image (16 * B bytes per rank), inside the timed step.
+    5 launches: forward, per-image sums, local pairs, [all_gather], combine (lme, ELBO, local softmax weights), gradient."""
+    import torch.distributed as dist
+    from vae_mdl_b200 import _abi
+    if S_total % world:
+        return {"skipped": f"{S_total} importance samples do not split evenly over {world} ranks"}
+    L = _abi.lib()
+    S, B = S_total // world, B_per_gpu * world
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    genx = torch.Generator(device=dev).manual_seed(99)            # every rank scores the same images
+    pool = [torch.randn(S, B, H, W, 10 * M, device=dev, generator=gen) for _ in range(2)]
+    x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=genx)
+    extra = torch.randn(S, B, device=dev, generator=gen)
+    dparams = torch.empty_like(pool[0])
+    ll64 = torch.empty(S, B, dtype=torch.float64, device=dev)
+    pair = torch.empty(2, B, dtype=torch.float64, device=dev)
+    pairs = torch.empty(world, 2, B, dtype=torch.float64, device=dev) if world > 1 else pair
+    g_ll, lme, elbo = torch.empty(S, B, device=dev), torch.empty(B, device=dev), torch.empty(1, device=dev)
+    wsb = L.vaemdl_modl_workspace_bytes(S * B, H, W)
+    ws = torch.empty(wsb // 8 + 1, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    st = ctypes.c_void_p(stream.cuda_stream)
+    k = [0]
+
+    def step():
+        k[0] += 1
+        p = pool[k[0] & 1]
+        rc = L.vaemdl_modl_fwd(p.data_ptr(), x.data_ptr(), 1, 0, 0, S * B, B, H, W, M, None, None, ll64.data_ptr(),
+                               ws.data_ptr(), wsb, st)
+        rc |= L.vaemdl_iwae_split_local(ll64.data_ptr(), extra.data_ptr(), S, B, pair.data_ptr(), st)
+        assert rc == 0, rc
+        if world > 1:
+            dist.all_gather_into_tensor(pairs.view(-1), pair.view(-1))
+        rc = L.vaemdl_iwae_split_combine(ll64.data_ptr(), extra.data_ptr(), S, B, pairs.data_ptr(), world, S_total, 0, None,
+                                         lme.data_ptr(), elbo.data_ptr(), g_ll.data_ptr(), st)
+        rc |= L.vaemdl_modl_bwd(p.data_ptr(), x.data_ptr(), 1, 0, 0, S * B, B, H, W, M, g_ll.data_ptr(), None,
+                                dparams.data_ptr(), st)
+        assert rc == 0, rc
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier(world)
+    t = max_over_ranks(e0.elapsed_time(e1), world, dev) * 1e-3 / steps
+    n_px = S * B * H * W
+    elbo_all = float(elbo.item())   # the GLOBAL value on every rank
+    return {"metric": "MoDL fwd+bwd px-samples/s, importance samples split over the ranks", "value": world * n_px / t,
+            "unit": "px-samples/s", "n_gpus": world, "steps": steps, "ms_per_step": t * 1e3, "scaling": "weak",
+            "config": {"S_total": S_total, "S_per_gpu": S, "B_all_ranks": B, "H": H, "W": W, "n_mix": M},
+            "launches_per_step": 5, "frac_of_hbm_peak_per_gpu": n_px * 120 * M / t / 1e9 / peak,
+            "collective": f"one all_gather of [2,{B}] float64 (max, sum-exp) pairs per step, inside the timed step"
+                          if world > 1 else "none at N=1 (the pairs stay local)",
+            "elbo_global": elbo_all}
 
 
 def also_workloads(dev, peak):
@@ -382,7 +592,7 @@ def also_workloads(dev, peak):
             fn_with_stream(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         return timeit(g.replay, iters)
 
-    for name in ["cfg1", "cfg1_m5", "cfg5_64_m5", "cfg5_64_m30", "cfg5_128_m10", "cfg5_128_m30"]:
+    for name in ["cfg5_64_m5", "cfg5_64_m20", "cfg5_64_m30", "cfg5_128_m10", "cfg5_128_m30"]:
         _, S, B, H, W, M = WORKLOADS[name]
         # small shapes rotate over enough buffers that a step's input was last touched > 2 x L2 bytes ago
         nbuf = max(2, -(-3 * L2_BYTES // (S * B * H * W * 40 * M)))
@@ -390,16 +600,8 @@ def also_workloads(dev, peak):
         t = timeit(st.step, 20)
         out[name] = {"px_samples_per_s": st.n_px / t, "us_per_step": t * 1e6, "launches_per_step": st.launches,
                      "algorithmic_GBs": st.n_px * 120 * M / t / 1e9, "frac_of_hbm_peak": st.n_px * 120 * M / t / 1e9 / peak}
-        if name.startswith("cfg1"):
-            def on_stream(sp, st=st):
-                keep, st.st = st.st, sp
-                for _ in range(len(st.pool)):  # one graph = one pass over every buffer of the rotation
-                    st.step()
-                st.st = keep
-            tg = time_as_graph(on_stream, 20) / len(st.pool)
-            out[name]["cuda_graph_us_per_step"] = tg * 1e6
-            out[name]["cuda_graph_frac_of_hbm_peak"] = st.n_px * 120 * M / tg / 1e9 / peak
         del st
+        torch.cuda.empty_cache()
     # bfloat16 parameters / gradient at the headline shape: same launches, half the parameter bytes.
     # NOT the headline (the reference computes in float32); reported to show what the narrower interface costs / buys.
     try:
@@ -543,6 +745,19 @@ def cpu_baseline_sample(S, H, W, M, budget_s=12.0):
                       f"(median {best * 1e3:.0f} ms/pass; torch-CPU float32 restatement of the TF graph, autograd backward)"}
 
 
+def workload_config(name, wl):
+    """`config` of the JSON line -- the same dict for both arms (ours and --impl reference)."""
+    kind, S, B, H, W, M = wl
+    n_px = S * B * H * W
+    return {"workload": name, "S": S, "B_per_gpu": B, "H": H, "W": W, "n_mix": M,
+            "px_samples_per_step_per_gpu": n_px,
+            "l2": (f"inputs larger than L2 (params {n_px * 40 * M / 2**20:.0f} MiB + grads {n_px * 40 * M / 2**20:.0f} MiB "
+                   "per step vs 126 MiB L2)") if n_px * 40 * M > L2_BYTES else "inputs NOT larger than L2",
+            "input_rotation": "2 parameter tensors alternate between steps (no L2 carry-over of a step's input)",
+            "step": "modl_fwd (tile partials, float64) -> fused finish (per-image ll, log-mean-exp, elbo, softmax weights) "
+                    "-> modl_bwd [-> all-reduce of the ELBO shares at N > 1]; inputs resident in HBM"}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path (restated; TensorFlow cannot run in this image)
 # ------------------------------------------------------------------------------------------------------------------
@@ -580,12 +795,12 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "MoDL fwd+bwd px-samples/s", "value": value, "unit": "px-samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "S": S, "B_per_gpu": B, "H": H, "W": W, "n_mix": M,
-                   "reference_sample_images_per_step": Bs},
+        "config": workload_config(args.workload, wl),
         "cpu_baseline": {"value": value, "unit": "px-samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "px-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_sample_images_per_step": Bs,
         "note": "TensorFlow/TFP are not installable in this image; this is the restated reference (kind=port)",
     }
     emit(line)
@@ -627,6 +842,9 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the summaries of the other BASELINE configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="skip the 5000-IS evaluation (BASELINE configs[3]) leg")
+    ap.add_argument("--no-small", action="store_true", help="skip BASELINE configs[0] / the reference-default shape")
+    ap.add_argument("--no-split", action="store_true", help="skip the sample-split variant of the step")
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="length of the sustained arm in seconds (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -649,20 +867,24 @@ def main():
     value = world * n_px * args.steps / total_s
     bwd_s = max_over_ranks(res["bwd_ms"], world, dev) * 1e-3
     fwd_s = max_over_ranks(res["fwd_ms"], world, dev) * 1e-3
-    elbo_device = float(step.elbo.item())
+
+    # the same step back to back for >= 3 s: sustained clocks, warm GPU
+    sustained = None
+    if args.sustain_s > 0:
+        sus = run_sustained(step, args.sustain_s, total_s / args.steps * 1e3, world, dev, local_rank)
+        sus_s = max_over_ranks(sus["total_ms"], world, dev) * 1e-3
+        sustained = {"value": world * n_px * sus["steps"] / sus_s, "unit": "px-samples/s", "steps": sus["steps"],
+                     "seconds": sus_s, "ms_per_step": sus_s / sus["steps"] * 1e3,
+                     "frac_of_hbm_peak_per_gpu": n_px * 120 * M * sus["steps"] / sus_s / 1e9 / peak, "clocks": sus["clocks"]}
 
     # roofline of the dominant kernel (backward: reads the 40M-byte row, writes the 40M-byte gradient row)
     bwd_bytes = n_px * 80 * M
     fwd_bytes = n_px * 40 * M
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get("modl_bwd_dram_bytes_per_launch")
-    except Exception:
-        pass
     roofline = {"bound": "hbm", "kernel": "modl_tile_kernel<BWD> (vaemdl_modl_bwd)", "achieved": bwd_bytes / bwd_s / 1e9,
                 "peak": peak, "peak_source": peak_how, "unit": "GB/s", "frac": bwd_bytes / bwd_s / 1e9 / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": bwd_bytes,
+                "traffic": traffic_from_profiles(args.workload, "modl_bwd_dram_bytes_per_launch"),
+                "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel; not re-measured here)",
+                "algorithmic_bytes_per_launch": bwd_bytes,
                 "fwd_plus_finish": {"achieved": fwd_bytes / fwd_s / 1e9, "frac": fwd_bytes / fwd_s / 1e9 / peak,
                                     "algorithmic_bytes_per_launch": fwd_bytes},
                 "step": {"achieved": n_px * 120 * M * args.steps / total_s / 1e9,
@@ -671,14 +893,27 @@ def main():
     del step
     torch.cuda.empty_cache()
 
-    # end to end through the host-buffer C-ABI call
+    # BASELINE configs[0] and the reference's real default shape: first-class, each with its own roofline block
+    small = {}
+    if not args.no_small:
+        for key, name in (("configs0", "cfg1"), ("configs0_ref_default", "cfg1_m5")):
+            small[key] = run_small_shape(name, world, dev, peak)
+
+    # the importance samples (not the batch) spread over the ranks: the variant with a real exchange step
+    split = None
+    if not args.no_split:
+        split = run_sample_split(S, B, H, W, M, min(args.steps, 30), max(3, min(args.warmup, 5)), world, rank, dev, peak)
+        torch.cuda.empty_cache()
+
+    # end to end through the host-buffer C-ABI call; then the SAME inputs through the device arm (elbo_check)
     e2e_steps = args.e2e_steps or min(args.steps, 10)
-    dt, h2d, d2h, elbo_e2e = run_e2e(S, B, H, W, M, e2e_steps, args.warmup, world, dev, seed=99 + rank)
+    dt, h2d, d2h, check = run_e2e(S, B, H, W, M, e2e_steps, args.warmup, world, dev, seed=99 + rank)
     dt = max_over_ranks(dt, world, dev)
     e2e = {"value": world * n_px * e2e_steps / dt, "unit": "px-samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
            "api": "vaemdl_modl_iwae_step_host (pinned host buffers; H2D params+x+extra, D2H grads+ll+lme+elbo each step)",
            "host_cpus_bound_near_gpu": bound_cpus}
+    torch.cuda.empty_cache()
 
     ev = None
     if not args.no_eval:
@@ -701,18 +936,20 @@ def main():
             "metric": "MoDL fwd+bwd px-samples/s", "value": value, "unit": "px-samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "S": S, "B_per_gpu": B, "H": H, "W": W, "n_mix": M,
-                       "px_samples_per_step_per_gpu": n_px, "l2": "inputs larger than L2 "
-                       f"(params {n_px * 40 * M / 2**20:.0f} MiB + grads {n_px * 40 * M / 2**20:.0f} MiB per step vs 126 MiB L2)"
-                       if n_px * 40 * M > L2_BYTES else "inputs NOT larger than L2",
-                       "input_rotation": "2 parameter tensors alternate between steps (no L2 carry-over of a step's input)",
-                       "step": "modl_fwd (tile partials, float64) -> fused finish (per-image ll, log-mean-exp, elbo, softmax weights) -> modl_bwd; inputs resident in HBM"},
+            "config": workload_config(args.workload, wl),
             "clocks": res["clocks"], "e2e": e2e, "gpu_launches": ModlStep.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
+            "collective_in_step": "all_reduce(sum) of the ELBO share, 4 bytes, every step" if world > 1 else None,
             "kernel_ms": {"fwd_plus_finish": res["fwd_ms"], "bwd": res["bwd_ms"], "probed_steps": res["probed_steps"],
                           "how": "CUDA events around the two launch groups on every 4th step of the timed region"},
-            "elbo_check": {"device": elbo_device, "e2e": elbo_e2e},
+            "elbo_check": check,
         }
+        if sustained is not None:
+            line["value_sustained"] = sustained["value"]
+            line["sustained"] = sustained
+        line.update(small)
+        if split is not None:
+            line["sample_split"] = split
         if ev is not None:
             line["iwae_eval_5000is"] = ev
         if also is not None:

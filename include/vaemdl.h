@@ -189,25 +189,26 @@ VAEMDL_API int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int 
  * replaces: PixelMixtureDiscretizedLogistic.log_prob + get_mixture_params   utils/mdl_plain.py:36-66, :124-168
  * Same parameter row, same outputs and workspace as the entry points above; the only difference is the chain of
  * means: loc_g = mu_g + tanh(kR)*loc_r, loc_b = mu_b + tanh(kG)*loc_r + tanh(kB)*loc_g (utils/mdl_plain.py:160-162)
- * instead of the observed x_r, x_g.  x in [0,1] (the class rescales, :45), edges x <= -1 / x >= 1, the class's default
- * low = -1, high = 1, levels = 256.
+ * instead of the observed x_r, x_g.  x in [0,1] (the class rescales to [-1,1], :45); low / high / levels are the class's
+ * constructor arguments (utils/mdl_plain.py:18; defaults -1, 1, 256): edge tests x <= low / x >= high, bin width
+ * (high - low) / (levels - 1) (utils/discretized_logistic.py:18-21, :71-76).
  * ------------------------------------------------------------------------ */
 VAEMDL_API int vaemdl_modl_plain_fwd(const float* params, const void* x, int x_dtype,
-                    long long n_img, int x_batch, int H, int W, int M,
+                    long long n_img, int x_batch, int H, int W, int M, float low, float high, float levels,
                     float* lp_pixel, float* ll_image, double* ll_image_f64,
                     void* workspace, size_t workspace_bytes, void* stream);
 VAEMDL_API int vaemdl_modl_plain_iwae_fwd(const float* params, const void* x, int x_dtype,
                     int S, long long B, long long B_total, int x_batch, int H, int W, int M,
-                    const float* extra,
+                    float low, float high, float levels, const float* extra,
                     float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
                     void* workspace, size_t workspace_bytes, void* stream);
 VAEMDL_API int vaemdl_modl_plain_iwae_step(const float* params, const void* x, int x_dtype,
                          int S, long long B, long long B_total, int x_batch, int H, int W, int M,
-                         const float* extra,
+                         float low, float high, float levels, const float* extra,
                          float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
                          float* dparams, void* workspace, size_t workspace_bytes, void* stream, int* launches);
 VAEMDL_API int vaemdl_modl_plain_bwd(const float* params, const void* x, int x_dtype,
-                    long long n_img, int x_batch, int H, int W, int M,
+                    long long n_img, int x_batch, int H, int W, int M, float low, float high, float levels,
                     const float* g_image, const float* g_pixel,
                     float* dparams, void* stream);
 
@@ -311,6 +312,21 @@ VAEMDL_API int vaemdl_latent_terms_bwd(const vaemdl_latent_term* terms, int n_te
                             const float* g_extra, float* const* dz, float* const* dloc, float* const* dscale,
                             void* stream);
 
+/* Importance samples split across ranks (batch smaller than the rank count, or to balance): this rank holds
+ * S_local of the S_total samples of every image.  replaces: logmeanexp over the FULL sample axis (utils/utils.py:9-11)
+ * and the tail of iwae_loss (models/loss.py:34-37) when axis 0 is spread over a process group.
+ *   vaemdl_iwae_split_local   : pair_out [2,B] float64 = (max_s log_w, sum_s exp(log_w - max)) over the local samples,
+ *                               log_w = ll_f64 + (extra ? extra : 0)
+ *   -- the caller all-gathers the pairs in rank order: pairs_all [world,2,B] (the path's ONE collective, 16*B bytes/rank) --
+ *   vaemdl_iwae_split_combine : lme_b [B] = log-mean-exp over all S_total samples, elbo [1] = sum_b lme_b / B_total,
+ *                               g_ll [S_local,B] = d(-elbo)/d ll of the LOCAL samples (-softmax over all samples / B_total),
+ *                               log_w [S_local,B]; all outputs nullable.  Bit-identical lme / elbo on every rank. */
+VAEMDL_API int vaemdl_iwae_split_local(const double* ll_f64, const float* extra, int S_local, long long B, double* pair_out,
+                            void* stream);
+VAEMDL_API int vaemdl_iwae_split_combine(const double* ll_f64, const float* extra, int S_local, long long B,
+                              const double* pairs_all, int world, int S_total, long long B_total,
+                              float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Samplers (explicit uniform noise; float64 internal arithmetic)
  * replaces: sample_from_discretized_mix_logistic   utils/mdl_openai.py:160-193 (explicit-noise lines :167, :185-186)
@@ -326,6 +342,13 @@ VAEMDL_API int vaemdl_latent_terms_bwd(const vaemdl_latent_term* terms, int n_te
  * ------------------------------------------------------------------------ */
 VAEMDL_API int vaemdl_modl_sample(const float* params, const float* u_mix, const float* u_log, int variant, int out_range,
                        long long n_rep, long long n_img, int H, int W, int M,
+                       float* x_out, uint8_t* x_q, uint8_t* idx, void* stream);
+
+/* PixelMixtureDiscretizedLogistic.sample / .mean (utils/mdl_plain.py:68-121) with the class's own low / high: the
+ * VAEMDL_SAMPLE_PLAIN variant of vaemdl_modl_sample, the logistic draws clipped to [low, high]
+ * (utils/discretized_logistic.py:83); u_log == NULL gives mean(): the selected locations clipped to [-1, 1] (:115). */
+VAEMDL_API int vaemdl_modl_plain_sample(const float* params, const float* u_mix, const float* u_log, float low, float high,
+                       int out_range, long long n_rep, long long n_img, int H, int W, int M,
                        float* x_out, uint8_t* x_q, uint8_t* idx, void* stream);
 
 /* Plain discretized-logistic sampler (utils/discretized_logistic.py:80-85; models/model06.py:166 calls it on every

@@ -294,18 +294,19 @@ def mdl_plain_get_mixture_params(parameters: torch.Tensor):
     return loc, logscale, mix_logits
 
 
-def mdl_plain_log_prob(parameters: torch.Tensor, x01: torch.Tensor) -> torch.Tensor:
-    """``PixelMixtureDiscretizedLogistic.log_prob`` -- utils/mdl_plain.py:36-66 (default low=-1, high=1, levels=256).
+def mdl_plain_log_prob(parameters: torch.Tensor, x01: torch.Tensor, low=-1.0, high=1.0, levels=256.0) -> torch.Tensor:
+    """``PixelMixtureDiscretizedLogistic.log_prob`` -- utils/mdl_plain.py:36-66; ``low, high, levels`` are the constructor
+    arguments (:18) handed to the ``DiscretizedLogistic`` base (:28-30).
     Returns ``[..., H, W]`` (no trailing 1: :66 reduces over the mixture axis only)."""
     loc, logscale, mix_logits = mdl_plain_get_mixture_params(parameters)         # :27
     x = x01 * 2.0 - 1.0                                                          # :45
-    lp = dlogistic_log_prob(x[..., None], loc, logscale, -1.0, 1.0, 256.0)       # :49-51 (DiscretizedLogistic.log_prob)
+    lp = dlogistic_log_prob(x[..., None], loc, logscale, low, high, levels)      # :49-51 (DiscretizedLogistic.log_prob)
     mix_log_weights = _log_softmax(mix_logits, -1)                               # :55
     weighted = torch.sum(lp, dim=-2) + mix_log_weights                           # :59-61
     return _reduce_logsumexp(weighted, -1)                                       # :66
 
 
-def mdl_plain_sample(parameters: torch.Tensor, u_mix: torch.Tensor, u_log):
+def mdl_plain_sample(parameters: torch.Tensor, u_mix: torch.Tensor, u_log, low=-1.0, high=1.0):
     """``PixelMixtureDiscretizedLogistic.sample`` (utils/mdl_plain.py:68-102) / ``.mean`` (:104-121) with explicit noise:
     ``u_mix [..., H, W, M]`` selects the component (Gumbel-argmax stands in for tfd.Categorical), ``u_log
     [..., H, W, 3, M]`` drives ``DiscretizedLogistic.sample`` for every component (:86-88); ``u_log=None`` gives
@@ -316,7 +317,7 @@ def mdl_plain_sample(parameters: torch.Tensor, u_mix: torch.Tensor, u_log):
     if u_log is None:
         vals = loc                                                               # :116-118
     else:
-        vals = dlogistic_sample(loc, logscale, u_log, -1.0, 1.0)                 # :86-88 (clipped to [low, high])
+        vals = dlogistic_sample(loc, logscale, u_log, low, high)                 # :86-88 (clipped to [low, high])
     sel = torch.sum(vals * onehot, dim=-1)                                       # :93-95
     if u_log is None:
         sel = torch.clamp(sel, -1.0, 1.0)                                        # :119

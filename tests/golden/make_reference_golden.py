@@ -175,6 +175,9 @@ def sample_outputs(R, fx, dtype):
     return out
 
 
+PLAIN_BINS = (-0.95, 0.9, 64.0)   # a non-default (low, high, levels) for PixelMixtureDiscretizedLogistic
+
+
 def plain_outputs(R, fx, dtype):
     tf, tfp, U, L, M6 = R
     tag = "_f64" if dtype == torch.float64 else "_f32"
@@ -193,6 +196,18 @@ def plain_outputs(R, fx, dtype):
     out["x_sample" + tag] = _np(d.sample())
     tfp.push_uniforms(u_mix[None])
     out["x_mean" + tag] = _np(d.mean())
+    # the same class built with its own bin geometry (utils/mdl_plain.py:18): edges at low / high, 64 levels
+    pb = params.clone().requires_grad_(True)
+    db = U.PixelMixtureDiscretizedLogistic(tf.Tensor(pb), low=PLAIN_BINS[0], high=PLAIN_BINS[1], levels=PLAIN_BINS[2])
+    lpb = db.log_prob(tf.Tensor(x))
+    llb = tf.reduce_sum(lpb, axis=[-1, -2])
+    (llb.t * g_image).sum().backward()
+    out.update({"bins_lp" + tag: _np(lpb), "bins_ll" + tag: _np(llb), "bins_grad" + tag: pb.grad.numpy().copy()})
+    db = U.PixelMixtureDiscretizedLogistic(tf.Tensor(params), low=PLAIN_BINS[0], high=PLAIN_BINS[1], levels=PLAIN_BINS[2])
+    tfp.push_uniforms(u_mix[None], u_log[None])
+    out["bins_x_sample" + tag] = _np(db.sample())
+    tfp.push_uniforms(u_mix[None])
+    out["bins_x_mean" + tag] = _np(db.mean())
     # models/loss.py::iwae_loss with real Normal latents, beta = 0.7, MoDL (utils/mdl.py) observation model
     z = torch.from_numpy(fx["z"]).to(dtype).requires_grad_(True)
     ql = torch.from_numpy(fx["q_loc"]).to(dtype).requires_grad_(True)
@@ -230,10 +245,12 @@ def generate(name, fn, R=None):
     return out
 
 
-def main(check=False):
+def main(check=False, only=None):
     R = import_reference()
     worst = 0.0
     for name, fn in JOBS:
+        if only and name not in only:
+            continue
         out = generate(name, fn, R)
         path = os.path.join(HERE, "refsrc_" + name + ".npz")
         if check:
@@ -250,4 +267,4 @@ def main(check=False):
 
 
 if __name__ == "__main__":
-    main(check="--check" in sys.argv)
+    main(check="--check" in sys.argv, only=[a for a in sys.argv[1:] if not a.startswith("--")])

@@ -112,11 +112,17 @@ def test_config2_plain_dl_full_size(F, V):
     assert abs(loss.item() - want.item()) <= 1e-6 * abs(want.item())
     loss2, _, dloc2, dls2 = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)
     assert torch.equal(dloc, dloc2) and torch.equal(dls, dls2)
-    for s_i, b_i in [(0, 0), (4, 127)]:
+    # oracle spot checks on whole images: log-likelihood AND gradient (upstream = the softmax weights of the step)
+    g_ll = -torch.softmax(ll64, 0) / B
+    both_grad = torch.cat([dloc, dls], dim=-1)
+    for s_i, b_i in [(0, 0), (4, 127), (2, 63)]:
         b64 = both[s_i, b_i].cpu().double()[None].requires_grad_(True)
         x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
         w = O.dlogistic_log_prob(x64, b64[..., :3], b64[..., 3:], 0.0, 1.0, 256.0).sum()
         assert abs(ll64[s_i, b_i].item() - w.item()) <= LL_RTOL * abs(w.item())
+        (w * g_ll[s_i, b_i].item()).backward()
+        assert relnorm(both_grad[s_i, b_i], b64.grad[0]) <= GRAD_RTOL
+        assert relnorm(dloc[s_i, b_i], b64.grad[0][..., :3]) <= GRAD_RTOL and relnorm(dls[s_i, b_i], b64.grad[0][..., 3:]) <= GRAD_RTOL
 
 
 def test_config3_sampler_full_size(V):
@@ -234,3 +240,43 @@ def test_soak_bitwise_reproducible_under_back_to_back_steps(F, S, B, H, W, M, re
         bad += (out[0] != ref_ll).sum() + (out[4] != ref_g).sum() + (out[5] != ref_dp).sum() + (out[3] != ref_elbo).sum()
     assert int(bad.item()) == 0
     assert not bool(torch.isnan(ref_dp).any())
+
+
+@pytest.mark.parametrize("name,H,W,M", [("cfg5_64_m30", 64, 64, 30), ("cfg5_128_m10", 128, 128, 10),
+                                        ("cfg5_128_m30", 128, 128, 30)])
+def test_config5_other_sweep_points_full_size(F, V, name, H, W, M):
+    """The other three points of BASELINE configs[4] at their full per-GPU size (16 importance samples x 32 images):
+    whole-image oracle spot checks of the log-likelihood (1e-5) and of the gradient (1e-4) taken from both ends and the
+    middle of the tensor.  cfg5_128_m30 is the one shape whose element offsets exceed 2^31 (8.39 M pixel-samples x 300
+    floats = 2.5 G elements, 10 GB of parameters + 10 GB of gradients): its last image (15, 31) starts at element
+    2,511,667,200 -- the 64-bit indexing path of the tile kernel, the bulk copies and the partial-sum bookkeeping."""
+    S, B = 16, 32
+    gen = torch.Generator(device=DEV).manual_seed(700 + M + H)
+    params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
+    x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
+    extra = torch.randn(S, B, device=DEV, generator=gen)
+    if name == "cfg5_128_m30":
+        assert (S * B - 1) * H * W * 10 * M > 2 ** 31
+    ll64, log_w, lme_b, elbo, g_ll, dp, launches = F.modl_iwae_step(params, x_u8, extra)
+    assert launches == 3
+    lw = ll64 + extra.double()
+    want_lme = torch.logsumexp(lw, 0) - math.log(S)
+    assert ((lme_b.double() - want_lme).abs() / want_lme.abs()).max().item() < 1e-6
+    assert abs(elbo.item() - want_lme.mean().item()) <= 1e-6 * abs(want_lme.mean().item())
+    assert relnorm(g_ll, -torch.softmax(lw, 0) / B) < 1e-5
+    # the per-pixel entry point sums to the fused per-image values everywhere (every pixel of the tensor is visited once)
+    lp = F.modl_log_prob(params, x_u8)
+    assert ((lp.double().sum((-1, -2)) - ll64).abs() / ll64.abs()).max().item() < 1e-12
+    del lp
+    # the logit gradients of every pixel sum to zero, and no element is NaN / left unwritten
+    assert dp[..., :M].sum(-1).abs().max().item() < 2e-5 * g_ll.abs().max().item()
+    assert bool(torch.isfinite(dp).all())
+    for s_i, b_i in [(0, 0), (S - 1, B - 1), (7, B // 2)]:
+        p64 = params[s_i, b_i].cpu().double()[None].requires_grad_(True)
+        x64 = O.normalize_u8(x_u8[b_i].cpu(), torch.float64)[None]
+        want = O.modl_log_prob(p64, x64).sum()
+        assert abs(ll64[s_i, b_i].item() - want.item()) <= LL_RTOL * abs(want.item()), (name, s_i, b_i)
+        (want * g_ll[s_i, b_i].item()).backward()
+        assert relnorm(dp[s_i, b_i], p64.grad[0]) <= GRAD_RTOL, (name, s_i, b_i)
+    del dp, params
+    torch.cuda.empty_cache()

@@ -227,6 +227,64 @@ def test_fused_iwae_loss_gradients_wrt_latents_and_parameters(V):
     assert relnorm(ql.grad, ql64b.grad) < GRAD_RTOL and relnorm(qs.grad, qs64b.grad) < GRAD_RTOL
 
 
+def test_iwae_loss_with_the_references_constant_prior_and_singleton_sample_axis(V):
+    """The reference's own prior is ``Normal(0.0, 1.0)`` built from Python numbers (models/model05.py:108,
+    models/model06.py:185): 0-dim CPU tensors.  The fused route takes it as the parameter-free standard-normal term; an
+    encoder Normal whose parameters carry a singleton sample axis ``[1,B,D]`` gets its gradient back in that shape."""
+    g = torch.Generator().manual_seed(33)
+    S, B, H, W, M, D = 4, 5, 8, 8, 5, 12
+    params, x_u8, q_loc, q_scale, _ = _setup_model05_like(g, S, B, H, W, M, D)
+    eps = torch.randn(S, B, D, generator=g)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    pd = params.to(DEV).requires_grad_(True)
+    ql = q_loc.to(DEV)[None].clone().requires_grad_(True)     # [1, B, D]
+    qs = q_scale.to(DEV)[None].clone().requires_grad_(True)
+    z = ql + qs * eps.to(DEV)
+    pz = td.Normal(0.0, 1.0)
+    pz.axes = [-1]
+    qzx = td.Normal(ql, qs)
+    qzx.axes = [-1]
+    pxz = V.MixtureDiscretizedLogistic(pd)
+    from vae_mdl_b200 import loss as Lmod
+    assert Lmod._fusable(O.normalize_u8(x_u8).to(DEV), z, pz, qzx, pxz)
+    loss, met = V.iwae_loss(O.normalize_u8(x_u8).to(DEV), z, pz, qzx, pxz, beta=0.7)
+    p64 = params.double().requires_grad_(True)
+    ql64 = q_loc.double()[None].clone().requires_grad_(True)
+    qs64 = q_scale.double()[None].clone().requires_grad_(True)
+    z64 = ql64 + qs64 * eps.double()
+    loss64, met64 = O.iwae_loss(O.modl_log_prob(p64, x64), td.Normal(0.0, 1.0).log_prob(z64).sum(-1),
+                                td.Normal(ql64, qs64).log_prob(z64).sum(-1), x64.shape, beta=0.7)
+    loss64.backward()
+    assert abs(loss.item() - loss64.item()) <= LL_RTOL * abs(loss64.item())
+    assert relnorm(met["lpz"], met64["lpz"]) < 1e-6
+    loss.backward()
+    assert ql.grad.shape == (1, B, D) and qs.grad.shape == (1, B, D)
+    assert_grad_close(pd.grad, p64.grad, M)
+    assert relnorm(ql.grad, ql64.grad) < GRAD_RTOL and relnorm(qs.grad, qs64.grad) < GRAD_RTOL
+    # model06's loss_fn with the same constant prior (models/model06.py:185)
+    D2 = 7
+    mu = torch.rand(S, B, H, W, 3, generator=g)
+    lstd = torch.randn(S, B, H, W, 3, generator=g) - 2.0
+    z1 = torch.randn(S, B, D, generator=g)
+    z2 = torch.randn(S, B, D2, generator=g)
+    a1, b1 = torch.randn(B, D, generator=g), torch.rand(B, D, generator=g) + 0.5
+    a2, b2 = torch.randn(S, B, D2, generator=g), torch.rand(S, B, D2, generator=g) + 0.5
+    a3, b3 = torch.randn(S, B, D, generator=g), torch.rand(S, B, D, generator=g) + 0.5
+    dl = V.DiscretizedLogistic(mu.to(DEV), lstd.to(DEV), low=0.0, high=1.0, levels=256.0)
+    T = V.DistributionTuple
+    out, met6 = V.loss_fn(O.normalize_u8(x_u8).to(DEV), pz,
+                          T(td.Normal(a1.to(DEV), b1.to(DEV)), z1.to(DEV), [-1]),
+                          T(td.Normal(a2.to(DEV), b2.to(DEV)), z2.to(DEV), [-1]),
+                          T(td.Normal(a3.to(DEV), b3.to(DEV)), None, [-1]),
+                          T(dl, None, [-1, -2, -3]))
+    lp = O.dlogistic_log_prob(x64, mu.double(), lstd.double(), 0.0, 1.0, 256.0).sum((-1, -2, -3))
+    lw = (lp + td.Normal(0.0, 1.0).log_prob(z2.double()).sum(-1) - td.Normal(a2.double(), b2.double()).log_prob(z2.double()).sum(-1)
+          + td.Normal(a3.double(), b3.double()).log_prob(z1.double()).sum(-1)
+          - td.Normal(a1.double(), b1.double()).log_prob(z1.double()).sum(-1))
+    want = -(torch.logsumexp(lw, 0) - math.log(S)).mean()
+    assert abs(out.item() - want.item()) <= LL_RTOL * abs(want.item())
+
+
 def test_latent_terms_model06_shapes(V):
     """models/model06.py:40-47: four Normal terms, two latent layers of different width, per-sample and shared parameters;
     forward sums and every gradient against float64 autograd."""
@@ -330,3 +388,46 @@ def test_sample_sharded_step_single_process(built_lib):
     assert torch.equal(lpxz, ref[0])
     assert abs(loss.item() + ref[3].item()) <= 1e-6 * abs(ref[3].item())
     assert relnorm(dp, ref[5]) <= 1e-5
+
+
+@pytest.mark.parametrize("S,B,world", [(16, 256, 2), (16, 32, 8), (6, 5, 3), (5000, 3, 4)])
+def test_split_sample_kernels_equal_the_unsplit_tail(built_lib, S, B, world):
+    """vaemdl_iwae_split_local / _combine (importance samples spread over `world` ranks, the all_gather of the (max, sum-exp)
+    pairs simulated by a concatenation in rank order): log-mean-exp, ELBO and the local softmax weights equal the unsplit
+    vaemdl_iwae_tail and the float64 formula (utils/utils.py:9-11, models/loss.py:34-37)."""
+    from vae_mdl_b200 import _abi, dist as vdist, functional as F
+    L = _abi.lib()
+    g = torch.Generator().manual_seed(S + B)
+    ll = (torch.randn(S, B, generator=g, dtype=torch.float64) * 3 - 2.0e4).to(DEV)
+    extra = torch.randn(S, B, generator=g).to(DEV)
+    lw = ll + extra.double()
+    want_lme = torch.logsumexp(lw, 0) - math.log(S)
+    want_g = -torch.softmax(lw, 0) / B
+    st = _abi.stream_ptr(torch.device(DEV))
+    bounds = [vdist.shard_bounds(S, r, world) for r in range(world)]
+    pairs = torch.empty(world, 2, B, dtype=torch.float64, device=DEV)
+    for r, (lo, hi) in enumerate(bounds):
+        rc = L.vaemdl_iwae_split_local(ll[lo:hi].contiguous().data_ptr(), extra[lo:hi].contiguous().data_ptr(), hi - lo, B,
+                                       pairs[r].data_ptr(), st)
+        assert rc == 0
+    for r, (lo, hi) in enumerate(bounds):
+        lme = torch.empty(B, device=DEV)
+        elbo = torch.empty(1, device=DEV)
+        g_ll = torch.empty(hi - lo, B, device=DEV)
+        log_w = torch.empty(hi - lo, B, device=DEV)
+        rc = L.vaemdl_iwae_split_combine(ll[lo:hi].contiguous().data_ptr(), extra[lo:hi].contiguous().data_ptr(), hi - lo, B,
+                                         pairs.data_ptr(), world, S, 0, log_w.data_ptr(), lme.data_ptr(), elbo.data_ptr(),
+                                         g_ll.data_ptr(), st)
+        assert rc == 0
+        assert ((lme.double() - want_lme).abs() / want_lme.abs()).max().item() < 1e-6
+        assert abs(elbo.item() - want_lme.mean().item()) <= 1e-6 * abs(want_lme.mean().item())
+        assert relnorm(g_ll, want_g[lo:hi]) < 1e-6
+        assert relnorm(log_w, lw[lo:hi]) < 1e-6
+        if r == 0:
+            first = (lme.clone(), elbo.clone())
+        else:   # bit-identical on every rank
+            assert torch.equal(lme, first[0]) and torch.equal(elbo, first[1])
+    # world size 1 through the host helper == the fused tail
+    elbo1, g1 = vdist.split_sample_tail(ll, extra, S)
+    _, lme_t, elbo_t, g_t = F.iwae_tail(ll, extra)
+    assert abs(elbo1.item() - elbo_t.item()) <= 1e-6 * abs(elbo_t.item()) and relnorm(g1, g_t) < 1e-5

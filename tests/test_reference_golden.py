@@ -24,6 +24,7 @@ MODL = [("modl_m10_randn", 10), ("modl_m5_trained", 5), ("modl_m30_randn", 30), 
 # functions add the float64 constant np.log(127.5) (utils/mdl_openai.py:148).  float32(log(2/255)) is 1.2e-7 away from
 # the real number, so float64 runs of the two formulations differ by that much per low-probability sub-pixel.
 CAST_ABS = 4e-7
+PLAIN_BINS = (-0.95, 0.9, 64.0)   # tests/golden/make_reference_golden.py: the non-default PixelMixtureDiscretizedLogistic
 
 
 def refsrc(name):
@@ -172,6 +173,19 @@ def test_oracle_matches_reference_source_mdl_plain_and_full_iwae_loss():
     xm, _ = O.mdl_plain_sample(torch.from_numpy(fx["params"]), torch.from_numpy(fx["u_mix"]), None)
     assert (xs - t64(rs["x_sample_f64"])).abs().max().item() <= 1e-12
     assert (xm - t64(rs["x_mean_f64"])).abs().max().item() <= 1e-12
+    # the class built with its own (low, high, levels) (utils/mdl_plain.py:18)
+    pb = torch.from_numpy(fx["params"]).double().requires_grad_(True)
+    lpb = O.mdl_plain_log_prob(pb, x, *PLAIN_BINS)
+    llb = lpb.sum((-1, -2))
+    (llb * t64(fx["g_image"])).sum().backward()
+    assert (lpb.detach() - t64(rs["bins_lp_f64"])).abs().max().item() <= CAST_ABS * 15
+    assert_ll_close(llb, rs["bins_ll_f64"], rtol=1e-8)
+    assert relnorm(pb.grad, t64(rs["bins_grad_f64"])) <= 1e-7
+    assert (lpb.detach() - lp.detach()).abs().max().item() > 0.5          # (it is a different density)
+    xsb, _ = O.mdl_plain_sample(torch.from_numpy(fx["params"]), torch.from_numpy(fx["u_mix"]), torch.from_numpy(fx["u_log"]),
+                                PLAIN_BINS[0], PLAIN_BINS[1])
+    assert (xsb - t64(rs["bins_x_sample_f64"])).abs().max().item() <= 1e-12
+    assert (xm - t64(rs["bins_x_mean_f64"])).abs().max().item() <= 1e-12  # mean() clips to [-1, 1] whatever low / high (:115)
     # iwae_loss with Normal latents, beta = 0.7 (models/loss.py:26-55 executed by the reference's code)
     import torch.distributions as td
     z = t64(fx["z"]).requires_grad_(True)
@@ -309,6 +323,19 @@ def test_gpu_mdl_plain_and_full_iwae_loss_match_reference_source(V):
     assert torch.equal(O.quantise(xs.cpu().double()), O.quantise(t64(rs["x_sample_f64"])))
     xm = d0.mean(u_mix=u_mix[None])
     assert (xm.cpu().double() - t64(rs["x_mean_f64"])).abs().max().item() <= 1e-6
+    # the class built with its own (low, high, levels) (utils/mdl_plain.py:18): edges at low / high, 64 levels
+    pb = params.clone().requires_grad_(True)
+    db = V.PixelMixtureDiscretizedLogistic(pb, low=PLAIN_BINS[0], high=PLAIN_BINS[1], levels=PLAIN_BINS[2])
+    lpb = db.log_prob(x)
+    assert (lpb.detach().cpu().double() - t64(rs["bins_lp_f64"])).abs().max().item() < 5e-5
+    llb = db.log_likelihood(x, dtype=torch.float64)
+    assert_ll_close(llb, rs["bins_ll_f64"])
+    (lpb.sum((-1, -2)) * torch.from_numpy(fx["g_image"]).to(DEV)).sum().backward()
+    assert_grad_close(pb.grad, rs["bins_grad_f64"], 5)
+    db0 = V.PixelMixtureDiscretizedLogistic(params, low=PLAIN_BINS[0], high=PLAIN_BINS[1], levels=PLAIN_BINS[2])
+    xsb = db0.sample(u_mix=u_mix[None], u_log=u_log[None])
+    assert (xsb.cpu().double() - t64(rs["bins_x_sample_f64"])).abs().max().item() <= 1e-6
+    assert (db0.mean(u_mix=u_mix[None]).cpu().double() - t64(rs["bins_x_mean_f64"])).abs().max().item() <= 1e-6
     # models/loss.py::iwae_loss with Normal latents, beta = 0.7: the package's iwae_loss (fused route) vs the reference's
     z = torch.from_numpy(fx["z"]).to(DEV).requires_grad_(True)
     ql = torch.from_numpy(fx["q_loc"]).to(DEV).requires_grad_(True)

@@ -46,7 +46,7 @@ PROTOTYPES = {
                                       c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vaemdl_modl_plain_iwae_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
-                                            c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "vaemdl_modl_step_workspace_bytes": (c_size_t, [c_longlong, c_int, c_int]),
     "vaemdl_modl_iwae_fwd_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int,
@@ -64,12 +64,12 @@ PROTOTYPES = {
     "vaemdl_modl_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_plain_fwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_plain_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,
-                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_plain_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
-                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_workspace_bytes": (c_size_t, [c_longlong, c_longlong]),
     "vaemdl_dlogistic_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_longlong, c_int, c_longlong,
                                      c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -91,8 +91,13 @@ PROTOTYPES = {
                                         c_void_p]),
     "vaemdl_iwae_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "vaemdl_iwae_split_local": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+    "vaemdl_iwae_split_combine": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_longlong, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_modl_plain_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_longlong, c_longlong, c_int,
+                                         c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_dlogistic_sample": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_longlong, c_float, c_float,
                                         c_void_p, c_void_p]),
     "vaemdl_modl_iwae_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

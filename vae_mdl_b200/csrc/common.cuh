@@ -168,7 +168,10 @@ const DeviceInfo& device_info();  // cached per current device (api_misc.cu)
 // one float64 partial per image its run touched, at partial[n*K + (w - first warp whose run touches image n)]: the
 // partials of one image are contiguous and in warp order.  HW = rows per image.
 constexpr long long kMaxGridWarps = 8192;  // bound on (CTAs x warps) of such a grid: sizes the partial-sum workspace
-inline size_t partial_elems(long long n_img) { return 3 * static_cast<size_t>(n_img) + 3 * kMaxGridWarps + 64; }
+// n_img * K <= 2 * n_img + 6 * (grid warps) for every plan the launchers can pick (K = tpi / tw_base + 2 with
+// tpi <= 3 * HW / PPT and tw_base >= tiles / (2 * warps)); the launchers check the plan against this before enqueuing
+inline size_t partial_elems(long long n_img) { return 3 * static_cast<size_t>(n_img) + 6 * kMaxGridWarps + 64; }
+inline bool partials_fit(long long n_img, int K) { return static_cast<size_t>(n_img) * static_cast<size_t>(K) <= partial_elems(n_img); }
 // K: the largest number of warp runs one image can intersect (runs are tw_base or tw_base + 1 tiles long)
 inline int partial_K(long long HW, int PPT, long long tw_base) {
   const long long tpi = (HW + PPT - 1) / PPT + 1;  // tiles an image can overlap

@@ -737,6 +737,7 @@ static int dl_launch(DlArgs a, int cpt, int kind, cudaStream_t st, PartialGeom* 
   a.tw_base = n_tiles / total_warps;
   a.tw_rem = n_tiles % total_warps;
   a.K = partial_K(a.rows_per_img, TR, a.tw_base);
+  if (a.partial && !partials_fit(a.n_rows / a.rows_per_img, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   if (geom) *geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, TR, a.rows_per_img};
   const unsigned grid = static_cast<unsigned>(blocks);
   if (kind == 1)
@@ -796,7 +797,6 @@ static int dl_fwd_impl(const float* loc, const float* logscale, int C, int ld, c
   PartialGeom geom{};
   rc = dl_launch<false>(a, cpt, kind, st, &geom);
   if (rc) return rc;
-  if (use_partials && static_cast<size_t>(n_img) * geom.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
   if (use_partials)
     return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
   if (!want_ll) return VAEMDL_OK;
@@ -937,7 +937,7 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   a.tw_base = n_tiles / total_warps;
   a.tw_rem = n_tiles % total_warps;
   a.K = partial_K(a.rows_per_img, 64, a.tw_base);
-  if (static_cast<size_t>(n_img) * a.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+  if (!partials_fit(n_img, a.K)) return VAEMDL_EWORKSPACE;
   DlStepArgs sa{};
   sa.a = a;
   sa.T = T;

@@ -38,6 +38,7 @@ struct HostCtx {
   float* lme_full = nullptr;    // [B]
   size_t extra_full_bytes = 0, ll_full_bytes = 0, lme_full_bytes = 0;
   cudaEvent_t x_ready = nullptr;
+  std::mutex mu;  // one step at a time per device; callers on different devices do not wait for each other
 };
 
 static std::mutex g_mu;
@@ -54,22 +55,48 @@ static cudaError_t grow(T*& p, size_t& have, size_t want) {
   return e;
 }
 
-static HostCtx* get_ctx() {
+// the per-device context (staging slots, streams); *err reports a failed stream / event creation
+static HostCtx* get_ctx(cudaError_t* err) {
+  *err = cudaSuccess;
   int dev = 0;
-  cudaGetDevice(&dev);
+  if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return nullptr;
   for (HostCtx* c : g_ctxs)
     if (c->device == dev) return c;
   HostCtx* c = new HostCtx();
   c->device = dev;
-  for (auto& s : c->slots) cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming);
+  for (auto& s : c->slots) {
+    if (*err == cudaSuccess) *err = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+  }
+  if (*err == cudaSuccess) *err = cudaEventCreateWithFlags(&c->x_ready, cudaEventDisableTiming);
+  if (*err != cudaSuccess) {  // never hand out a context whose null streams would alias the legacy stream
+    for (auto& s : c->slots)
+      if (s.stream) cudaStreamDestroy(s.stream);
+    if (c->x_ready) cudaEventDestroy(c->x_ready);
+    delete c;
+    return nullptr;
+  }
   g_ctxs.push_back(c);
   return c;
+}
+
+// An error return must not leave copies in flight that still read / write the caller's host buffers.
+static int drain(HostCtx* c, int rc) {
+  for (auto& s : c->slots)
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  cudaGetLastError();
+  return rc;
 }
 
 }  // namespace vaemdl
 
 using namespace vaemdl;
+
+// from the first enqueued copy on: wait for everything in flight before reporting the error
+#define VAEMDL_TRY_DRAIN(expr)                            \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
+    if (e__ != cudaSuccess) return drain(c, cuda_rc(e__)); \
+  } while (0)
 
 #define VAEMDL_TRY(expr)                       \
   do {                                         \
@@ -83,8 +110,14 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
   if (!params_host || !x_host || !ll_host || !lme_host || !elbo_host) return VAEMDL_EINVAL;
   if (S <= 0 || B <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
   if (M < 1 || M > VAEMDL_MAX_MIX) return VAEMDL_EUNSUPPORTED;
-  std::lock_guard<std::mutex> lock(g_mu);
-  HostCtx* c = get_ctx();
+  cudaError_t ctx_err = cudaSuccess;
+  HostCtx* c;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);  // the registry only
+    c = get_ctx(&ctx_err);
+  }
+  if (!c) return cuda_rc(ctx_err);
+  std::lock_guard<std::mutex> step_lock(c->mu);
   const size_t HW = static_cast<size_t>(H) * W;
   const size_t img_bytes = HW * 10 * M * sizeof(float);  // one (s,b) image of parameters
   if (chunk_b <= 0) {
@@ -120,11 +153,11 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
   }
 
   // the observed images: one small copy, every slot stream waits for it
-  VAEMDL_TRY(cudaMemcpyAsync(c->x, x_host, static_cast<size_t>(B) * HW * 3, cudaMemcpyHostToDevice, c->slots[0].stream));
+  VAEMDL_TRY_DRAIN(cudaMemcpyAsync(c->x, x_host, static_cast<size_t>(B) * HW * 3, cudaMemcpyHostToDevice, c->slots[0].stream));
   if (extra_host)
-    VAEMDL_TRY(cudaMemcpyAsync(c->extra_full, extra_host, sb_bytes, cudaMemcpyHostToDevice, c->slots[0].stream));
-  VAEMDL_TRY(cudaEventRecord(c->x_ready, c->slots[0].stream));
-  for (int k = 1; k < kSlots; ++k) VAEMDL_TRY(cudaStreamWaitEvent(c->slots[k].stream, c->x_ready, 0));
+    VAEMDL_TRY_DRAIN(cudaMemcpyAsync(c->extra_full, extra_host, sb_bytes, cudaMemcpyHostToDevice, c->slots[0].stream));
+  VAEMDL_TRY_DRAIN(cudaEventRecord(c->x_ready, c->slots[0].stream));
+  for (int k = 1; k < kSlots; ++k) VAEMDL_TRY_DRAIN(cudaStreamWaitEvent(c->slots[k].stream, c->x_ready, 0));
 
   const size_t host_pitch = img_bytes * B;  // bytes between consecutive s in the host tensors
   // Chunk schedule: the first chunk's upload and the last chunk's download have nothing to overlap with, so the two
@@ -139,33 +172,33 @@ extern "C" int vaemdl_modl_iwae_step_host(const float* params_host, const uint8_
     const size_t width = img_bytes * cb;
     const long long n_img = static_cast<long long>(S) * cb;
     // [S, B, ...] host  ->  [S, cb, ...] device: S rows of `width` bytes
-    VAEMDL_TRY(cudaMemcpy2DAsync(s.params, width, reinterpret_cast<const char*>(params_host) + img_bytes * b0, host_pitch,
+    VAEMDL_TRY_DRAIN(cudaMemcpy2DAsync(s.params, width, reinterpret_cast<const char*>(params_host) + img_bytes * b0, host_pitch,
                                  width, S, cudaMemcpyHostToDevice, s.stream));
     if (extra_host)  // [S, B] -> the chunk's dense [S, cb], device to device
-      VAEMDL_TRY(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), c->extra_full + b0, static_cast<size_t>(B) * sizeof(float),
+      VAEMDL_TRY_DRAIN(cudaMemcpy2DAsync(s.extra, cb * sizeof(float), c->extra_full + b0, static_cast<size_t>(B) * sizeof(float),
                                    cb * sizeof(float), S, cudaMemcpyDeviceToDevice, s.stream));
     // forward + fused finish (per-image sums, log-mean-exp, softmax weights normalised by the WHOLE batch): 2 launches
     int rc = vaemdl_modl_iwae_fwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
                                   VAEMDL_EDGE_MDL, S, cb, B, cb, H, W, M, extra_host ? s.extra : nullptr, s.ll, nullptr,
                                   nullptr, s.lme, nullptr, dparams_host ? s.g_ll : nullptr, s.ws, s.ws_bytes, s.stream);
-    if (rc) return rc;
-    VAEMDL_TRY(cudaMemcpy2DAsync(c->ll_full + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
+    if (rc) return drain(c, rc);
+    VAEMDL_TRY_DRAIN(cudaMemcpy2DAsync(c->ll_full + b0, static_cast<size_t>(B) * sizeof(float), s.ll, cb * sizeof(float),
                                  cb * sizeof(float), S, cudaMemcpyDeviceToDevice, s.stream));
-    VAEMDL_TRY(cudaMemcpyAsync(c->lme_full + b0, s.lme, cb * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
+    VAEMDL_TRY_DRAIN(cudaMemcpyAsync(c->lme_full + b0, s.lme, cb * sizeof(float), cudaMemcpyDeviceToDevice, s.stream));
     if (dparams_host) {
       rc = vaemdl_modl_bwd(s.params, c->x + static_cast<size_t>(b0) * HW * 3, VAEMDL_X_U8, VAEMDL_RANGE_UNIT,
                            VAEMDL_EDGE_MDL, n_img, cb, H, W, M, s.g_ll, nullptr, s.grads, s.stream);
-      if (rc) return rc;
-      VAEMDL_TRY(cudaMemcpy2DAsync(reinterpret_cast<char*>(dparams_host) + img_bytes * b0, host_pitch, s.grads, width,
+      if (rc) return drain(c, rc);
+      VAEMDL_TRY_DRAIN(cudaMemcpy2DAsync(reinterpret_cast<char*>(dparams_host) + img_bytes * b0, host_pitch, s.grads, width,
                                    width, S, cudaMemcpyDeviceToHost, s.stream));
     }
     b0 += cb;
   }
-  for (auto& s : c->slots) VAEMDL_TRY(cudaStreamSynchronize(s.stream));
-  VAEMDL_TRY(cudaMemcpyAsync(ll_host, c->ll_full, sb_bytes, cudaMemcpyDeviceToHost, c->slots[0].stream));
-  VAEMDL_TRY(cudaMemcpyAsync(lme_host, c->lme_full, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToHost,
+  for (auto& s : c->slots) VAEMDL_TRY_DRAIN(cudaStreamSynchronize(s.stream));
+  VAEMDL_TRY_DRAIN(cudaMemcpyAsync(ll_host, c->ll_full, sb_bytes, cudaMemcpyDeviceToHost, c->slots[0].stream));
+  VAEMDL_TRY_DRAIN(cudaMemcpyAsync(lme_host, c->lme_full, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToHost,
                              c->slots[0].stream));
-  VAEMDL_TRY(cudaStreamSynchronize(c->slots[0].stream));
+  VAEMDL_TRY_DRAIN(cudaStreamSynchronize(c->slots[0].stream));
   double acc = 0.0;
   for (int b = 0; b < B; ++b) acc += static_cast<double>(lme_host[b]);  // models/loss.py:37 (mean over the batch)
   elbo_host[0] = static_cast<float>(acc / B);
@@ -177,6 +210,7 @@ extern "C" void vaemdl_host_release(void) {
   int cur = 0;
   cudaGetDevice(&cur);
   for (HostCtx* c : g_ctxs) {
+    { std::lock_guard<std::mutex> wait_for_step(c->mu); }  // a step in flight on that device finishes first
     cudaSetDevice(c->device);
     for (auto& s : c->slots) {
       if (s.stream) cudaStreamSynchronize(s.stream);

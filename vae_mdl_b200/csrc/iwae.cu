@@ -176,3 +176,80 @@ extern "C" int vaemdl_iwae_tail(const float* ll, const double* ll_f64, const flo
   }
   return rc;
 }
+
+// ---- importance samples split across ranks (second row) ---------------------------------------------------------
+// Each rank holds S_local of the S_total samples of every image.  The log-mean-exp over s (utils/utils.py:9-11) needs one
+// exchange of a (max, sum exp) pair per image: split_local forms the rank's pairs, the caller all-gathers them
+// ([world, 2, B] float64, rank order), split_combine turns them into the global log-mean-exp, the ELBO and the softmax
+// weights of the LOCAL samples (the upstream gradient of the rank's slice).  Every rank computes bit-identical lme / elbo
+// (pairs are combined in rank order, the batch mean in a fixed order).
+namespace vaemdl {
+__device__ __forceinline__ double split_log_w(const double* ll64, const float* extra, long long i) {
+  return ll64[i] + (extra ? static_cast<double>(extra[i]) : 0.0);  // models/loss.py:34
+}
+__global__ void __launch_bounds__(kLmeThreads)
+    split_local_kernel(const double* __restrict__ ll64, const float* __restrict__ extra, int S, long long B,
+                       double* __restrict__ pair) {
+  const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double mx = -INFINITY;
+  for (int s = 0; s < S; ++s) mx = fmax(mx, split_log_w(ll64, extra, static_cast<long long>(s) * B + b));
+  double sm = 0.0;
+  for (int s = 0; s < S; ++s) sm += exp(split_log_w(ll64, extra, static_cast<long long>(s) * B + b) - mx);
+  pair[b] = mx;
+  pair[B + b] = sm;
+}
+// one block: thread t takes images t, t + 256, ...; the batch mean is a fixed-order tree over the block
+__global__ void __launch_bounds__(kLmeThreads)
+    split_combine_kernel(const double* __restrict__ ll64, const float* __restrict__ extra, int S, long long B,
+                         const double* __restrict__ pairs, int world, double s_total, double b_norm,
+                         float* __restrict__ log_w_out, float* __restrict__ lme_b, float* __restrict__ elbo,
+                         float* __restrict__ g_ll) {
+  __shared__ double red[kLmeThreads];
+  double acc = 0.0;
+  for (long long b = threadIdx.x; b < B; b += kLmeThreads) {
+    double gmax = -INFINITY;
+    for (int r = 0; r < world; ++r) gmax = fmax(gmax, pairs[(static_cast<long long>(r) * 2) * B + b]);
+    double gsum = 0.0;
+    for (int r = 0; r < world; ++r)
+      gsum += pairs[(static_cast<long long>(r) * 2 + 1) * B + b] * exp(pairs[(static_cast<long long>(r) * 2) * B + b] - gmax);
+    const double lme = gmax + log(gsum / s_total);  // utils/utils.py:11 over all S_total samples
+    if (lme_b) lme_b[b] = static_cast<float>(lme);
+    acc += lme;
+    const double scale = -1.0 / (gsum * b_norm);  // d(-mean_b lme_b) / d log_w[s,b] = -softmax_s / B
+    for (int s = 0; s < S; ++s) {
+      const long long i = static_cast<long long>(s) * B + b;
+      const double v = split_log_w(ll64, extra, i);
+      if (log_w_out) log_w_out[i] = static_cast<float>(v);
+      if (g_ll) g_ll[i] = static_cast<float>(exp(v - gmax) * scale);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kLmeThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && elbo) elbo[0] = static_cast<float>(red[0] / b_norm);  // models/loss.py:37
+}
+}  // namespace vaemdl
+
+extern "C" int vaemdl_iwae_split_local(const double* ll_f64, const float* extra, int S_local, long long B, double* pair_out,
+                                       void* stream) {
+  if (!ll_f64 || !pair_out || S_local <= 0 || B <= 0) return VAEMDL_EINVAL;
+  const long long grid = (B + kLmeThreads - 1) / kLmeThreads;
+  split_local_kernel<<<static_cast<unsigned>(grid), kLmeThreads, 0, static_cast<cudaStream_t>(stream)>>>(ll_f64, extra, S_local,
+                                                                                                       B, pair_out);
+  return cuda_rc(cudaGetLastError());
+}
+
+extern "C" int vaemdl_iwae_split_combine(const double* ll_f64, const float* extra, int S_local, long long B,
+                                         const double* pairs_all, int world, int S_total, long long B_total, float* log_w,
+                                         float* lme_b, float* elbo, float* g_ll, void* stream) {
+  if (!ll_f64 || !pairs_all || S_local <= 0 || B <= 0 || world <= 0 || S_total < S_local || B_total < 0) return VAEMDL_EINVAL;
+  if (B_total == 0) B_total = B;
+  split_combine_kernel<<<1, kLmeThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      ll_f64, extra, S_local, B, pairs_all, world, static_cast<double>(S_total), static_cast<double>(B_total), log_w, lme_b,
+      elbo, g_ll);
+  return cuda_rc(cudaGetLastError());
+}

@@ -55,7 +55,17 @@ struct ModlArgs {
   int spread;  // 1: run r belongs to warp (r / #CTAs) of CTA (r % #CTAs), 0: to warp (r % warps) of CTA (r / warps)
   // run-time tile geometry (modl_rt_kernel: any n_mix without its own instantiation)
   int rt_MC, rt_LPP, rt_PPT, rt_rot, rt_warp_f;
+  // bin geometry of the un-conditioned pixel mixture (utils/mdl_plain.py:18, utils/discretized_logistic.py:10-21): the
+  // x-conditioned classes (AR = 0) are fixed to 8-bit pixels on [-1, 1] and keep kDx / kWidth / kLsNarrow as compile-time
+  // constants; the AR = 1 instantiations read these
+  float low, high;   // edge tests x <= low / x >= high (AR = 0: -1 / 1)
+  float dx, width;   // half bin width, bin width = (high - low) / (levels - 1)
+  float ls_narrow;   // log-scales below this have h = exp(-ls) * dx >= kHSmall
 };
+template <int AR>
+__device__ __forceinline__ float bin_dx(const ModlArgs& a) { return AR ? a.dx : kDx; }
+template <int AR>
+__device__ __forceinline__ float bin_width(const ModlArgs& a) { return AR ? a.width : kWidth; }
 
 // Which run of consecutive tiles a warp owns.  The first tw_rem runs are one tile longer than the rest; numbering the
 // runs CTA-minor spreads those evenly over the SMs (CTA-major puts all of them on the first tw_rem / warps SMs, which
@@ -125,10 +135,12 @@ __device__ __forceinline__ const float* param_row(const ModlArgs& a, long long i
 struct Pixel {  // one pixel: both halves of a packed register see the same observation
   float x[3];
   bool left[3], right[3];
+  float dx = kDx, width = kWidth;  // bin geometry (compile-time constants for the x-conditioned classes)
 };
 struct PixelPair {  // two pixels: lo half = pixel A, hi half = pixel B (the pixel-pair kernel for small n_mix)
   f2 x[3];
   bool ll[3], lh[3], rl[3], rh[3];
+  float dx = kDx, width = kWidth;
 };
 struct EdgeFlags {  // x at the lowest / highest bin, per half
   bool ll, lh, rl, rh;
@@ -156,9 +168,11 @@ __device__ __forceinline__ void load_pixel(const ModlArgs& a, long long n, int p
     }
     if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);  // utils/mdl.py:65
     px.x[c] = v;
-    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
-    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= a.low);
+    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= a.high);
   }
+  px.dx = a.dx;
+  px.width = a.width;
 }
 
 // ---- rare fallback: one mixture's  logit + sum_c log f_c  in the log domain, straight from global memory -------
@@ -179,7 +193,7 @@ static __device__ __noinline__ float modl_logt(const float* __restrict__ row, in
       if (c == 1) a1 = loc;
     }
     const float ls = fmaxf(ld_param(row, M + c * 3 * M + M + m, bf16), -7.0f);
-    t += subpix_logf(px.x[c], px.left[c], px.right[c], loc, ls, kDx, kWidth);
+    t += subpix_logf(px.x[c], px.left[c], px.right[c], loc, ls, px.dx, px.width);
   }
   return t;
 }
@@ -256,9 +270,9 @@ __device__ __forceinline__ float mix_fwd(const Pixel& px, const float mu[3], con
   const float a1 = plain ? loc1 : px.x[1];
   const float loc2 = fmaf(k2, a1, fmaf(k1, a0, mu[2]));              // utils/mdl.py:141-145 | utils/mdl_plain.py:162
   SubF f0, f1, f2;
-  subpix<false>(px.x[0], px.left[0], px.right[0], loc0, fmaxf(s[0], -7.0f), kDx, kWidth, f0);
-  subpix<false>(px.x[1], px.left[1], px.right[1], loc1, fmaxf(s[1], -7.0f), kDx, kWidth, f1);
-  subpix<false>(px.x[2], px.left[2], px.right[2], loc2, fmaxf(s[2], -7.0f), kDx, kWidth, f2);
+  subpix<false>(px.x[0], px.left[0], px.right[0], loc0, fmaxf(s[0], -7.0f), px.dx, px.width, f0);
+  subpix<false>(px.x[1], px.left[1], px.right[1], loc1, fmaxf(s[1], -7.0f), px.dx, px.width, f1);
+  subpix<false>(px.x[2], px.left[2], px.right[2], loc2, fmaxf(s[2], -7.0f), px.dx, px.width, f2);
   return (f0.num * f1.num * f2.num) * rcpa(f0.den * f1.den * f2.den);
 }
 
@@ -275,7 +289,7 @@ __device__ __forceinline__ float mix_bwd(const Pixel& px, const float mu[3], con
   loc[2] = fmaf(k[2], a1, fmaf(k[1], a0, mu[2]));
   SubB f[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) subpix<true>(px.x[c], px.left[c], px.right[c], loc[c], fmaxf(s[c], -7.0f), kDx, kWidth, f[c]);
+  for (int c = 0; c < 3; ++c) subpix<true>(px.x[c], px.left[c], px.right[c], loc[c], fmaxf(s[c], -7.0f), px.dx, px.width, f[c]);
   const float d01 = f[0].den * f[1].den;
   const float R = rcpa(d01 * f[2].den);
   float rd[3];
@@ -318,12 +332,12 @@ struct Sub2 {
 };
 
 template <bool NARROW, bool BWD>
-__device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub2& o) {
+__device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub2& o, float dx, float width) {
   const f2 ls = max_2(s_raw, -7.0f);                                  // utils/mdl.py:109
   const f2 inv = ex2_2(ls * (-kLog2e));
   const f2 mid = inv * (x - loc);
   const f2 A = ex2_negabs_2(mid * kLog2e);
-  const f2 h = inv * kDx;
+  const f2 h = inv * dx;
   f2 q = fma2(h, -1.0f / 720.0f, 1.0f / 120.0f);
   q = fma2(h, q, -1.0f / 24.0f);
   q = fma2(h, q, 1.0f / 6.0f);
@@ -350,7 +364,7 @@ __device__ __forceinline__ void subpix2(f2 x, EdgeFlags e, f2 loc, f2 s_raw, Sub
   const f2 den_n = ApG * opAG;
   const f2 thr = den_n * 1e-5f;
   const bool il = lo(num_n) > lo(thr), ih = hi(num_n) > hi(thr);    // sigmoid(p)-sigmoid(q) > 1e-5 (utils/mdl.py:193)
-  const f2 num_l = (A * inv) * kWidth;
+  const f2 num_l = (A * inv) * width;
   const f2 den_l = opA * opA;
   f2 num = sel_2(il, ih, num_n, num_l);
   f2 den = sel_2(il, ih, den_n, den_l);
@@ -430,7 +444,7 @@ __device__ __forceinline__ f2 pair_eval(const PX& px, const f2 mu[3], const f2 s
   loc[2] = fma2(k[2], x1, fma2(k[1], x0, mu[2]));               // utils/mdl.py:141-145 | utils/mdl_plain.py:162
   Sub2 f[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) subpix2<NARROW, BWD>(px_x(px, c), px_edge(px, c), loc[c], s[c], f[c]);
+  for (int c = 0; c < 3; ++c) subpix2<NARROW, BWD>(px_x(px, c), px_edge(px, c), loc[c], s[c], f[c], px.dx, px.width);
   const f2 d01 = f[0].den * f[1].den;
   const f2 R = rcp_2(d01 * f[2].den);
   const f2 P = (f[0].num * f[1].num) * (f[2].num * R);

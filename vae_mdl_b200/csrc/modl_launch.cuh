@@ -109,6 +109,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  if (a.partial && !partials_fit(a.n_px / a.HW, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   apply_l2_opt(a, total_warps, T::TILE_B / (PD ? 2 : 1));
   if (plan) {
     plan->total_warps = total_warps;
@@ -175,7 +176,7 @@ static int launch_step(ModlArgs a, StepFinish f, long long n_img, cudaStream_t s
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
-  if (static_cast<size_t>(n_img) * a.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
+  if (!partials_fit(n_img, a.K)) return VAEMDL_EWORKSPACE;
   a.reverse = 1;
   a.keep_tiles = 0;
   a.bwd_hint = 0;
@@ -226,6 +227,7 @@ static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  if (a.partial && !partials_fit(a.n_px / a.HW, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   a.small = a.n_px < (1ll << 31) - 64;
   apply_l2_opt(a, total_warps, T::TILE_B);
   if (plan) {
@@ -375,6 +377,7 @@ static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan*
   a.tw_base = a.num_tiles / total_warps;
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, rp.PPT, a.tw_base);
+  if (a.partial && !partials_fit(a.n_px / a.HW, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   a.small = a.n_px < (1ll << 31) - 64;
   apply_l2_opt(a, total_warps, static_cast<long long>(tile_f) * (PD ? 2 : 4));
   if (plan) {
@@ -478,6 +481,24 @@ static int tile_ppt(int M, long long n_px, bool bf16 = false) {
   }
 }
 
+// bin geometry of the class (utils/discretized_logistic.py:10-21); the x-conditioned classes are fixed to the default
+struct BinGeom {
+  float low = -1.0f, high = 1.0f, levels = 256.0f;
+  bool is_default() const { return low == -1.0f && high == 1.0f && levels == 256.0f; }
+};
+static int set_bins(ModlArgs& a, const BinGeom& g, int AR) {
+  if (!(g.levels > 1.0f) || !(g.high > g.low)) return VAEMDL_EINVAL;
+  if (AR == 0 && !g.is_default()) return VAEMDL_EUNSUPPORTED;
+  a.low = g.low;
+  a.high = g.high;
+  const double width = (static_cast<double>(g.high) - static_cast<double>(g.low)) / (static_cast<double>(g.levels) - 1.0);
+  a.width = static_cast<float>(width);          // utils/discretized_logistic.py:18
+  a.dx = static_cast<float>(width / 2.0);       // :21
+  // h = exp(-ls) * dx >= kHSmall  <=>  ls <= log(dx / kHSmall); nudged up so the cut errs towards the exact exp(-h)
+  a.ls_narrow = g.is_default() ? kLsNarrow : static_cast<float>(log(width / 2.0 / static_cast<double>(kHSmall)) + 1e-4);
+  return VAEMDL_OK;
+}
+
 static int check_common(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                         int x_batch, int H, int W, int M) {
   if (!params || !x) return VAEMDL_EINVAL;
@@ -499,7 +520,7 @@ template <int AR>
 static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, float* lp_pixel, float* ll_image, double* ll_image_f64,
                          const IwaeOut& iw, void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0,
-                         float* pix_stats = nullptr) {
+                         float* pix_stats = nullptr, const BinGeom& bins = BinGeom{}) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   const bool iwae = iw.S > 0;
@@ -519,6 +540,7 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.M = M;
   a.bf16 = bf16;
   a.pix_stats = reinterpret_cast<float2*>(pix_stats);
+  if ((rc = set_bins(a, bins, AR))) return rc;
   const int ppt = tile_ppt(M, a.n_px, bf16 != 0);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
   char* ws = static_cast<char*>(workspace);
@@ -542,7 +564,6 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   rc = launch_modl<false, AR>(a, st, &plan);
   if (rc) return rc;
   if (use_partials) {
-    if (static_cast<size_t>(n_img) * plan.K > partial_elems(n_img)) return VAEMDL_EWORKSPACE;
     const PartialGeom geom{a.partial, plan.tw_base, plan.tw_rem, plan.K, plan.PPT, a.HW};
     return finish_partials(geom, n_img, ll_image, ll_image_f64, iw, reinterpret_cast<double*>(ws + tail_off), counter, st);
   }
@@ -561,7 +582,7 @@ namespace vaemdl {
 template <int AR>
 static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, long long n_img,
                          int x_batch, int H, int W, int M, const float* g_image, const float* g_pixel, float* dparams,
-                         cudaStream_t st, int bf16 = 0, const float* pix_stats = nullptr) {
+                         cudaStream_t st, int bf16 = 0, const float* pix_stats = nullptr, const BinGeom& bins = BinGeom{}) {
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
   if (rc) return rc;
   if (!dparams || (!g_image && !g_pixel)) return VAEMDL_EINVAL;
@@ -582,6 +603,7 @@ static int modl_bwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.bf16 = bf16;
   a.pix_stats = reinterpret_cast<float2*>(const_cast<float*>(pix_stats));
   if (pix_stats && (reinterpret_cast<uintptr_t>(pix_stats) & 7u)) return VAEMDL_EALIGN;
+  if ((rc = set_bins(a, bins, AR))) return rc;
   return launch_modl<true, AR>(a, st);
 }
 
@@ -590,7 +612,7 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
                               long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
                               float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
                               void* workspace, size_t workspace_bytes, cudaStream_t st, int bf16 = 0,
-                              float* pix_stats = nullptr) {
+                              float* pix_stats = nullptr, const BinGeom& bins = BinGeom{}) {
   if (S <= 0 || B <= 0 || B_total < 0) return VAEMDL_EINVAL;
   if (pix_stats && (reinterpret_cast<uintptr_t>(pix_stats) & 7u)) return VAEMDL_EALIGN;
   if (elbo && !lme_b) return VAEMDL_EINVAL;
@@ -604,7 +626,7 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
   iw.elbo = elbo;
   iw.g_ll = g_ll;
   return modl_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
-                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16, pix_stats);
+                           ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16, pix_stats, bins);
 }
 }  // namespace vaemdl
 
@@ -643,7 +665,8 @@ template <int AR>
 static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
                                long long B, long long B_total, int x_batch, int H, int W, int M, const float* extra,
                                float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
-                               float* dparams, void* workspace, size_t workspace_bytes, cudaStream_t st, int* launches) {
+                               float* dparams, void* workspace, size_t workspace_bytes, cudaStream_t st, int* launches,
+                               const BinGeom& bins = BinGeom{}) {
   if (S <= 0 || B <= 0 || B_total < 0 || !lme_b || !g_ll || !dparams) return VAEMDL_EINVAL;
   const long long n_img = static_cast<long long>(S) * B;
   int rc = check_common(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M);
@@ -664,10 +687,10 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   if (!fused) {
     if (launches) *launches = 3;
     rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
-                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats);
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats, bins);
     if (rc) return rc;
     return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st, 0,
-                             stats);
+                             stats, bins);
   }
   ModlArgs a{};
   a.params = params;
@@ -685,6 +708,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   a.plain = AR;
   a.spread = spread_runs();
   a.pix_stats = reinterpret_cast<float2*>(stats);
+  if ((rc = set_bins(a, bins, AR))) return rc;
   StepFinish f{};
   f.extra = extra;
   f.ll = ll_image;
@@ -719,10 +743,10 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
     cudaGetLastError();
     if (launches) *launches = 3;
     rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
-                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats);
+                                ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats, bins);
     if (rc) return rc;
     return modl_bwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M, g_ll, nullptr, dparams, st, 0,
-                             stats);
+                             stats, bins);
   }
   return rc;
 }

@@ -28,6 +28,8 @@ __device__ __forceinline__ Pixel half_pixel(const PixelPair& pp, bool hi_half) {
     px.left[c] = hi_half ? pp.lh[c] : pp.ll[c];
     px.right[c] = hi_half ? pp.rh[c] : pp.rl[c];
   }
+  px.dx = pp.dx;
+  px.width = pp.width;
   return px;
 }
 
@@ -157,8 +159,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
     PixelPair px;
     {
       Pixel pa, pb;
-      decode_pixel(a, cur.rawA, pa);
-      decode_pixel(a, cur.rawB, pb);
+      decode_pixel<AR>(a, cur.rawA, pa);
+      decode_pixel<AR>(a, cur.rawB, pb);
+      px.dx = pa.dx;
+      px.width = pa.width;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         px.x[c] = pk(pa.x[c], pb.x[c]);
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
         kp[c] = pk(rowA[(3 + 3 * c) * M + m], rowB[(3 + 3 * c) * M + m]);
       }
       const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
-      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const bool narrow = __any_sync(kFull, smin < (AR ? a.ls_narrow : kLsNarrow));
       const f2 W = ex2_2((lg - lmax) * kLog2e);
       f2 u[9];
       f2 P;

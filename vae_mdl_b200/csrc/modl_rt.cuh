@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
     const long long n = n_cur, n_first = nfirst_cur;
     const float g = g_cur;
     Pixel px;
-    decode_pixel(a, raw_cur, px);
+    decode_pixel<AR>(a, raw_cur, px);
     if (!rev) {
       n_own += step_n;
       pix_own += step_pix;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(512, 1) modl_rt_kernel(const ModlArgs a) {
         kp[c] = ld_pair<AL>(q, 2 * M + ml, !vhi);
       }
       const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
-      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const bool narrow = __any_sync(kFull, smin < (AR ? a.ls_narrow : kLsNarrow));
       const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
       f2 u[9];
       f2 P;

@@ -55,15 +55,23 @@ __device__ __forceinline__ PixRaw load_pixel_raw(const ModlArgs& a, long long n,
                     : __float_as_uint(static_cast<const float*>(a.x)[xo + c]);
   return r;
 }
+template <int AR>
 __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r, Pixel& px) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float v = a.x_u8 ? u8_to_unit(r.v[c]) : __uint_as_float(r.v[c]);  // utils/data.py:15-16
     if (a.x_unit) v = __fmaf_rn(v, 2.0f, -1.0f);                                                  // utils/mdl.py:65
     px.x[c] = v;
-    px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
-    px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+    if constexpr (AR != 0) {  // utils/discretized_logistic.py:71-76 with the class's own low / high
+      px.left[c] = v <= a.low;
+      px.right[c] = v >= a.high;
+    } else {
+      px.left[c] = a.edge_openai ? (v < -0.999f) : (v <= -1.0f);
+      px.right[c] = a.edge_openai ? (v > 0.999f) : (v >= 1.0f);
+    }
   }
+  px.dx = bin_dx<AR>(a);
+  px.width = bin_width<AR>(a);
 }
 
 // FUSED: the forward and the backward pass of one step run inside ONE cooperative kernel (modl_step_kernel): both use
@@ -218,7 +226,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const float g = g_cur;
     const float2 st = st_cur;
     Pixel px;
-    decode_pixel(a, raw_cur, px);
+    decode_pixel<AR>(a, raw_cur, px);
     // advance the index and prefetch the next tile's pixel / upstream gradient
     if (!rev) {
       n_own += step_n;
@@ -292,7 +300,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         kp[c] = ld_pair<AL>(rowp, (3 + 3 * c) * M + m, single);
       }
       const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
-      const bool narrow = __any_sync(kFull, smin < kLsNarrow);
+      const bool narrow = __any_sync(kFull, smin < (AR ? a.ls_narrow : kLsNarrow));
       const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
       f2 u[9];
       f2 P;

@@ -28,6 +28,8 @@ struct SampleArgs {
   int variant_mdl;    // u_log carries a draw for every mixture: [.., 3, M]
   int variant_plain;  // utils/mdl_plain.py: means chained on the means, no sequential dependence between the channels
   int out_unit;
+  double clip_lo, clip_hi;  // plain variant: DiscretizedLogistic.sample clips to the class's [low, high]
+                            // (utils/discretized_logistic.py:83); its mean() to [-1, 1] (utils/mdl_plain.py:115)
 };
 
 // Per-warp shared-memory slot: [ parameter tile: 32 rows x 10M | u_mix tile: 32 x M | u_log tile: 32 x 3 (x M) ], each
@@ -172,9 +174,9 @@ __global__ void __launch_bounds__(512) modl_sample_kernel(const SampleArgs a) {
       const double l0 = xs[0];                                                                      // utils/mdl_plain.py:160
       const double l1 = xs[1] + coef[0] * l0;                                                       // :161
       const double l2 = xs[2] + coef[1] * l0 + coef[2] * l1;                                        // :162
-      xo[0] = fmin(fmax(l0 + noise_keep[0], -1.0), 1.0);                                            // discretized_logistic.py:80-85
-      xo[1] = fmin(fmax(l1 + noise_keep[1], -1.0), 1.0);
-      xo[2] = fmin(fmax(l2 + noise_keep[2], -1.0), 1.0);
+      xo[0] = fmin(fmax(l0 + noise_keep[0], a.clip_lo), a.clip_hi);                                 // discretized_logistic.py:80-85
+      xo[1] = fmin(fmax(l1 + noise_keep[1], a.clip_lo), a.clip_hi);
+      xo[2] = fmin(fmax(l2 + noise_keep[2], a.clip_lo), a.clip_hi);
     }
     if (active) {
 #pragma unroll
@@ -192,9 +194,9 @@ __global__ void __launch_bounds__(512) modl_sample_kernel(const SampleArgs a) {
 
 using namespace vaemdl;
 
-extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const float* u_log, int variant,
-                                  int out_range, long long n_rep, long long n_img, int H, int W, int M, float* x_out,
-                                  uint8_t* x_q, uint8_t* idx, void* stream) {
+static int modl_sample_impl(const float* params, const float* u_mix, const float* u_log, int variant, int out_range,
+                            long long n_rep, long long n_img, int H, int W, int M, float* x_out, uint8_t* x_q, uint8_t* idx,
+                            void* stream, double clip_lo, double clip_hi) {
   if (!params || !u_mix || n_rep <= 0 || n_img <= 0 || H <= 0 || W <= 0) return VAEMDL_EINVAL;
   if (!u_log && variant != VAEMDL_SAMPLE_PLAIN) return VAEMDL_EINVAL;
   if (!x_out && !x_q && !idx) return VAEMDL_EINVAL;
@@ -215,6 +217,8 @@ extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const
   a.variant_mdl = variant != VAEMDL_SAMPLE_OPENAI;
   a.variant_plain = variant == VAEMDL_SAMPLE_PLAIN;
   a.out_unit = out_range == VAEMDL_RANGE_UNIT;
+  a.clip_lo = clip_lo;
+  a.clip_hi = clip_hi;
   const DeviceInfo& di = device_info();
   const size_t ul_per = u_log ? (a.variant_mdl ? 3 * M : 3) : 0;
   const size_t per_warp = (static_cast<size_t>(32) * 10 * M + 32 * M + 32 * ul_per) * 4 + 8;
@@ -242,4 +246,21 @@ extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const
   if (grid > cap) grid = cap;
   modl_sample_kernel<<<static_cast<unsigned>(grid), warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return cuda_rc(cudaGetLastError());
+}
+
+extern "C" int vaemdl_modl_sample(const float* params, const float* u_mix, const float* u_log, int variant,
+                                  int out_range, long long n_rep, long long n_img, int H, int W, int M, float* x_out,
+                                  uint8_t* x_q, uint8_t* idx, void* stream) {
+  return modl_sample_impl(params, u_mix, u_log, variant, out_range, n_rep, n_img, H, W, M, x_out, x_q, idx, stream, -1.0, 1.0);
+}
+
+/* PixelMixtureDiscretizedLogistic.sample / .mean with the class's own low / high (utils/mdl_plain.py:68-121): the logistic
+ * draws are clipped to [low, high] (utils/discretized_logistic.py:83), the mean (u_log == NULL) to [-1, 1] (:115). */
+extern "C" int vaemdl_modl_plain_sample(const float* params, const float* u_mix, const float* u_log, float low, float high,
+                                        int out_range, long long n_rep, long long n_img, int H, int W, int M, float* x_out,
+                                        uint8_t* x_q, uint8_t* idx, void* stream) {
+  if (!(high > low)) return VAEMDL_EINVAL;
+  const bool mean = u_log == nullptr;
+  return modl_sample_impl(params, u_mix, u_log, VAEMDL_SAMPLE_PLAIN, out_range, n_rep, n_img, H, W, M, x_out, x_q, idx, stream,
+                          mean ? -1.0 : static_cast<double>(low), mean ? 1.0 : static_cast<double>(high));
 }

@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["init_from_env", "shard_bounds", "round_robin", "gather_round_robin", "allreduce_sum", "IwaeEvaluator",
-           "sharded_modl_iwae_step", "combine_lme_over_ranks", "sample_sharded_iwae_step"]
+           "sharded_modl_iwae_step", "combine_lme_over_ranks", "sample_sharded_iwae_step", "split_sample_tail"]
 
 
 def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
@@ -149,6 +149,12 @@ def sample_sharded_iwae_step(ll_fn: Callable, bwd_fn: Callable, params_shard, x,
     Returns ``(loss = -elbo, lpxz [S_local, B], dparams_shard)``; the loss is the GLOBAL loss on every rank (no further
     collective), the gradient is the rank's own slice of the global gradient."""
     lpxz = ll_fn(params_shard, x)
+    if lpxz.is_cuda and lpxz.dtype == torch.float64:
+        # device route: two small kernels around the one all_gather (vaemdl_iwae_split_local / _combine)
+        elbo, g_ll = split_sample_tail(lpxz, extra_shard, s_total, group)
+        dparams = bwd_fn(params_shard, x, g_ll)
+        return -elbo, lpxz, dparams
+    # host-logic route (CPU tensors over gloo in the tests): the same arithmetic with torch ops
     log_w = lpxz.double() + (extra_shard.double() if extra_shard is not None else 0.0)  # models/loss.py:34
     lme, weights = combine_lme_over_ranks(log_w, s_total, group)
     B = log_w.shape[1]
@@ -156,3 +162,32 @@ def sample_sharded_iwae_step(ll_fn: Callable, bwd_fn: Callable, params_shard, x,
     g_ll = (-weights / B).float()                                                 # d(-elbo) / d lpxz
     dparams = bwd_fn(params_shard, x, g_ll.contiguous())
     return (-elbo).reshape(1).float(), lpxz, dparams
+
+
+def split_sample_tail(lpxz64: torch.Tensor, extra_shard: Optional[torch.Tensor], s_total: int, group=None,
+                      pairs_out: Optional[torch.Tensor] = None):
+    """The IWAE tail for importance samples split across ranks, on the device: ``lpxz64 [S_local, B]`` float64 CUDA.
+    ``vaemdl_iwae_split_local`` -> ONE ``all_gather`` of the ``[2, B]`` float64 (max, sum-exp) pairs ->
+    ``vaemdl_iwae_split_combine``.  Returns ``(elbo [1], g_ll [S_local, B])`` float32; ``elbo`` is the global value on
+    every rank, ``g_ll = d(-elbo)/d lpxz`` for the local samples."""
+    from . import _abi
+    from ._abi import check, lib, ptr, stream_ptr
+    S_local, B = lpxz64.shape
+    dev = lpxz64.device
+    ex = _abi.dense_f32(extra_shard, "extra") if extra_shard is not None else None
+    ll = lpxz64.contiguous()
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    pair = torch.empty((2, B), dtype=torch.float64, device=dev)
+    with _abi.on_device(dev):
+        check(lib().vaemdl_iwae_split_local(ptr(ll), ptr(ex), S_local, B, ptr(pair), stream_ptr(dev)), "vaemdl_iwae_split_local")
+    if world > 1:
+        pairs = pairs_out if pairs_out is not None else torch.empty((world, 2, B), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(pairs.reshape(-1), pair.reshape(-1), group=group)
+    else:
+        pairs = pair
+    elbo = torch.empty(1, dtype=torch.float32, device=dev)
+    g_ll = torch.empty((S_local, B), dtype=torch.float32, device=dev)
+    with _abi.on_device(dev):
+        check(lib().vaemdl_iwae_split_combine(ptr(ll), ptr(ex), S_local, B, ptr(pairs), world, int(s_total), 0, None, None,
+                                              ptr(elbo), ptr(g_ll), stream_ptr(dev)), "vaemdl_iwae_split_combine")
+    return elbo, g_ll

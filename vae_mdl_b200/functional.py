@@ -55,6 +55,15 @@ def _check_batch(n_img: int, x_batch: int, what: str):
                          "(the leading dims of the parameters must end with the batch dim of x)")
 
 
+def _bins(plain):
+    """``plain``: False (x-conditioned classes), True (utils/mdl_plain.py with its default low=-1, high=1, levels=256) or
+    the ``(low, high, levels)`` the un-conditioned class was built with (utils/mdl_plain.py:18)."""
+    if isinstance(plain, (tuple, list)):
+        low, high, levels = (float(v) for v in plain)
+        return low, high, levels
+    return -1.0, 1.0, 256.0
+
+
 class _ModlFn(torch.autograd.Function):
     """Forward: per-pixel log-prob or per-image log-likelihood (float32 or float64 sums).  Backward: one fused kernel."""
 
@@ -89,8 +98,8 @@ class _ModlFn(torch.autograd.Function):
             if plain:
                 if x_range != _abi.RANGE_UNIT or edge_mode != _abi.EDGE_MDL:
                     raise ValueError("the plain pixel mixture takes x in [0,1] and the <= -1 / >= 1 edge tests")
-                check(L.vaemdl_modl_plain_fwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(lp), ptr(ll), ptr(ll64),
-                                              ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_plain_fwd")
+                check(L.vaemdl_modl_plain_fwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, *_bins(plain), ptr(lp), ptr(ll),
+                                              ptr(ll64), ptr(ws), ws_bytes, stream_ptr(p.device)), "vaemdl_modl_plain_fwd")
             else:
                 fn = L.vaemdl_modl_fwd_bf16 if bf16 else L.vaemdl_modl_fwd
                 check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
@@ -110,8 +119,9 @@ class _ModlFn(torch.autograd.Function):
         dp = torch.empty_like(p)
         with _abi.on_device(p.device):
             if plain:
-                check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, ptr(g_image),
-                                                  ptr(g_pixel), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
+                check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, M, *_bins(plain),
+                                                  ptr(g_image), ptr(g_pixel), ptr(dp), stream_ptr(p.device)),
+                      "vaemdl_modl_plain_bwd")
             else:
                 fn = lib().vaemdl_modl_bwd_bf16 if bf16 else lib().vaemdl_modl_bwd  # dp has the dtype of p
                 check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
@@ -138,8 +148,8 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
     dp = torch.empty_like(p)
     with _abi.on_device(p.device):
         if plain:
-            check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, ptr(gi), ptr(gp),
-                                              ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
+            check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, *_bins(plain), ptr(gi),
+                                              ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
         elif pix_stats is not None and not bf16:
             # the per-pixel mixture sums of the forward call on the same parameters: one-pass gradient kernel
             check(lib().vaemdl_modl_bwd_stats(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
@@ -182,7 +192,8 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
     ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
     with _abi.on_device(dev):
         if plain:
-            check(L.vaemdl_modl_plain_iwae_fwd(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex), None,
+            check(L.vaemdl_modl_plain_iwae_fwd(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, *_bins(plain),
+                                               ptr(ex), None,
                                                ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
                                                stream_ptr(dev)), "vaemdl_modl_plain_iwae_fwd")
         else:
@@ -235,7 +246,8 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     n_launch = ctypes.c_int(0)
     with _abi.on_device(dev):
         if plain:
-            check(L.vaemdl_modl_plain_iwae_step(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M, ptr(ex),
+            check(L.vaemdl_modl_plain_iwae_step(ptr(p), ptr(xd), x_dtype, S, B, int(b_total), x_batch, H, W, M,
+                                                *_bins(plain), ptr(ex),
                                                 None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(dp),
                                                 ptr(ws), ws_bytes, stream_ptr(dev), ctypes.byref(n_launch)),
                   "vaemdl_modl_plain_iwae_step")
@@ -542,7 +554,8 @@ def iwae_tail(ll: torch.Tensor, extra: Optional[torch.Tensor] = None, b_total: i
 # samplers
 # --------------------------------------------------------------------------------------------------
 def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, variant: int = _abi.SAMPLE_OPENAI,
-                out_range: int = _abi.RANGE_SYM, want_quantised: bool = False, want_index: bool = False):
+                out_range: int = _abi.RANGE_SYM, want_quantised: bool = False, want_index: bool = False,
+                clip=(-1.0, 1.0)):
     """Explicit-noise MoDL sampler.  ``params [..., H, W, 10M]``; the noise may carry extra leading dims ``[n..., ...]``
     (``u_mix [n..., ..., H, W, M]``): the parameters are then re-used for every ``n`` without being tiled.
     Returns ``x [n..., ..., H, W, 3]`` float32 (+ uint8 quantised values, + uint8 mixture indices)."""
@@ -569,8 +582,14 @@ def modl_sample(params: torch.Tensor, u_mix: torch.Tensor, u_log: torch.Tensor, 
     xq = torch.empty(out_lead + (H, W, 3), device=p.device, dtype=torch.uint8) if want_quantised else None
     idx = torch.empty(out_lead + (H, W), device=p.device, dtype=torch.uint8) if want_index else None
     with _abi.on_device(p.device):
-        check(lib().vaemdl_modl_sample(ptr(p), ptr(um), ptr(ul), variant, out_range, n_rep, n_img, H, W, M, ptr(x),
-                                       ptr(xq), ptr(idx), stream_ptr(p.device)), "vaemdl_modl_sample")
+        if variant == _abi.SAMPLE_PLAIN and tuple(float(v) for v in clip) != (-1.0, 1.0):
+            # the un-conditioned class built with its own low / high (utils/mdl_plain.py:18, discretized_logistic.py:83)
+            check(lib().vaemdl_modl_plain_sample(ptr(p), ptr(um), ptr(ul), float(clip[0]), float(clip[1]), out_range, n_rep,
+                                                 n_img, H, W, M, ptr(x), ptr(xq), ptr(idx), stream_ptr(p.device)),
+                  "vaemdl_modl_plain_sample")
+        else:
+            check(lib().vaemdl_modl_sample(ptr(p), ptr(um), ptr(ul), variant, out_range, n_rep, n_img, H, W, M, ptr(x),
+                                           ptr(xq), ptr(idx), stream_ptr(p.device)), "vaemdl_modl_sample")
     outs = [x]
     if want_quantised:
         outs.append(xq)
@@ -682,6 +701,15 @@ def _expand_param(t: torch.Tensor, S: int, B: int, D: int):
     return t.expand(S, B, D).contiguous()
 
 
+def _reduce_to(g: torch.Tensor, shape) -> torch.Tensor:
+    """Sums the gradient of an expanded Normal parameter back to the parameter's own shape (which may carry leading
+    singleton dims the expansion dropped, e.g. ``[1,B,D]`` -> ``[B,D]``)."""
+    shape = tuple(shape)
+    if g.dim() < len(shape):
+        g = g.reshape((1,) * (len(shape) - g.dim()) + tuple(g.shape))
+    return g.sum_to_size(shape) if len(shape) else g.sum()
+
+
 class _FusedIwaeFn(torch.autograd.Function):
     """The IWAE objective after the networks (models/loss.py:26-46, models/model06.py:38-55): latent terms ->
     observation-model forward -> fused finish; backward: observation-model gradient kernel + latent-term gradient kernel.
@@ -757,8 +785,8 @@ class _FusedIwaeFn(torch.autograd.Function):
                 d_tensors[zi] = dzs[t]
             for t, (zi, w, pi) in enumerate(ctx.term_meta):
                 if pi >= 0:
-                    d_tensors[ctx.n_z + 2 * pi] = dlocs[t].sum_to_size(ctx.raw_shapes[2 * pi])
-                    d_tensors[ctx.n_z + 2 * pi + 1] = dscs[t].sum_to_size(ctx.raw_shapes[2 * pi + 1])
+                    d_tensors[ctx.n_z + 2 * pi] = _reduce_to(dlocs[t], ctx.raw_shapes[2 * pi])
+                    d_tensors[ctx.n_z + 2 * pi + 1] = _reduce_to(dscs[t], ctx.raw_shapes[2 * pi + 1])
         if not ctx.has_p1:
             dp1 = None
         return (None, None, None, None, None, dp0, dp1, *d_tensors)

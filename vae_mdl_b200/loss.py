@@ -43,27 +43,52 @@ def _lpxz(pxz, x):
     return torch.sum(pxz.log_prob(x), dim=tuple(axes))
 
 
+def _is_std_const(dist):
+    """``Normal(0.0, 1.0)`` built from Python numbers (the reference's prior, models/model05.py:108): 0-dim CPU tensors."""
+    loc, scale = dist.loc, dist.scale
+    return (not loc.is_cuda and not scale.is_cuda and loc.numel() == 1 and scale.numel() == 1
+            and not loc.requires_grad and not scale.requires_grad and float(loc) == 0.0 and float(scale) == 1.0)
+
+
 def _normal_ok(dist, axes, z):
-    """A Normal density reduced over the last axis of a ``[S,B,D]`` sample, parameters not wider than the sample."""
-    if not isinstance(dist, td.Normal) or list(axes) != [-1] or z is None or z.dim() != 3:
+    """A plain Normal density (not a subclass / transformed / Independent wrapper) reduced over the last axis of a CUDA
+    ``[S,B,D]`` float sample; parameters not wider than the sample and either on z's device or the constant (0, 1)."""
+    if type(dist) is not td.Normal or list(axes) != [-1] or z is None or z.dim() != 3:
         return False
+    if not z.is_cuda or not z.is_floating_point():
+        return False
+    if _is_std_const(dist):
+        return True
     for t in (dist.loc, dist.scale):
+        if not t.is_floating_point() or t.device != z.device:
+            return False
         if t.dim() > 3 or (t.dim() == 3 and t.shape[0] not in (1, z.shape[0])):
             return False
     return True
+
+
+def _term(z, dist, weight):
+    """One Normal density of ``log_w`` for ``F.fused_iwae_loss``; the constant (0, 1) prior is the parameter-free term."""
+    if _is_std_const(dist):
+        return (z, None, None, weight)
+    return (z, dist.loc, dist.scale, weight)
 
 
 def _obs_ok(pxz, axes, x, S, B):
     """One of this package's observation models scored over the image axes, parameters ``[S,B,H,W,...]``, x ``[B,H,W,3]``."""
     if not hasattr(pxz, "_iwae_spec") or sorted(axes) != [-3, -2, -1]:
         return False
-    p0 = pxz._iwae_spec()[2]
-    return p0.dim() == 5 and x.dim() == 4 and p0.shape[0] == S and p0.shape[1] == B and x.shape[0] == B
+    _, _, p0, p1 = pxz._iwae_spec()
+    if not (p0.dim() == 5 and x.dim() == 4 and p0.shape[0] == S and p0.shape[1] == B and x.shape[0] == B):
+        return False
+    return p0.is_cuda and x.is_cuda and x.device == p0.device and (p1 is None or p1.device == p0.device)
 
 
 def _fusable(x, z, pz, qzx, pxz):
-    return (_normal_ok(pz, _axes(pz), z) and _normal_ok(qzx, _axes(qzx), z)
-            and _obs_ok(pxz, pxz.axes, x, z.shape[0], z.shape[1]))
+    if not (_normal_ok(pz, _axes(pz), z) and _normal_ok(qzx, _axes(qzx), z)
+            and _obs_ok(pxz, pxz.axes, x, z.shape[0], z.shape[1])):
+        return False
+    return z.device == x.device
 
 
 def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
@@ -74,8 +99,8 @@ def iwae_loss(x, z, pz, qzx, pxz, beta=1.0):
     launches backward; anything else takes the generic op-by-op route below."""
     if _fusable(x, z, pz, qzx, pxz):
         kind, meta, p0, p1 = pxz._iwae_spec()
-        loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, [(z, pz.loc, pz.scale, beta),      # :34
-                                                                        (z, qzx.loc, qzx.scale, -beta)])
+        loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, [_term(z, pz, beta),               # :34
+                                                                        _term(z, qzx, -beta)])
         neg_elbo = loss.detach()
         lpz, lqzx = sums[0], sums[1]
         n_dims = float(math.prod(x.shape[1:]))                              # :42
@@ -108,10 +133,10 @@ def loss_fn(x, pz, qz1x, qz2z1, pz1z2, pxz1):
     z1, z2 = qz1x.z, qz2z1.z
     if (z1 is not None and z2 is not None and _normal_ok(qz2z1.dist, qz2z1.axes, z2) and _normal_ok(qz1x.dist, qz1x.axes, z1)
             and _normal_ok(pz, _axes(pz), z2) and _normal_ok(pz1z2.dist, qz1x.axes, z1)
-            and _obs_ok(pxz1.dist, pxz1.axes, x, z1.shape[0], z1.shape[1])):
+            and _obs_ok(pxz1.dist, pxz1.axes, x, z1.shape[0], z1.shape[1]) and z1.device == x.device == z2.device):
         kind, meta, p0, p1 = pxz1.dist._iwae_spec()
-        terms = [(z2, pz.loc, pz.scale, 1.0), (z2, qz2z1.dist.loc, qz2z1.dist.scale, -1.0),                # :47
-                 (z1, pz1z2.dist.loc, pz1z2.dist.scale, 1.0), (z1, qz1x.dist.loc, qz1x.dist.scale, -1.0)]
+        terms = [_term(z2, pz, 1.0), _term(z2, qz2z1.dist, -1.0),                                          # :47
+                 _term(z1, pz1z2.dist, 1.0), _term(z1, qz1x.dist, -1.0)]
         loss, lpxz, sums, _ = F.fused_iwae_loss(kind, meta, x, p0, p1, terms)
         iwae_elbo = -loss.detach()
         lpz2, lqz2z1, lpz1z2, lqz1x = sums[0], sums[1], sums[2], sums[3]

@@ -36,9 +36,10 @@ class PixelMixtureDiscretizedLogistic:
     def __init__(self, parameters: torch.Tensor, low=-1.0, high=1.0, levels=256.0):
         """``parameters [..., batch, h, w, n_mix * 10]`` (utils/mdl_plain.py:18-34)."""
         _abi.require_cuda(parameters, "parameters")
-        if (float(low), float(high), float(levels)) != (-1.0, 1.0, 256.0):
-            raise ValueError("the kernels implement the class defaults low=-1, high=1, levels=256 (8-bit pixels)")
+        if not float(levels) > 1.0 or not float(high) > float(low):
+            raise ValueError("need high > low and levels > 1")
         self._parameters = parameters
+        self._bins = (float(low), float(high), float(levels))
         self.n_mix = parameters.shape[-1] // 10                                           # :34
         if self.n_mix * 10 != parameters.shape[-1] or self.n_mix < 1:
             raise ValueError(f"last dim must be n_mix * 10, got {parameters.shape[-1]}")
@@ -62,11 +63,11 @@ class PixelMixtureDiscretizedLogistic:
 
     def log_prob(self, x: torch.Tensor) -> torch.Tensor:
         """x in [0,1] ``[batch, h, w, 3]``; returns ``[..., h, w]`` (utils/mdl_plain.py:36-66, no trailing 1)."""
-        return F.modl_log_prob(self._parameters, x, plain=True)
+        return F.modl_log_prob(self._parameters, x, plain=self._bins)
 
     def log_likelihood(self, x: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         """Sum of ``log_prob`` over the image, fused into the kernel (per-pixel tensor never written)."""
-        return F.modl_log_likelihood(self._parameters, x, dtype=dtype, plain=True)
+        return F.modl_log_likelihood(self._parameters, x, dtype=dtype, plain=self._bins)
 
     def sample(self, n_samples=[], u_mix=None, u_log=None, generator=None, return_index=False, return_quantised=False):
         """utils/mdl_plain.py:68-102: ``n_samples=[]`` -> ``[..., h, w, 3]``, ``n`` / ``[n]`` -> leading ``[n]``; values in
@@ -86,7 +87,8 @@ class PixelMixtureDiscretizedLogistic:
         if u_log is None:
             u_log = uniform_noise((n,) + lead + (3, self.n_mix), p.device, generator)
         out = F.modl_sample(p, u_mix.reshape((n,) + lead + (self.n_mix,)), u_log.reshape((n,) + lead + (3, self.n_mix)),
-                            _abi.SAMPLE_PLAIN, _abi.RANGE_UNIT, want_quantised=return_quantised, want_index=return_index)
+                            _abi.SAMPLE_PLAIN, _abi.RANGE_UNIT, want_quantised=return_quantised, want_index=return_index,
+                            clip=self._bins[:2])
         outs = out if isinstance(out, tuple) else (out,)
         if not ns:
             outs = tuple(o[0] for o in outs)
