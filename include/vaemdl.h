@@ -191,7 +191,9 @@ VAEMDL_API int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int 
  * means: loc_g = mu_g + tanh(kR)*loc_r, loc_b = mu_b + tanh(kG)*loc_r + tanh(kB)*loc_g (utils/mdl_plain.py:160-162)
  * instead of the observed x_r, x_g.  x in [0,1] (the class rescales to [-1,1], :45); low / high / levels are the class's
  * constructor arguments (utils/mdl_plain.py:18; defaults -1, 1, 256): edge tests x <= low / x >= high, bin width
- * (high - low) / (levels - 1) (utils/discretized_logistic.py:18-21, :71-76).
+ * (high - low) / (levels - 1) (utils/discretized_logistic.py:18-21, :71-76).  Supported: bin width <= 0.049 (levels >= 42
+ * on [-1,1]; the defaults give 0.0078) -- coarser grids return VAEMDL_EUNSUPPORTED: with log-scales clamped at -7 the
+ * linear-domain product of the three sub-pixel terms would leave the float32 range.
  * ------------------------------------------------------------------------ */
 VAEMDL_API int vaemdl_modl_plain_fwd(const float* params, const void* x, int x_dtype,
                     long long n_img, int x_batch, int H, int W, int M, float low, float high, float levels,

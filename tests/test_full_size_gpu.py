@@ -112,8 +112,14 @@ def test_config2_plain_dl_full_size(F, V):
     assert abs(loss.item() - want.item()) <= 1e-6 * abs(want.item())
     loss2, _, dloc2, dls2 = V.dlogistic_iwae_step(mu, lstd, x_u8, None, 0.0, 1.0, 256.0)
     assert torch.equal(dloc, dloc2) and torch.equal(dls, dls2)
-    # oracle spot checks on whole images: log-likelihood AND gradient (upstream = the softmax weights of the step)
-    g_ll = -torch.softmax(ll64, 0) / B
+    # oracle spot checks on whole images: log-likelihood AND gradient.  With random parameters one importance sample
+    # carries all the weight (the others' gradients underflow), so the gradient is checked on a second step whose `extra`
+    # makes the weights of a batch element comparable -- upstream = that step's softmax weights.
+    extra = (ll64.mean(0, keepdim=True) - ll64).float() + torch.randn(S, B, device=DEV, generator=gen)
+    _, lpxz_b, dloc, dls = V.dlogistic_iwae_step(mu, lstd, x_u8, extra, 0.0, 1.0, 256.0)
+    assert torch.equal(lpxz_b, ll64)
+    g_ll = -torch.softmax(ll64 + extra.double(), 0) / B
+    assert g_ll.abs().min().item() > 1e-8
     both_grad = torch.cat([dloc, dls], dim=-1)
     for s_i, b_i in [(0, 0), (4, 127), (2, 63)]:
         b64 = both[s_i, b_i].cpu().double()[None].requires_grad_(True)
@@ -254,11 +260,15 @@ def test_config5_other_sweep_points_full_size(F, V, name, H, W, M):
     gen = torch.Generator(device=DEV).manual_seed(700 + M + H)
     params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
     x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
-    extra = torch.randn(S, B, device=DEV, generator=gen)
     if name == "cfg5_128_m30":
         assert (S * B - 1) * H * W * 10 * M > 2 ** 31
+    # `extra` balances the importance weights of every image (random parameters would give one sample all the weight and
+    # leave the other samples' gradients in the float32 denormals): every spot-checked image carries a real gradient
+    ll_first = F.modl_log_likelihood(params, x_u8, dtype=torch.float64)
+    extra = (ll_first.mean(0, keepdim=True) - ll_first).float() + torch.randn(S, B, device=DEV, generator=gen)
     ll64, log_w, lme_b, elbo, g_ll, dp, launches = F.modl_iwae_step(params, x_u8, extra)
-    assert launches == 3
+    assert launches == 3 and torch.equal(ll64, ll_first)
+    assert g_ll.abs().min().item() > 1e-8
     lw = ll64 + extra.double()
     want_lme = torch.logsumexp(lw, 0) - math.log(S)
     assert ((lme_b.double() - want_lme).abs() / want_lme.abs()).max().item() < 1e-6

@@ -15,6 +15,19 @@ def V(built_lib):
     return vae_mdl_b200
 
 
+def threshold_ambiguous_plain(params64, x64, low, high, levels, rel=1e-3):
+    """Pixels holding a sub-pixel whose CDF difference sits within `rel` of the 1e-5 branch threshold (the reference's own
+    branch choice there depends on float32 rounding, cf. util.threshold_ambiguous).  -> bool [S,B,H,W]."""
+    loc, logscale, _ = O.mdl_plain_get_mixture_params(params64)
+    x = (x64 * 2 - 1)[..., None]
+    dx = (high - low) / (levels - 1.0) / 2.0
+    inv = torch.exp(-logscale)
+    prob = torch.sigmoid((x - loc + dx) * inv) - torch.sigmoid((x - loc - dx) * inv)
+    edge = ((x <= low) | (x >= high)).expand_as(prob)
+    amb = ((prob - 1e-5).abs() < rel * 1e-5) & ~edge
+    return amb.flatten(-2).any(-1)
+
+
 def _oracle(params, x_u8, g_image):
     p64 = params.double().requires_grad_(True)
     x64 = O.normalize_u8(x_u8, torch.float64)
@@ -88,7 +101,48 @@ def test_sample_mean_and_attributes(V):
     loc64, ls64, _ = O.mdl_plain_get_mixture_params(p.double())
     assert relnorm(d.loc, loc64) < 1e-6 and relnorm(d.logscale, ls64) < 1e-6
     with pytest.raises(ValueError):
-        V.PixelMixtureDiscretizedLogistic(p.to(DEV), low=0.0)
+        V.PixelMixtureDiscretizedLogistic(p.to(DEV), low=1.0, high=1.0)
+    with pytest.raises(ValueError):                      # 2-level grid: bin width 2 > 0.049 (include/vaemdl.h)
+        V.PixelMixtureDiscretizedLogistic(p.to(DEV), levels=2.0)
+    # the class built with its own (low, high, levels) (utils/mdl_plain.py:18): sampler clipped to [low, high], mean to [-1, 1]
+    lo_, hi_ = -0.4, 0.7
+    d2 = V.PixelMixtureDiscretizedLogistic(p.to(DEV), low=lo_, high=hi_, levels=64.0)
+    x2, xq2, idx2 = d2.sample(n, u_mix=um.to(DEV), u_log=ul.to(DEV), return_index=True, return_quantised=True)
+    want2, widx2 = O.mdl_plain_sample(p.expand(n, B, H, W, 10 * M), um, ul, lo_, hi_)
+    assert int((idx2.cpu().long() != widx2).sum()) == 0 and int((xq2.cpu() != O.quantise(want2)).sum()) == 0
+    assert (x2.cpu().double() - want2).abs().max().item() < 1e-6
+    assert x2.min().item() >= (lo_ + 1) / 2 - 1e-6 and x2.max().item() <= (hi_ + 1) / 2 + 1e-6
+    assert (d2.mean(u_mix=um[:1].to(DEV)).cpu().double() - wm).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("low,high,levels,M", [(-0.95, 0.9, 64.0, 5), (-1.0, 1.0, 128.0, 10), (-0.5, 0.5, 256.0, 7),
+                                               (-1.0, 1.0, 42.0, 3), (-2.0, 3.0, 1024.0, 20)])
+def test_plain_mixture_with_its_own_bins(V, low, high, levels, M):
+    """PixelMixtureDiscretizedLogistic(parameters, low, high, levels) (utils/mdl_plain.py:18): edge tests x <= low /
+    x >= high, bin width (high - low) / (levels - 1) (utils/discretized_logistic.py:18-21, :71-76): per-pixel values,
+    per-image sums and the gradient against the float64 oracle, canonical and trained-like (narrow-scale) parameters."""
+    from vae_mdl_b200 import functional as F
+    S, B, H, W = 3, 4, 16, 16
+    for seed, maker in ((1, canonical), (2, trained_like)):
+        params, x_u8, g = maker(40 + seed + M, S, B, H, W, M)
+        p64 = params.double().requires_grad_(True)
+        x64 = O.normalize_u8(x_u8, torch.float64)
+        lp64 = O.mdl_plain_log_prob(p64, x64, low, high, levels)
+        ll64 = lp64.sum((-1, -2))
+        gi = torch.randn(S, B, generator=g)
+        (ll64 * gi.double()).sum().backward()
+        d = V.PixelMixtureDiscretizedLogistic(params.to(DEV).requires_grad_(True), low=low, high=high, levels=levels)
+        lp = d.log_prob(x_u8.to(DEV))
+        keep = ~threshold_ambiguous_plain(p64.detach(), x64, low, high, levels)
+        assert ((lp.detach().cpu().double() - lp64.detach()).abs()[keep]).max().item() < 2e-4
+        ll = d.log_likelihood(x_u8.to(DEV), dtype=torch.float64)
+        ok_img = keep.reshape(S, B, -1).all(-1)
+        assert ((ll.cpu() - ll64.detach()).abs() / ll64.detach().abs())[ok_img].max().item() <= LL_RTOL
+        dp = F.modl_backward(params.to(DEV), x_u8.to(DEV), g_image=gi.to(DEV), plain=(low, high, levels))
+        if bool(ok_img.all()):
+            assert_grad_close(dp, p64.grad, M)
+        else:
+            assert relnorm(dp.cpu()[ok_img], p64.grad[ok_img]) <= GRAD_RTOL
 
 
 def test_golden_plain_mixture_and_latent_terms(V):

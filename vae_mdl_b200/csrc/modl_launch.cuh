@@ -482,6 +482,7 @@ static int tile_ppt(int M, long long n_px, bool bf16 = false) {
 }
 
 // bin geometry of the class (utils/discretized_logistic.py:10-21); the x-conditioned classes are fixed to the default
+constexpr double kMaxH = 27.0;  // largest half bin width in units of the narrowest scale the linear-domain product carries
 struct BinGeom {
   float low = -1.0f, high = 1.0f, levels = 256.0f;
   bool is_default() const { return low == -1.0f && high == 1.0f && levels == 256.0f; }
@@ -489,6 +490,11 @@ struct BinGeom {
 static int set_bins(ModlArgs& a, const BinGeom& g, int AR) {
   if (!(g.levels > 1.0f) || !(g.high > g.low)) return VAEMDL_EINVAL;
   if (AR == 0 && !g.is_default()) return VAEMDL_EUNSUPPORTED;
+  // The kernels multiply the three sub-pixel terms in the linear domain, each a ratio whose denominator is >= exp(-h),
+  // h = exp(-logscale) * dx <= e^7 * dx (log-scales are clamped at -7, utils/mdl_plain.py:150): the product of three stays
+  // inside the float32 range while h <= kMaxH, i.e. bin width <= 2 * kMaxH / e^7 = 0.049 (levels >= 42 on [-1, 1]).
+  if (!g.is_default() && (static_cast<double>(g.high) - g.low) / (static_cast<double>(g.levels) - 1.0) / 2.0 * exp(7.0) > kMaxH)
+    return VAEMDL_EUNSUPPORTED;
   a.low = g.low;
   a.high = g.high;
   const double width = (static_cast<double>(g.high) - static_cast<double>(g.low)) / (static_cast<double>(g.levels) - 1.0);

@@ -6,6 +6,8 @@ the other chain), same parameter row ``[logit(M) | (mu, s, kappa) x RGB]``.
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _abi
@@ -38,6 +40,10 @@ class PixelMixtureDiscretizedLogistic:
         _abi.require_cuda(parameters, "parameters")
         if not float(levels) > 1.0 or not float(high) > float(low):
             raise ValueError("need high > low and levels > 1")
+        if (float(low), float(high), float(levels)) != (-1.0, 1.0, 256.0) and \
+                (float(high) - float(low)) / (float(levels) - 1.0) > 2.0 * 27.0 / math.exp(7.0):
+            raise ValueError("bin width (high - low) / (levels - 1) must not exceed 0.049 (e.g. levels >= 42 on [-1, 1]): "
+                             "coarser grids are outside the float32 range of the kernels' linear-domain evaluation")
         self._parameters = parameters
         self._bins = (float(low), float(high), float(levels))
         self.n_mix = parameters.shape[-1] // 10                                           # :34
