@@ -53,6 +53,7 @@ struct ModlArgs {
   int M;
   int bf16;    // parameters (and the gradient) are bfloat16 in global memory; all arithmetic stays float32
   int spread;  // 1: run r belongs to warp (r / #CTAs) of CTA (r % #CTAs), 0: to warp (r % warps) of CTA (r / warps)
+  int pair_rot;  // tiled kernels: walk the component pairs in a per-lane rotated order (shared-memory bank conflicts)
   // run-time tile geometry (modl_rt_kernel: any n_mix without its own instantiation)
   int rt_MC, rt_LPP, rt_PPT, rt_rot, rt_warp_f;
   // bin geometry of the un-conditioned pixel mixture (utils/mdl_plain.py:18, utils/discretized_logistic.py:10-21): the

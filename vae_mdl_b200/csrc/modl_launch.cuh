@@ -403,6 +403,20 @@ static bool use_pixel_pairs(int M, long long n_px, bool bf16 = false) {
   return n_px >= 64ll * 148 * 16 * 6;
 }
 
+// Rotated component-pair order against shared-memory bank conflicts (Tile::pair_rot).  Measured on B200 (tools/ab_rot.sh,
+// tools/ncu_smem.sh, profiles/r02e_*): it removes 65 % of the conflict wavefronts (31.0 M -> 20.2 M per backward launch at
+// n_mix 10) but the shared-memory pipe was not what limits these kernels: n_mix 30 gains 1.3 %, n_mix 20 is level, and the
+// n_mix 10 backward kernel LOSES 7 % back to back (280 -> 299 us; level under ncu's serialised replay) -- so it is on for
+// three lanes per pixel only.  VAEMDL_ROT = 0 / 1 forces it off / on for every tiled kernel (A/B).
+static int pair_rot_on(int M) {
+  static const int forced = [] {
+    const char* e = getenv("VAEMDL_ROT");
+    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  if (forced >= 0) return forced;
+  return M == 30;
+}
+
 static int spread_runs() {
   const char* e = getenv("VAEMDL_SPREAD");  // "0": CTA-major run numbering (A/B)
   return !(e && e[0] == '0');
@@ -428,6 +442,7 @@ template <bool BWD, int AR>
 static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   a.plain = AR;
   a.spread = spread_runs();
+  a.pair_rot = pair_rot_on(a.M);
   if (!stats_supported(a.M, a.n_px, a.bf16 != 0)) a.pix_stats = nullptr;
   if (use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
     switch (a.M) {
@@ -713,6 +728,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   a.M = M;
   a.plain = AR;
   a.spread = spread_runs();
+  a.pair_rot = pair_rot_on(M);
   a.pix_stats = reinterpret_cast<float2*>(stats);
   if ((rc = set_bins(a, bins, AR))) return rc;
   StepFinish f{};

@@ -18,6 +18,19 @@ struct Tile {
   static constexpr int NPAIR = (MC + 1) / 2;
   static constexpr bool ALIGNED = (M % 2 == 0) && (MC % 2 == 0);  // component pairs sit on 8-byte boundaries
   static_assert(TILE_B % 16 == 0, "bulk copies need 16-byte multiples");
+  // Shared-memory bank conflicts: a row is 10 M words, so the rows of lanes l and l + 8 (M = 10: 100 = 4 mod 32 words
+  // apart) start in the same bank and every 64-bit access of a half-warp takes two wavefronts instead of one.  A lane can
+  // walk its component pairs in a rotated order, the rotation chosen per lane group so that the pairs touched in one
+  // iteration spread over the banks (wavefronts per pair iteration 20 -> 12 / 14 / 20 at M = 10 / 20 / 30; with five pairs
+  // one iteration in five keeps a two-way conflict).  Whether that pays is decided per n_mix by pair_rot_on()
+  // (modl_launch.cuh): the shared-memory pipe is not what limits these kernels.
+  __device__ static __forceinline__ int pair_rot(int lane) {
+    if constexpr (!ALIGNED) return 0;
+    if constexpr (LPP == 1) return (lane >> 3) & 1;
+    if constexpr (LPP == 2) return ((lane >> 3) & 1) * 2;
+    if constexpr (LPP == 3) return (3 * (lane / 3)) % NPAIR;
+    return 0;
+  }
 };
 
 // a pair of consecutive floats at row[off], row[off+1]; `single`: only row[off] exists (odd MC), both halves get it
@@ -104,12 +117,19 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     }
     __syncwarp();
   }
+  // A backward kernel launched programmatically behind the finish kernel may not read g_image (nor the forward pass's
+  // per-pixel sums) before griddepcontrol.wait.  The two-pass kernel needs the upstream gradient only in the SECOND pass
+  // over a row, so it loads its first tile and forms that tile's unscaled derivatives while the finish kernel is still
+  // running (LATE_G): the finish kernel (6-8 us per step) leaves the critical path.  The parameters themselves are inputs
+  // of the whole step, not products of the preceding kernels.
+  constexpr bool LATE_G = BWD && !FUSED && !ST;
   if constexpr (!FUSED) {
     if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
-    if constexpr (BWD)
-      pdl_wait();     // launched programmatically behind the finish kernel: g_image (and, in general, the parameters) must be complete
-    else
+    if constexpr (BWD) {
+      if constexpr (!LATE_G) pdl_wait();
+    } else {
       pdl_trigger();  // let the finish kernel's launch overlap this kernel's tail
+    }
   }
 
   const long long gw = run_index(a, warp, nwarps);
@@ -117,6 +137,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
   const int sub = lane % LPP;
   const int m0 = sub * MC;
+  const int rot = a.pair_rot ? T::pair_rot(lane) : 0;  // this lane's first component pair (bank-conflict rotation)
 
   // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
   // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
@@ -190,7 +211,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
 
   // software prefetch of the (L2-resident) pixel and upstream-gradient values one tile ahead
   auto fetch = [&](long long t, long long n_lane, int pix_lane, long long& n_out, long long& nfirst_out, PixRaw& raw,
-                   float& g_out, float2& st_out) {
+                   float& g_out, float2& st_out, bool want_g = true) {
     const int rows = tile_rows(t);
     const long long n_first = __shfl_sync(kFull, n_lane, 0);
     const int pix_first = __shfl_sync(kFull, pix_lane, 0);
@@ -200,19 +221,28 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     raw = load_pixel_raw(a, n, pix);
     g_out = 0.0f;
     if constexpr (BWD) {
-      if (a.g_image) g_out = a.g_image[n];
-      if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+      if (want_g) {
+        if (a.g_image) g_out = a.g_image[n];
+        if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+      }
     }
     (void)st_out;
     n_out = n;
     nfirst_out = n_first;
+  };
+  // the upstream gradient of pixel `pix` of image n on its own (LATE_G: the first tile's, read after griddepcontrol.wait)
+  [[maybe_unused]] auto fetch_g = [&](long long n, int pix) -> float {
+    float g_out = 0.0f;
+    if (a.g_image) g_out = a.g_image[n];
+    if (a.g_pixel) g_out += a.g_pixel[n * a.HW + pix];
+    return g_out;
   };
 
   long long n_cur = 0, nfirst_cur = 0;
   PixRaw raw_cur{};
   float g_cur = 0.0f;
   float2 st_cur = make_float2(1.0f, 1.0f);
-  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
+  if (t_cnt > 0) fetch(t_first, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur, !LATE_G);
 
   for (long long it = 0; it < t_cnt; ++it) {
     const long long t = t_first + it * t_dir;
@@ -223,10 +253,15 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const bool active = lane_used && (p < rows);
     const long long i = t * PPT + pp;  // this lane's pixel-sample
     const long long n = n_cur, n_first = nfirst_cur;
-    const float g = g_cur;
+    float g = g_cur;
     const float2 st = st_cur;
     Pixel px;
     decode_pixel<AR>(a, raw_cur, px);
+    [[maybe_unused]] int pix_this = pix_own;  // this lane's pixel within its image (before the advance below)
+    if constexpr (LATE_G) {
+      const int pix_first = __shfl_sync(kFull, pix_own, 0);  // (every lane takes part: lanes past a ragged tile shadow lane 0)
+      if (!(p < rows)) pix_this = pix_first;
+    }
     // advance the index and prefetch the next tile's pixel / upstream gradient
     if (!rev) {
       n_own += step_n;
@@ -243,7 +278,8 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         --n_own;
       }
     }
-    if (it + 1 < t_cnt) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
+    // (LATE_G: the first iteration's look-ahead reads the upstream gradient too, so it waits until after griddepcontrol.wait)
+    if (it + 1 < t_cnt && !(LATE_G && it == 0)) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
 
     float* slot = slots + s * TILE_F;
     float* rowp = slot + pp * ROWF;
@@ -269,9 +305,20 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     }
 
     // W_m = exp(logit_m - max logit)
-    float lmax = rowp[m0];
+    float lmax;
+    if constexpr (AL) {  // 64-bit loads in the rotated pair order (no bank conflicts)
+      lmax = -INFINITY;
 #pragma unroll
-    for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, rowp[m0 + m]);
+      for (int pr = 0; pr < NPAIR; ++pr) {
+        const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
+        const float2 t = *reinterpret_cast<const float2*>(rowp + m0 + 2 * prr);
+        lmax = fmaxf(lmax, fmaxf(t.x, t.y));
+      }
+    } else {
+      lmax = rowp[m0];
+#pragma unroll
+      for (int m = 1; m < MC; ++m) lmax = fmaxf(lmax, rowp[m0 + m]);
+    }
     lmax = group_max<LPP>(lmax, lane);
 
     // ST backward: the pixel's sums come from the forward pass
@@ -288,8 +335,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
 #pragma unroll 1
     for (int pr = 0; pr < NPAIR; ++pr) {
-      const int m = m0 + 2 * pr;
-      const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+      const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
+      const int m = m0 + 2 * prr;
+      const bool single = (MC % 2 == 1) && (prr == NPAIR - 1);
       f2 lg = ld_pair<AL>(rowp, m, single);
       if (single) lg = pk(lo(lg), -INFINITY);  // the padding half gets zero weight
       f2 mu[3], sc[3], kp[3];
@@ -385,13 +433,21 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       }
     } else {
       if constexpr (!ST) {
+      if constexpr (LATE_G) {
+        if (it == 0) {  // the first tile's derivatives are formed: from here on the upstream gradient is needed
+          pdl_wait();
+          g = fetch_g(n, pix_this);
+          if (t_cnt > 1) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
+        }
+      }
       const float rS = rcpa(S), rSW = rcpa(SW);
       float lt = 0.f, ll = 0.f;
       if (tiny) modl_pixel_logdomain(grow, M, px, a.plain != 0, lt, ll, PD != 0);
 #pragma unroll 1
       for (int pr = 0; pr < NPAIR; ++pr) {
-        const int m = m0 + 2 * pr;
-        const bool single = (MC % 2 == 1) && (pr == NPAIR - 1);
+        const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
+        const int m = m0 + 2 * prr;
+        const bool single = (MC % 2 == 1) && (prr == NPAIR - 1);
         f2 lg = ld_pair<AL>(rowp, m, single);
         const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
         const f2 wp = ld_pair<AL>(auxp, m, single);
