@@ -330,6 +330,29 @@ VAEMDL_API int vaemdl_iwae_split_combine(const double* ll_f64, const float* extr
                               float* log_w, float* lme_b, float* elbo, float* g_ll, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * The step's one collective at N > 1, over peer memory
+ * replaces: the batch mean of models/loss.py:37 when the batch is split over the GPUs of one box (each rank's step ends
+ *           with its additive ELBO share sum_b lme_b / B_total; the loss is the sum of the shares).
+ * Instead of a collective launch after the step, the kernel that forms the share stores it into EVERY rank's exchange buffer
+ * (NVLink P2P stores through CUDA-IPC mappings): one 8-byte word {step sequence number << 32 | float bits} at
+ * [seq % ring][rank] of a [ring][n_ranks] array of 64-bit words.
+ *   vaemdl_peer_next     : attaches an exchange to the NEXT call of this host thread that produces an `elbo` output
+ *                          (vaemdl_*_iwae_fwd*, vaemdl_*_iwae_step); that call publishes its share and detaches it.
+ *                          slots[r] = rank r's buffer as mapped in this process (slots[rank] = the local buffer).
+ *   vaemdl_peer_elbo_sum : waits (device-side, bounded) until the n_ranks words of step `seq` have arrived in THIS rank's
+ *                          buffer and writes their sum, added in rank order, to out[0] (NaN on time-out or overrun).
+ * ------------------------------------------------------------------------ */
+#define VAEMDL_MAX_PEERS 8
+typedef struct VaemdlPeer {
+  unsigned long long* slots[VAEMDL_MAX_PEERS];
+  int n_ranks, rank, ring;
+  unsigned seq;
+} VaemdlPeer;
+VAEMDL_API int vaemdl_peer_next(const VaemdlPeer* peer);
+VAEMDL_API int vaemdl_peer_elbo_sum(const unsigned long long* my_slots, int n_ranks, int ring, unsigned seq, float* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Samplers (explicit uniform noise; float64 internal arithmetic)
  * replaces: sample_from_discretized_mix_logistic   utils/mdl_openai.py:160-193 (explicit-noise lines :167, :185-186)
  *           MixtureDiscretizedLogistic._sample_n   utils/mdl.py:209-252

@@ -431,3 +431,69 @@ def test_split_sample_kernels_equal_the_unsplit_tail(built_lib, S, B, world):
     elbo1, g1 = vdist.split_sample_tail(ll, extra, S)
     _, lme_t, elbo_t, g_t = F.iwae_tail(ll, extra)
     assert abs(elbo1.item() - elbo_t.item()) <= 1e-6 * abs(elbo_t.item()) and relnorm(g1, g_t) < 1e-5
+
+
+def test_peer_elbo_exchange_single_process(built_lib):
+    """The peer-memory exchange of the ELBO shares (include/vaemdl.h: vaemdl_peer_next / vaemdl_peer_elbo_sum) with every
+    "rank" mapped into one local buffer: each ELBO-producing route (one-launch step, forward + finish, the unfused tail for
+    S > 512, the plain discretized logistic) publishes {seq, share} at [seq % ring][rank]; the reader adds the words of a
+    step in rank order and answers NaN for a step that never arrived.  (Two real ranks over NVLink: tools/peer_check.py.)"""
+    import ctypes
+    from vae_mdl_b200 import _abi, functional as F
+    from vae_mdl_b200.peer import ElboExchange
+    L = _abi.lib()
+    dev = torch.device(DEV)
+    n, ring = 3, 4
+    buf = torch.zeros(ring * n, dtype=torch.int64, device=dev)
+    out = torch.empty(1, device=dev)
+    st = _abi.stream_ptr(dev)
+
+    def attach(rank, seq):
+        p = _abi.VaemdlPeer()
+        for r in range(n):
+            p.slots[r] = buf.data_ptr()
+        p.n_ranks, p.rank, p.ring, p.seq = n, rank, ring, seq
+        assert L.vaemdl_peer_next(ctypes.byref(p)) == 0
+
+    g = torch.Generator().manual_seed(11)
+    S, B, H, W, M = 4, 6, 16, 16, 10
+    shares = []
+    for seq in (1, 2, 5):                                  # (5 % 4 == 1: the ring wraps onto step 1's row)
+        want = 0.0
+        for rank in range(n):
+            params = torch.randn(S, B, H, W, 10 * M, generator=g).to(dev)
+            x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).to(dev)
+            attach(rank, seq)
+            if rank == 0:      # one cooperative launch
+                elbo = F.modl_iwae_step(params, x_u8, None, b_total=n * B)[3]
+            elif rank == 1:    # forward + fused finish
+                elbo = F.modl_iwae_forward(params, x_u8, None, b_total=n * B)[3]
+            else:              # plain discretized logistic step
+                both = torch.randn(S, B, H, W, 6, generator=g).to(dev)
+                elbo = F.dlogistic_iwae_step(both[..., :3], both[..., 3:], x_u8, None, 0.0, 1.0, 256.0, b_total=n * B)[3]
+            want += float(elbo.item())
+        assert L.vaemdl_peer_elbo_sum(buf.data_ptr(), n, ring, seq, out.data_ptr(), st) == 0
+        assert abs(out.item() - want) <= 1e-6 * abs(want)
+        shares.append(want)
+    words = buf.cpu().view(ring, n)
+    assert int(words[1, 0].item() >> 32) == 5 and int(words[2, 2].item() >> 32) == 2
+    # a detached call publishes nothing; an overrun step (1 was overwritten by 5) reads as NaN
+    before = buf.clone()
+    F.modl_iwae_forward(params, x_u8, None)
+    assert torch.equal(buf, before)
+    assert L.vaemdl_peer_elbo_sum(buf.data_ptr(), n, ring, 1, out.data_ptr(), st) == 0
+    assert math.isnan(out.item())
+    # the unfused tail (S > 512) publishes through the one-thread push kernel
+    params = torch.randn(600, 1, 8, 8, 10 * M, generator=g).to(dev)
+    x1 = torch.randint(0, 256, (1, 8, 8, 3), dtype=torch.uint8, generator=g).to(dev)
+    for rank in range(n):
+        attach(rank, 7)
+        e7 = F.modl_iwae_forward(params, x1, None, b_total=n)[3]
+    assert L.vaemdl_peer_elbo_sum(buf.data_ptr(), n, ring, 7, out.data_ptr(), st) == 0
+    assert abs(out.item() - 3 * e7.item()) <= 1e-6 * abs(3 * e7.item())
+    # the host helper with one rank
+    ex = ElboExchange(dev)
+    seq = ex.attach()
+    e1 = F.modl_iwae_forward(params, x1, None)[3]
+    assert abs(ex.read(seq).item() - e1.item()) <= 1e-7 * abs(e1.item())
+    ex.close()

@@ -30,6 +30,13 @@ class LatentTerm(ctypes.Structure):
     _fields_ = [("z", c_void_p), ("loc", c_void_p), ("scale", c_void_p), ("D", c_int), ("params_per_sample", c_int),
                 ("weight", c_float)]
 
+
+
+class VaemdlPeer(ctypes.Structure):
+    """``VaemdlPeer`` of include/vaemdl.h (the peer-memory exchange of the ELBO shares)."""
+    _fields_ = [("slots", ctypes.c_uint64 * 8), ("n_ranks", c_int), ("rank", c_int), ("ring", c_int), ("seq", ctypes.c_uint)]
+
+
 _LIB = None
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
@@ -94,6 +101,8 @@ PROTOTYPES = {
     "vaemdl_iwae_split_local": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "vaemdl_iwae_split_combine": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_longlong, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_peer_next": (c_int, [c_void_p]),
+    "vaemdl_peer_elbo_sum": (c_int, [c_void_p, c_int, c_int, ctypes.c_uint, c_void_p, c_void_p]),
     "vaemdl_modl_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_plain_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_longlong, c_longlong, c_int,

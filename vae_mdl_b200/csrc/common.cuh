@@ -221,6 +221,33 @@ __device__ __forceinline__ double image_sum(const PartialGeom& g, long long n, b
   return small ? image_sum_t<unsigned>(g, n) : image_sum_t<long long>(g, n);
 }
 
+// ---- the ELBO share of a batch shard, published to every rank of the box over peer memory (NVLink P2P stores) ---------------
+// With the batch split across ranks each rank's step ends with its additive share of the ELBO,
+// sum_b lme_b / B_total (models/loss.py:37); the global value is the sum of the shares.  Instead of a separate collective
+// launch, the kernel that forms the share stores it -- one self-describing 8-byte word {sequence number, value} -- into slot
+// [seq % ring][rank] of EVERY rank's exchange buffer (the peers' buffers are mapped through CUDA IPC).  A reader sums the
+// `n` words of step `seq` in rank order (vaemdl_peer_elbo_sum): bit-identical on every rank.
+struct PeerOut {
+  unsigned long long* slots[VAEMDL_MAX_PEERS];  // slots[r]: rank r's buffer, [ring][n] words, as mapped in THIS process
+  int n = 0;                                    // ranks (0: nothing to publish)
+  int rank = 0;
+  int ring = 1;
+  unsigned seq = 0;
+};
+__device__ __forceinline__ void peer_publish(const PeerOut& p, float value) {  // one thread
+  if (p.n <= 0) return;
+  const unsigned long long word = (static_cast<unsigned long long>(p.seq) << 32) | __float_as_uint(value);
+  const size_t at = static_cast<size_t>(p.seq % static_cast<unsigned>(p.ring)) * p.n + p.rank;
+  for (int r = 0; r < p.n; ++r) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.slots[r] + at), "l"(word) : "memory");
+  }
+}
+// host: the exchange attached to the next ELBO-producing call of this host thread (vaemdl_peer_next), consumed by it
+PeerOut take_peer();
+void give_peer(const PeerOut& p);  // hand it back (a one-launch step that falls back to separate launches)
+// fallback for the routes whose ELBO comes out of vaemdl_iwae_tail: one tiny launch that publishes elbo[0]
+int peer_push(const PeerOut& p, const float* elbo, cudaStream_t st);
+
 // ---- the IWAE finish inside a cooperative one-launch step (modl_step_kernel, dl_step_kernel) --------------------------------
 struct StepFinish {
   PartialGeom geom;
@@ -236,6 +263,7 @@ struct StepFinish {
   int S;  // <= 32: one importance sample per lane
   float b_norm;
   bool small;
+  PeerOut peer;  // where the ELBO share also goes (n = 0: nowhere)
 };
 // warp `gw` of `total_warps` takes batch elements gw, gw + total_warps, ...: same arithmetic, in the same order, as
 // finish_kernel steps (1) and (2) with S <= 32
@@ -271,6 +299,7 @@ struct IwaeOut {  // outputs of the fused IWAE finish (all nullable); active whe
   long long B = 0, B_total = 0;
   const float* extra = nullptr;
   float *log_w = nullptr, *lme_b = nullptr, *elbo = nullptr, *g_ll = nullptr;
+  PeerOut peer;
 };
 // ll / ll64 [n_img] nullable.  iw.S == 0: one reduction launch.  Otherwise also log_w, log-mean-exp, elbo and
 // g_ll = d(-elbo)/d ll: ONE fused launch when S <= 512, else reduction + IWAE tail.  scratch: n_img doubles;

@@ -591,7 +591,11 @@ __global__ void __launch_bounds__(kStepWarps * 32, 1) dl_step_kernel(const DlSte
     double t = 0.0;
     for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
     t = dl_warp_sum(t);
-    if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+    if (lane == 0) {
+      const float e = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+      sa.f.elbo[0] = e;
+      peer_publish(sa.f.peer, e);
+    }
   }
   for (long long t = t_begin; t < t_end; ++t) {
     const float* kp = keep + (t - t_begin) * (kStepKeep * 32);
@@ -805,7 +809,9 @@ static int dl_fwd_impl(const float* loc, const float* logscale, int C, int ld, c
     rc = cuda_rc(cudaGetLastError());
   }
   if (rc || !iwae) return rc;
-  return vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  rc = vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  if (rc || !iw.elbo) return rc;
+  return peer_push(iw.peer, iw.elbo, st);
 }
 }  // namespace vaemdl
 
@@ -833,6 +839,7 @@ extern "C" int vaemdl_dlogistic_iwae_fwd(const float* loc, const float* logscale
   iw.lme_b = lme_b;
   iw.elbo = elbo;
   iw.g_ll = g_ll;
+  iw.peer = take_peer();
   return dl_fwd_impl(loc, logscale, C, ld, x, x_dtype, static_cast<long long>(S) * B, x_batch, D, low, high, levels,
                      nullptr, ll_image, ll_image_f64, iw, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -954,6 +961,7 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   sa.f.S = S;
   sa.f.b_norm = static_cast<float>(B_total > 0 ? B_total : B);
   sa.f.small = n_img * a.rows_per_img < (1ll << 31);
+  sa.f.peer = elbo ? take_peer() : PeerOut{};
   if (launches) *launches = 1;
   void* args[] = {&sa};
   void* kern = kind == 1 ? reinterpret_cast<void*>(dl_step_kernel<true>) : reinterpret_cast<void*>(dl_step_kernel<false>);
@@ -962,6 +970,7 @@ extern "C" int vaemdl_dlogistic_iwae_step(const float* loc, const float* logscal
   if (rc == static_cast<int>(cudaErrorCooperativeLaunchTooLarge) || rc == static_cast<int>(cudaErrorLaunchOutOfResources)) {
     // the grid cannot be co-resident right now: nothing was enqueued, run the three ordinary launches instead
     cudaGetLastError();
+    give_peer(sa.f.peer);
     if (launches) *launches = 3;
     rc = vaemdl_dlogistic_iwae_fwd(loc, logscale, C, ld, x, x_dtype, S, B, B_total, x_batch, D, low, high, levels, extra,
                                    ll_image, ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, stream);

@@ -35,6 +35,7 @@ struct FinishArgs {
   int S, BB;
   float b_norm;
   bool small;             // 32-bit index arithmetic suffices
+  PeerOut peer;
 };
 
 constexpr int kFinishThreads = 128;    // block size when several blocks share the batch
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(kFinishMaxThreads) finish_kernel(const FinishA
     if (threadIdx.x == 0) {
       double t = 0.0;
       for (int w = 0; w < NW; ++w) t += blk[w];
-      a.elbo[0] = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+      const float e = static_cast<float>(t / static_cast<double>(a.b_norm));  // models/loss.py:37
+      a.elbo[0] = e;
+      peer_publish(a.peer, e);
     }
     return;
   }
@@ -121,7 +124,9 @@ __global__ void __launch_bounds__(kFinishMaxThreads) finish_kernel(const FinishA
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    a.elbo[0] = static_cast<float>(total / static_cast<double>(a.b_norm));  // models/loss.py:37
+    const float e = static_cast<float>(total / static_cast<double>(a.b_norm));  // models/loss.py:37
+    a.elbo[0] = e;
+    peer_publish(a.peer, e);
     *a.counter = 0u;
   }
 }
@@ -155,7 +160,9 @@ __global__ void __launch_bounds__(256) finish_warp_kernel(const FinishWarpArgs a
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
   if (lane == 0) {
-    a.f.elbo[0] = static_cast<float>(t / static_cast<double>(a.f.b_norm));  // models/loss.py:37
+    const float e = static_cast<float>(t / static_cast<double>(a.f.b_norm));  // models/loss.py:37
+    a.f.elbo[0] = e;
+    peer_publish(a.f.peer, e);
     *a.counter = 0u;
   }
 }
@@ -193,6 +200,7 @@ int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll
     w.f.S = iw.S;
     w.f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
     w.f.small = small;
+    w.f.peer = iw.elbo ? iw.peer : PeerOut{};
     w.counter = counter;
     const long long grid = (iw.B + 7) / 8;
     return cuda_rc(launch_pdl(finish_warp_kernel, static_cast<unsigned>(grid), 256u, 0, st, w));
@@ -214,6 +222,7 @@ int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll
     f.BB = BB;
     f.b_norm = static_cast<float>(iw.B_total > 0 ? iw.B_total : iw.B);
     f.small = small;
+    f.peer = iw.elbo ? iw.peer : PeerOut{};
     const long long grid = (iw.B + BB - 1) / BB;
     return cuda_rc(launch_pdl(finish_kernel, static_cast<unsigned>(grid), static_cast<unsigned>(threads),
                               static_cast<size_t>(BB) * iw.S * sizeof(double), st, f));
@@ -222,7 +231,91 @@ int finish_partials(const PartialGeom& g, long long n_img, float* ll, double* ll
   reduce_partials_kernel<<<static_cast<unsigned>((n_img + 127) / 128), 128, 0, st>>>(g, small, ll, ll64_dst, n_img);
   int rc = cuda_rc(cudaGetLastError());
   if (rc || !iwae) return rc;
-  return vaemdl_iwae_tail(nullptr, ll64_dst, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  rc = vaemdl_iwae_tail(nullptr, ll64_dst, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  if (rc || !iw.elbo) return rc;
+  return peer_push(iw.peer, iw.elbo, st);
+}
+
+// ---- peer-memory exchange of the ELBO shares (common.cuh: PeerOut) -----------------------------------------------------------
+static thread_local PeerOut g_next_peer;
+
+PeerOut take_peer() {
+  PeerOut p = g_next_peer;
+  g_next_peer = PeerOut{};
+  return p;
+}
+
+void give_peer(const PeerOut& p) { g_next_peer = p; }
+
+__global__ void peer_push_kernel(const PeerOut p, const float* __restrict__ elbo) {
+  pdl_wait();
+  if (threadIdx.x == 0) peer_publish(p, elbo[0]);
+}
+
+int peer_push(const PeerOut& p, const float* elbo, cudaStream_t st) {
+  if (p.n <= 0) return VAEMDL_OK;
+  peer_push_kernel<<<1, 32, 0, st>>>(p, elbo);
+  return cuda_rc(cudaGetLastError());
+}
+
+// thread r waits for rank r's word of step `seq`; thread 0 adds the values in rank order
+__global__ void peer_sum_kernel(const unsigned long long* slots, int n, int ring, unsigned seq, float* out) {
+  __shared__ float val[VAEMDL_MAX_PEERS];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const int r = threadIdx.x;
+  if (r < n) {
+    const unsigned long long* src = slots + static_cast<size_t>(seq % static_cast<unsigned>(ring)) * n + r;
+    const long long t0 = clock64();
+    unsigned long long w;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+      const unsigned got = static_cast<unsigned>(w >> 32);
+      if (got == seq) break;
+      if (static_cast<int>(got - seq) > 0 || clock64() - t0 > 4000000000ll) {  // overrun by a later step, or ~2 s without news
+        atomicExch(&bad, 1);
+        break;
+      }
+      __nanosleep(200);
+    }
+    val[r] = __uint_as_float(static_cast<unsigned>(w & 0xffffffffu));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.0f;
+    for (int q = 0; q < n; ++q) acc += val[q];
+    out[0] = bad ? __int_as_float(0x7fc00000) : acc;
+  }
 }
 
 }  // namespace vaemdl
+
+using namespace vaemdl;
+
+extern "C" int vaemdl_peer_next(const VaemdlPeer* peer) {
+  if (!peer) {
+    g_next_peer = PeerOut{};
+    return VAEMDL_OK;
+  }
+  if (peer->n_ranks < 1 || peer->n_ranks > VAEMDL_MAX_PEERS || peer->rank < 0 || peer->rank >= peer->n_ranks || peer->ring < 1)
+    return VAEMDL_EINVAL;
+  PeerOut p;
+  for (int r = 0; r < peer->n_ranks; ++r) {
+    if (!peer->slots[r] || (reinterpret_cast<uintptr_t>(peer->slots[r]) & 7u)) return VAEMDL_EINVAL;
+    p.slots[r] = peer->slots[r];
+  }
+  p.n = peer->n_ranks;
+  p.rank = peer->rank;
+  p.ring = peer->ring;
+  p.seq = peer->seq;
+  g_next_peer = p;
+  return VAEMDL_OK;
+}
+
+extern "C" int vaemdl_peer_elbo_sum(const unsigned long long* my_slots, int n_ranks, int ring, unsigned seq, float* out,
+                                    void* stream) {
+  if (!my_slots || !out || n_ranks < 1 || n_ranks > VAEMDL_MAX_PEERS || ring < 1) return VAEMDL_EINVAL;
+  peer_sum_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(my_slots, n_ranks, ring, seq, out);
+  return cuda_rc(cudaGetLastError());
+}

@@ -595,7 +595,9 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
     rc = cuda_rc(cudaGetLastError());
   }
   if (rc || !iwae) return rc;
-  return vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  rc = vaemdl_iwae_tail(nullptr, a.ll_atomic, iw.extra, iw.S, iw.B, iw.B_total, iw.log_w, iw.lme_b, iw.elbo, iw.g_ll, st);
+  if (rc || !iw.elbo) return rc;
+  return peer_push(iw.peer, iw.elbo, st);
 }
 }  // namespace vaemdl
 
@@ -646,6 +648,7 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
   iw.lme_b = lme_b;
   iw.elbo = elbo;
   iw.g_ll = g_ll;
+  iw.peer = take_peer();
   return modl_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, static_cast<long long>(S) * B, x_batch, H, W, M, nullptr,
                            ll_image, ll_image_f64, iw, workspace, workspace_bytes, st, bf16, pix_stats, bins);
 }
@@ -744,6 +747,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   f.S = S;
   f.b_norm = static_cast<float>(B_total > 0 ? B_total : B);
   f.small = n_px < (1ll << 31);
+  f.peer = elbo ? take_peer() : PeerOut{};
   if (launches) *launches = 1;
   switch (M) {
     case 5:
@@ -763,6 +767,7 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
     // the grid cannot be co-resident right now (another context holds SMs, MPS partition, ...): nothing was enqueued,
     // the step runs as three ordinary launches instead
     cudaGetLastError();
+    give_peer(f.peer);
     if (launches) *launches = 3;
     rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,
                                 ll_image_f64, log_w, lme_b, elbo, g_ll, workspace, workspace_bytes, st, 0, stats, bins);

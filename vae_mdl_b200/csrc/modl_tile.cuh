@@ -550,7 +550,11 @@ __global__ void __launch_bounds__(512, 1) modl_step_kernel(const StepArgs sa) {
     double t = 0.0;
     for (long long b = lane; b < sa.f.B; b += 32) t += sa.f.lme64[b];
     t = warp_sum(t);
-    if (lane == 0) sa.f.elbo[0] = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+    if (lane == 0) {
+      const float e = static_cast<float>(t / static_cast<double>(sa.f.b_norm));  // models/loss.py:37
+      sa.f.elbo[0] = e;
+      peer_publish(sa.f.peer, e);  // N > 1: the share goes straight into every rank's exchange buffer (NVLink P2P stores)
+    }
   }
   tile_body<MC, LPP, true, 1, AR, true, 0, true>(sa.a, smem_raw);    // one-pass gradient from a.pix_stats
 }

@@ -108,10 +108,19 @@ class IwaeEvaluator:
         return llh.mean(), llh
 
 
-def sharded_modl_iwae_step(step_fn: Callable, params_shard, x_shard, extra_shard, b_total: int, group=None):
+def sharded_modl_iwae_step(step_fn: Callable, params_shard, x_shard, extra_shard, b_total: int, group=None,
+                           exchange=None):
     """One IWAE observation-model step with the batch split across ranks.  ``step_fn`` is
-    ``vae_mdl_b200.modl_iwae_step``; each rank gets its additive share of the loss, one scalar all-reduce makes it the
-    global loss.  Gradients stay rank-local (they belong to the rank's own decoder activations)."""
+    ``vae_mdl_b200.modl_iwae_step``; each rank gets its additive share of the loss, the sum over the ranks is the global
+    loss.  Gradients stay rank-local (they belong to the rank's own decoder activations).
+
+    ``exchange``: a ``vae_mdl_b200.peer.ElboExchange`` -- the kernel that forms the share then stores it straight into
+    every rank's exchange buffer (NVLink P2P) and the global loss is a rank-order sum of those words: no collective
+    launch.  Without it: one scalar ``all_reduce`` (NCCL on GPUs, gloo in the CPU tests)."""
+    if exchange is not None:
+        seq = exchange.attach()
+        loss, lpxz, dparams = step_fn(params_shard, x_shard, extra_shard, True, b_total)
+        return -exchange.read(seq).clone(), lpxz, dparams
     loss, lpxz, dparams = step_fn(params_shard, x_shard, extra_shard, True, b_total)
     loss = allreduce_sum(loss.clone(), group)
     return loss, lpxz, dparams
