@@ -214,6 +214,8 @@ class ModlStep:
 
     def fwd(self):
         # forward kernel + fused finish kernel: lpxz (float64), log-mean-exp, elbo, g_ll = d(-elbo)/d lpxz
+        if LINK is not None:
+            LINK.attach()
         rc = self.L.vaemdl_modl_iwae_fwd_stats(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B,
                                                self.b_total, self.B, self.H, self.W, self.M, self.extra.data_ptr(), None,
                                                self.ll64.data_ptr(), None, self.lme.data_ptr(), self.elbo.data_ptr(),
@@ -236,6 +238,8 @@ class ModlStep:
         forward + finish + backward (3 launches) otherwise; self.launches holds what the library enqueued."""
         self.next_input()
         n = ctypes.c_int(0)
+        if LINK is not None:
+            LINK.attach()
         rc = self.L.vaemdl_modl_iwae_step(self.params.data_ptr(), self.x.data_ptr(), 1, 0, 0, self.S, self.B, self.b_total,
                                           self.B, self.H, self.W, self.M, self.extra.data_ptr(), None, self.ll64.data_ptr(),
                                           None, self.lme.data_ptr(), self.elbo.data_ptr(), self.g_ll.data_ptr(),
@@ -247,12 +251,85 @@ class ModlStep:
 PROBE_EVERY = 4  # every 4th timed step carries the per-kernel CUDA events
 
 
-def allreduce_elbo(step, world):
-    """The path's one collective at N > 1 (models/loss.py:37 over a batch split across ranks): every rank's additive
-    share of the ELBO -> the global value, on the stream the kernels run on."""
-    if world > 1:
+class ElboLink:
+    """The path's one collective at N > 1 (models/loss.py:37 over a batch split across ranks): every rank's additive share
+    of the ELBO -> the global value.  Preferred: the peer-memory exchange (vae_mdl_b200/peer.py) -- the kernel that forms
+    the share stores it into every rank's buffer over NVLink, a one-warp kernel adds the shares in rank order; if the IPC
+    mappings cannot be set up on this box (any rank), all ranks fall back to a 4-byte NCCL all-reduce per step."""
+
+    def __init__(self, world, dev):
+        self.world, self.dev, self.ex, self.kind, self.why = world, dev, None, None, None
+        self.pending = None
+        self.lag = int(os.environ.get("VAEMDL_BENCH_LINK_LAG", "1"))
+        if world <= 1:
+            if os.environ.get("VAEMDL_BENCH_LINK1"):  # measurement aid: the exchange machinery with a single rank
+                from vae_mdl_b200.peer import ElboExchange
+                self.ex = ElboExchange(dev)
+                self.kind = "peer memory (single rank, measurement aid)"
+                self.global_elbo = torch.zeros(1, device=dev)
+                self.world = 2
+            return
         import torch.distributed as dist
-        dist.all_reduce(step.elbo, op=dist.ReduceOp.SUM)
+        ok = 1
+        try:
+            if os.environ.get("VAEMDL_BENCH_NCCL"):
+                raise RuntimeError("VAEMDL_BENCH_NCCL set")
+            from vae_mdl_b200.peer import ElboExchange
+            self.ex = ElboExchange(dev)
+        except Exception as e:  # pragma: no cover - depends on the box
+            ok, self.why = 0, repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if self.ex is not None:
+                self.ex.close()
+                self.ex = None
+            self.kind = "nccl all_reduce(sum) of the ELBO share, 4 bytes, every step" + (f" (peer memory unavailable: {self.why})" if self.why else "")
+        else:
+            self.kind = ("peer memory: the kernel that forms the ELBO share stores it into every rank's exchange buffer "
+                         "(CUDA-IPC mappings, NVLink P2P) + a one-warp rank-order sum kernel, every step")
+        self.global_elbo = torch.zeros(1, device=dev)
+
+    def attach(self):      # right before the call that produces the share
+        if self.ex is not None:
+            self.seq = self.ex.attach()
+
+    def finish(self, elbo):  # right after the step's launches, same stream
+        if self.world <= 1:
+            return
+        if self.ex is not None:
+            # The shares of step k are stored by the step's own kernels (every rank, over NVLink).  Their rank-order sum is
+            # enqueued `lag` steps later (default 1): by then every peer's word has long arrived, so no rank ever spins on a
+            # slower one inside its critical path.  flush() enqueues what is still outstanding.
+            if self.lag <= 0:
+                self.ex.read(self.seq, out=self.global_elbo)
+            else:
+                if self.pending is not None:
+                    self.ex.read(self.pending, out=self.global_elbo)
+                self.pending = self.seq
+        else:
+            import torch.distributed as dist
+            self.global_elbo.copy_(elbo)
+            dist.all_reduce(self.global_elbo, op=dist.ReduceOp.SUM)
+
+    def flush(self):
+        if self.ex is not None and self.pending is not None:
+            self.ex.read(self.pending, out=self.global_elbo)
+            self.pending = None
+
+    def close(self):
+        self.flush()
+        if self.ex is not None:
+            self.ex.close()
+            self.ex = None
+
+
+LINK = None  # set in main()
+
+
+def allreduce_elbo(step, world):
+    if LINK is not None:
+        LINK.finish(step.elbo)
 
 
 def run_sustained(step: ModlStep, seconds, ms_per_step, world, dev, sampler_index):
@@ -270,6 +347,8 @@ def run_sustained(step: ModlStep, seconds, ms_per_step, world, dev, sampler_inde
             step.fwd()
             step.bwd()
             allreduce_elbo(step, world)
+        if LINK is not None:
+            LINK.flush()
         e1.record(step.stream)
         torch.cuda.synchronize(dev)
     barrier(world)
@@ -307,6 +386,8 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
                 step.fwd()
                 step.bwd()
             allreduce_elbo(step, world)
+        if LINK is not None:
+            LINK.flush()
         e_end.record(step.stream)
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
@@ -461,6 +542,8 @@ def run_small_shape(name, world, dev, peak, steps=60, warm=6):
     for _ in range(steps):
         st.step()
         allreduce_elbo(st, world)
+    if LINK is not None:
+        LINK.flush()
     e1.record(st.stream)
     torch.cuda.synchronize(dev)
     barrier(world)
@@ -860,6 +943,8 @@ def main():
     kind, S, B, H, W, M = wl
     peak, peak_how = measured_hbm_peak()
 
+    global LINK
+    LINK = ElboLink(world, dev)
     step = ModlStep(S, B, H, W, M, dev, seed=1234 + rank, b_total=B * world)
     res = run_device_resident(step, args.steps, args.warmup, world, dev, local_rank)
     total_s = max_over_ranks(res["total_ms"], world, dev) * 1e-3
@@ -905,6 +990,9 @@ def main():
         split = run_sample_split(S, B, H, W, M, min(args.steps, 30), max(3, min(args.warmup, 5)), world, rank, dev, peak)
         torch.cuda.empty_cache()
 
+    link_kind = LINK.kind
+    LINK.close()
+    LINK = None
     # end to end through the host-buffer C-ABI call; then the SAME inputs through the device arm (elbo_check)
     e2e_steps = args.e2e_steps or min(args.steps, 10)
     dt, h2d, d2h, check = run_e2e(S, B, H, W, M, e2e_steps, args.warmup, world, dev, seed=99 + rank)
@@ -939,7 +1027,7 @@ def main():
             "config": workload_config(args.workload, wl),
             "clocks": res["clocks"], "e2e": e2e, "gpu_launches": ModlStep.LAUNCHES_PER_STEP * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "collective_in_step": "all_reduce(sum) of the ELBO share, 4 bytes, every step" if world > 1 else None,
+            "collective_in_step": link_kind,
             "kernel_ms": {"fwd_plus_finish": res["fwd_ms"], "bwd": res["bwd_ms"], "probed_steps": res["probed_steps"],
                           "how": "CUDA events around the two launch groups on every 4th step of the timed region"},
             "elbo_check": check,

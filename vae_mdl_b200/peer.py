@@ -24,6 +24,11 @@ _LAZY_PEER_ACCESS = 1  # cudaIpcMemLazyEnablePeerAccess
 _rt = None
 
 
+class _IpcHandle(ctypes.Structure):
+    """``cudaIpcMemHandle_t``: 64 opaque bytes, passed to ``cudaIpcOpenMemHandle`` BY VALUE."""
+    _fields_ = [("reserved", ctypes.c_char * _IPC_HANDLE_BYTES)]
+
+
 def _cudart():
     global _rt
     if _rt is None:
@@ -38,8 +43,8 @@ def _cudart():
         _rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
         _rt.cudaFree.argtypes = [ctypes.c_void_p]
         _rt.cudaMemset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
-        _rt.cudaIpcGetMemHandle.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        _rt.cudaIpcOpenMemHandle.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char * _IPC_HANDLE_BYTES, ctypes.c_uint]
+        _rt.cudaIpcGetMemHandle.argtypes = [ctypes.POINTER(_IpcHandle), ctypes.c_void_p]
+        _rt.cudaIpcOpenMemHandle.argtypes = [ctypes.POINTER(ctypes.c_void_p), _IpcHandle, ctypes.c_uint]
         _rt.cudaIpcCloseMemHandle.argtypes = [ctypes.c_void_p]
     return _rt
 
@@ -76,31 +81,39 @@ class ElboExchange:
             slots = [None] * self.world
             slots[self.rank] = base.value
             if self.world > 1:
-                handle = (ctypes.c_char * _IPC_HANDLE_BYTES)()
-                _ok(rt.cudaIpcGetMemHandle(handle, base), "cudaIpcGetMemHandle")
+                handle = _IpcHandle()
+                _ok(rt.cudaIpcGetMemHandle(ctypes.byref(handle), base), "cudaIpcGetMemHandle")
                 gathered = [None] * self.world
-                dist.all_gather_object(gathered, bytes(handle), group=group)
+                dist.all_gather_object(gathered, bytes(bytearray(handle)), group=group)
                 for r, raw in enumerate(gathered):
                     if r == self.rank:
                         continue
-                    h = (ctypes.c_char * _IPC_HANDLE_BYTES).from_buffer_copy(raw)
+                    h = _IpcHandle.from_buffer_copy(raw)
                     p = ctypes.c_void_p()
                     _ok(rt.cudaIpcOpenMemHandle(ctypes.byref(p), h, _LAZY_PEER_ACCESS), "cudaIpcOpenMemHandle")
                     self._peer_ptrs.append(p)
                     slots[r] = p.value
                 dist.barrier(group=group)  # every mapping exists before anyone stores
         self._slots = slots
+        self._struct = None
         self._out = torch.empty(1, dtype=torch.float32, device=self.device)
 
     def attach(self) -> int:
         """Attaches the exchange to the next ELBO-producing C-ABI call of this host thread; returns the step's sequence
         number (pass it to ``read``)."""
         self.seq += 1
-        p = _abi.VaemdlPeer()
-        for r in range(self.world):
-            p.slots[r] = self._slots[r]
-        p.n_ranks, p.rank, p.ring, p.seq = self.world, self.rank, self.ring, self.seq
-        _abi.check(_abi.lib().vaemdl_peer_next(ctypes.byref(p)), "vaemdl_peer_next")
+        p = self._struct
+        if p is None:
+            p = self._struct = _abi.VaemdlPeer()
+            for r in range(self.world):
+                p.slots[r] = self._slots[r]
+            p.n_ranks, p.rank, p.ring = self.world, self.rank, self.ring
+            self._struct_ref = ctypes.byref(p)
+            self._next = _abi.lib().vaemdl_peer_next
+        p.seq = self.seq
+        rc = self._next(self._struct_ref)
+        if rc:
+            _abi.check(rc, "vaemdl_peer_next")
         return self.seq
 
     def detach(self):
