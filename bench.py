@@ -1000,7 +1000,17 @@ def main():
     e2e = {"value": world * n_px * e2e_steps / dt, "unit": "px-samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
            "api": "vaemdl_modl_iwae_step_host (pinned host buffers; H2D params+x+extra, D2H grads+ll+lme+elbo each step)",
-           "host_cpus_bound_near_gpu": bound_cpus}
+           "host_cpus_bound_near_gpu": bound_cpus,
+           "achieved_GBs_per_direction_per_gpu": h2d / (dt / e2e_steps) / 1e9}
+    try:  # the box's measured copy ceiling with this many ranks copying both ways at once (tools/pcie_probe.py)
+        with open(os.path.join(ROOT, "profiles", "e2e_pcie.json")) as f:
+            ceil = json.load(f)["per_n"].get(str(world), {}).get("both", {}).get("per_gpu_GBs_per_direction")
+        if ceil:
+            e2e["copy_ceiling_GBs_per_direction_per_gpu"] = ceil
+            e2e["frac_of_copy_ceiling"] = e2e["achieved_GBs_per_direction_per_gpu"] / ceil
+            e2e["ceiling_source"] = "profiles/e2e_pcie.json (simultaneous H2D + D2H, all ranks; the aggregate saturates at 2 GPUs)"
+    except Exception:
+        pass
     torch.cuda.empty_cache()
 
     ev = None
