@@ -183,6 +183,19 @@ VAEMDL_API int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int 
                     long long n_img, int x_batch, int H, int W, int M,
                     const float* g_image, const float* g_pixel,
                     void* dparams_bf16, void* stream);
+/* The same with the per-pixel mixture sums handed from the forward to the backward call (pix_stats [n_img*H*W*2] float32,
+ * written by the forward kernel): for n_mix 10 / 20 / 30 the backward kernel then keeps the tile in bfloat16 in shared
+ * memory (two slots per warp), widens every component pair as it reads it and writes the final gradient rounded ONCE --
+ * the route that makes bfloat16 parameters faster than float32 ones.  Other n_mix ignore pix_stats. */
+VAEMDL_API int vaemdl_modl_iwae_fwd_stats_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                         int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                         const float* extra,
+                         float* ll_image, double* ll_image_f64, float* log_w, float* lme_b, float* elbo, float* g_ll,
+                         float* pix_stats, void* workspace, size_t workspace_bytes, void* stream);
+VAEMDL_API int vaemdl_modl_bwd_stats_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                          long long n_img, int x_batch, int H, int W, int M,
+                          const float* g_image, const float* g_pixel, const float* pix_stats,
+                          void* dparams_bf16, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Pixel mixture of discretized logistics WITHOUT conditioning on the observed x

@@ -1,5 +1,5 @@
-"""bfloat16 parameters: the kernels read a bf16 decoder output, widen it in shared memory, compute in
-float32 and write a bf16 gradient.  Checked against (1) the float32 kernels on the widened parameters -- bit-identical
+"""bfloat16 parameters: the kernels read a bf16 decoder output, widen it (in place in shared memory, or -- n_mix
+10 / 20 / 30 -- pair by pair as they read a tile that stays bfloat16), compute in float32 and write a bf16 gradient.  Checked against (1) the float32 kernels on the widened parameters -- bit-identical
 where both run the same kernel family -- and (2) the float64 oracle on the widened parameters."""
 import pytest
 import torch
@@ -119,3 +119,44 @@ def test_bf16_no_write_outside_the_gradient_buffer(built_lib):
         torch.cuda.synchronize()
         assert bool((buf[:G] == -7.0).all()) and bool((buf[-G:] == -7.0).all())
         assert not bool(torch.isnan(dp.float()).any()) and bool((dp != -7.0).any())
+
+
+@pytest.mark.parametrize("S,B,H,W,M", [(2, 3, 8, 8, 10), (2, 2, 8, 8, 20), (2, 2, 8, 4, 30), (1, 3, 3, 3, 10), (1, 1, 1, 1, 10),
+                                       (3, 5, 32, 32, 10), (2, 3, 16, 16, 30), (4, 2, 64, 64, 10)])
+def test_bf16_direct_route_with_forward_sums(F, monkeypatch, S, B, H, W, M):
+    """n_mix 10 / 20 / 30 with the per-pixel sums handed from the forward to the backward call (vaemdl_modl_iwae_fwd_stats_bf16 /
+    vaemdl_modl_bwd_stats_bf16): the tile stays bfloat16 in shared memory, two slots per warp.  Same arithmetic as the float32
+    kernels on the widened parameters: the per-image sums are bit-identical, the gradient is the float32 one-pass gradient
+    rounded once; both within tolerance of the float64 oracle; and identical to the widen-in-place route's sums."""
+    params, x_u8, g = trained_like(5500 + 7 * M + H, S, B, H, W, M)
+    pb = params.bfloat16()
+    wide = pb.float()
+    p64 = wide.double().requires_grad_(True)
+    x64 = O.normalize_u8(x_u8, torch.float64)
+    ll64 = O.modl_log_prob(p64, x64)[..., 0].sum((-1, -2))
+    extra = (ll64.detach().mean(0, keepdim=True) - ll64.detach()).float() + torch.randn(S, B, generator=g)
+    loss64 = -O.logmeanexp(ll64 + extra.double(), 0).mean()
+    loss64.backward()
+    pbd, wd, xd, ed = pb.to(DEV), wide.to(DEV), x_u8.to(DEV), extra.to(DEV)
+    out_b = F.modl_iwae_forward(pbd, xd, ed, want_stats=True)
+    assert out_b[5] is not None
+    dp_b = F.modl_backward(pbd, xd, g_image=out_b[4], pix_stats=out_b[5])
+    assert dp_b.dtype == torch.bfloat16
+    # float32 kernels on the widened parameters, one-pass gradient from the same kind of sums
+    monkeypatch.setenv("VAEMDL_STATS", "all")
+    out_f = F.modl_iwae_forward(wd, xd, ed, want_stats=True)
+    dp_f = F.modl_backward(wd, xd, g_image=out_f[4], pix_stats=out_f[5])
+    monkeypatch.delenv("VAEMDL_STATS")
+    assert torch.equal(out_b[0], out_f[0]) and torch.equal(out_b[4], out_f[4]) and torch.equal(out_b[5], out_f[5])
+    assert torch.equal(dp_b, dp_f.bfloat16()), "the bf16 gradient must be the float32 one-pass gradient rounded once"
+    # the widen-in-place route (no sums handed over) gives the same forward results
+    monkeypatch.setenv("VAEMDL_BF16_WIDEN", "1")
+    out_w = F.modl_iwae_forward(pbd, xd, ed)
+    monkeypatch.delenv("VAEMDL_BF16_WIDEN")
+    assert torch.equal(out_b[0], out_w[0])
+    # float64 oracle
+    assert abs(out_b[3].item() + loss64.item()) <= LL_RTOL * abs(loss64.item())
+    assert relnorm(dp_b.float().cpu(), p64.grad) <= 2 * BF16_GRAD_RTOL
+    # the one-call step takes the same route
+    step = F.modl_iwae_step(pbd, xd, ed)
+    assert torch.equal(step[5], dp_b) and torch.equal(step[0], out_b[0])

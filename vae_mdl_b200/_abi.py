@@ -70,6 +70,11 @@ PROTOTYPES = {
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vaemdl_modl_iwae_fwd_stats_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_longlong, c_longlong, c_int,
+                                                c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vaemdl_modl_bwd_stats_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vaemdl_modl_plain_fwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int,
                                       c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vaemdl_modl_plain_iwae_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_longlong, c_longlong, c_int, c_int,

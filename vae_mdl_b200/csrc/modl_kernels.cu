@@ -80,6 +80,25 @@ extern "C" int vaemdl_modl_bwd_bf16(const void* params_bf16, const void* x, int 
                           g_image, g_pixel, static_cast<float*>(dparams_bf16), static_cast<cudaStream_t>(stream), 1);
 }
 
+// bfloat16 parameters with the per-pixel mixture sums handed from the forward to the backward call: the backward kernel then
+// keeps the tile in bfloat16 (two slots per warp, one-pass gradient rounded once).  pix_stats [n_img*H*W*2] float32.
+extern "C" int vaemdl_modl_iwae_fwd_stats_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                                               int S, long long B, long long B_total, int x_batch, int H, int W, int M,
+                                               const float* extra, float* ll_image, double* ll_image_f64, float* log_w,
+                                               float* lme_b, float* elbo, float* g_ll, float* pix_stats, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  return modl_iwae_fwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, S, B, B_total,
+                               x_batch, H, W, M, extra, ll_image, ll_image_f64, log_w, lme_b, elbo, g_ll, workspace,
+                               workspace_bytes, static_cast<cudaStream_t>(stream), 1, pix_stats);
+}
+
+extern "C" int vaemdl_modl_bwd_stats_bf16(const void* params_bf16, const void* x, int x_dtype, int x_range, int edge_mode,
+                                          long long n_img, int x_batch, int H, int W, int M, const float* g_image,
+                                          const float* g_pixel, const float* pix_stats, void* dparams_bf16, void* stream) {
+  return modl_bwd_impl<0>(static_cast<const float*>(params_bf16), x, x_dtype, x_range, edge_mode, n_img, x_batch, H, W, M,
+                          g_image, g_pixel, static_cast<float*>(dparams_bf16), static_cast<cudaStream_t>(stream), 1, pix_stats);
+}
+
 // ---- forward / backward as two calls that share the per-pixel mixture sums (what vaemdl_modl_iwae_step does inside) -----------
 extern "C" int vaemdl_modl_iwae_fwd_stats(const float* params, const void* x, int x_dtype, int x_range, int edge_mode, int S,
                                           long long B, long long B_total, int x_batch, int H, int W, int M,

@@ -73,7 +73,9 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   using T = Tile<MC, LPP>;
   a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
   const DeviceInfo& di = device_info();
-  const size_t per_warp = (static_cast<size_t>(NSLOT) * T::TILE_F + ((BWD && !ST) ? T::AUX_F : 0) + (ST ? 2 * T::PPT : 0)) * 4 + NSLOT * 8;
+  // (PD = 2: the slots hold bfloat16; ST with two slots: one (S, SW) strip per slot -- the layout of tile_body)
+  const size_t per_warp = (static_cast<size_t>(NSLOT) * (PD == 2 ? T::TILE_F / 2 : T::TILE_F) + ((BWD && !ST) ? T::AUX_F : 0) +
+                           (ST ? (NSLOT > 1 ? NSLOT : 1) * 2 * T::PPT : 0)) * 4 + NSLOT * 8;
   if (warps > MAXT / 32) warps = MAXT / 32;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
   warps = pick_warps(a.num_tiles, di.sm_count, warps);
@@ -111,6 +113,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
   if (a.partial && !partials_fit(a.n_px / a.HW, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   apply_l2_opt(a, total_warps, T::TILE_B / (PD ? 2 : 1));
+  if (PD == 2 && NSLOT > 1 && a.keep_tiles > 0 && a.keep_tiles < NSLOT) a.keep_tiles = NSLOT;
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -125,11 +128,25 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
 
 template <int MC, int LPP, bool BWD, int AR>
 static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
-  if (a.bf16) {  // bfloat16 parameters: x-conditioned class only, one slot per warp
-    if constexpr (AR == 0)
+  if (a.bf16) {  // bfloat16 parameters: x-conditioned class only
+    if constexpr (AR == 0) {
+      // Aligned component pairs (n_mix 10 / 20 / 30): the tile stays bfloat16 in shared memory, two slots per warp, pairs
+      // widened as they are read (PD = 2).  The backward pass takes that route when the forward pass left its per-pixel
+      // sums (one-pass gradient, rounded once); without them -- and for n_mix 5 -- the tile is widened in place (PD = 1).
+      static const bool direct_off = getenv("VAEMDL_BF16_WIDEN") != nullptr;  // A/B: always widen in place
+      if constexpr (Tile<MC, LPP>::ALIGNED) {
+        if (!direct_off) {
+          if constexpr (!BWD) return launch_tiled_shape<MC, LPP, false, 2, 512, 0, 2>(a, 16, st, plan);
+          if constexpr (BWD) {
+            if (a.pix_stats) return launch_tiled_shape<MC, LPP, true, 2, 512, 0, 2, true>(a, 16, st, plan);
+          }
+        }
+      }
+      a.pix_stats = nullptr;
       return launch_tiled_shape<MC, LPP, BWD, 1, 512, 0, 1>(a, tune_shape(BWD, Shape{1, 16}).warps, st, plan);
-    else
+    } else {
       return VAEMDL_EUNSUPPORTED;
+    }
   }
   // 1 slot x 16 warps: measured best on B200 for every M (profiles/r01_tune_shapes.txt); latency is hidden by the 4
   // warps per scheduler rather than by a second slot per warp
@@ -432,7 +449,8 @@ static bool stats_off() {
   return getenv("VAEMDL_NO_STATS") != nullptr || (e && e[0] == 'n');
 }
 static bool stats_supported(int M, long long n_px, bool bf16) {
-  if (stats_off() || bf16 || use_pixel_pairs(M, n_px, bf16)) return false;
+  if (stats_off() || use_pixel_pairs(M, n_px, bf16)) return false;
+  if (bf16) return (M == 10 || M == 20 || M == 30) && getenv("VAEMDL_BF16_WIDEN") == nullptr;  // the direct bf16 backward pass needs them
   const char* e = getenv("VAEMDL_STATS");
   if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
   return M == 5 || M == 30;

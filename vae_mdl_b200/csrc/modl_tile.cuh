@@ -55,6 +55,31 @@ __device__ __forceinline__ void st_pair(float* row, int off, bool single, f2 v) 
   }
 }
 
+// A component pair of a row that holds bfloat16 values (PD = 2): the two neighbours share one aligned 32-bit word (the
+// pair index is even); widening is a shift and a mask, narrowing one cvt.rn.bf16x2.f32.
+__device__ __forceinline__ f2 ld_pair_bf16(const float* row_as_bf16, int off) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned short*>(row_as_bf16) + off);
+  return pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ void st_pair_bf16(float* row_as_bf16, int off, f2 v) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo(v), hi(v));  // .x = low half-word = the lower index
+  *reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned short*>(row_as_bf16) + off) = *reinterpret_cast<const uint32_t*>(&b);
+}
+template <bool ALIGNED, bool DIRECT>
+__device__ __forceinline__ f2 ld_row(const float* row, int off, bool single) {
+  if constexpr (DIRECT)
+    return ld_pair_bf16(row, off);
+  else
+    return ld_pair<ALIGNED>(row, off, single);
+}
+template <bool ALIGNED, bool DIRECT>
+__device__ __forceinline__ void st_row(float* row, int off, bool single, f2 v) {
+  if constexpr (DIRECT)
+    st_pair_bf16(row, off, v);
+  else
+    st_pair<ALIGNED>(row, off, single, v);
+}
+
 struct PixRaw {
   unsigned v[3];
 };
@@ -91,6 +116,10 @@ __device__ __forceinline__ void decode_pixel(const ModlArgs& a, const PixRaw& r,
 // the backward shared-memory layout, the mbarrier is initialised once and its phase carries over, the forward pass
 // leaves its last tile in the slot and the (reversed) backward pass starts on it without loading anything.
 // PD = 1: bfloat16 parameters / gradient in global memory (widened / narrowed in place in the slot, see widen_bf16_inplace)
+// PD = 2: bfloat16 parameters / gradient that STAY bfloat16 in the slot (half the shared memory: two slots per warp, the next
+//         tile lands while this one is processed); every component pair is widened as it is read and the final gradient
+//         narrowed as it is written, one rounding.  Needs 4-byte aligned pairs (T::ALIGNED) and, backward, the forward
+//         pass's per-pixel sums (ST): unscaled derivatives must never be rounded to bfloat16.
 // ST: the backward pass takes every pixel's mixture sums from a.pix_stats (written by the forward pass of the same step)
 // instead of forming them itself: the gradient of a component is scaled as soon as it is computed -- one pass over the
 // row, no aux strip.  (The forward body of a FUSED step is instantiated with the same ST: both share the slot layout.)
@@ -101,12 +130,16 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   constexpr bool AL = T::ALIGNED;
   // ST: instead of the aux strip the slot is followed by the tile's (S, SW) pairs, which travel with the tile (bulk copy)
   constexpr int STAT_F = 2 * PPT;
-  constexpr int WARP_F = NSLOT * TILE_F + (((BWD || FUSED) && !ST) ? T::AUX_F : 0) + (ST ? STAT_F : 0);
+  constexpr bool DIRECT = PD == 2;
+  constexpr int SLOT_F = DIRECT ? TILE_F / 2 : TILE_F;            // floats of shared memory per slot
+  constexpr int NSTAT = (ST && NSLOT > 1) ? NSLOT : 1;            // one (S, SW) strip per slot in flight
+  constexpr int WARP_F = NSLOT * SLOT_F + (((BWD || FUSED) && !ST) ? T::AUX_F : 0) + (ST ? NSTAT * STAT_F : 0);
   static_assert(!FUSED || NSLOT == 1, "the fused step keeps one slot per warp");
-  static_assert(PD == 0 || (NSLOT == 1 && !FUSED), "bf16 parameters: one slot per warp, three-launch step");
+  static_assert(PD != 1 || (NSLOT == 1 && !FUSED), "widened bf16 parameters: one slot per warp, three-launch step");
+  static_assert(!DIRECT || (AL && !FUSED && (!BWD || ST)), "direct bf16: aligned pairs, no unscaled derivatives in bf16");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   float* slots = reinterpret_cast<float*>(smem_raw) + static_cast<size_t>(warp) * WARP_F;
-  float* aux = slots + NSLOT * TILE_F;   // (ST: the tile's (S, SW) pairs live here)
+  float* aux = slots + NSLOT * SLOT_F;   // (ST: the tiles' (S, SW) pairs live here, one strip per slot)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(nwarps) * WARP_F * 4) + warp * NSLOT;
 
   if constexpr (!(FUSED && BWD)) {
@@ -158,13 +191,14 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const int rows = tile_rows(t);
     const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
     const char* src = reinterpret_cast<const char*>(a.params) + t * TILE_F * (PD ? 2 : 4);
-    float* slot_f = slots + s * TILE_F;
-    char* dst = reinterpret_cast<char*>(slot_f) + (PD ? bytes : 0u);  // bf16 lands behind the room its float32 image needs
+    float* slot_f = slots + s * SLOT_F;
+    char* dst = reinterpret_cast<char*>(slot_f) + (PD == 1 ? bytes : 0u);  // (PD = 1: bf16 lands behind the room its float32 image needs)
+    [[maybe_unused]] float* stat_s = aux + (NSTAT > 1 ? s * STAT_F : 0);
     [[maybe_unused]] const uint32_t sbytes = static_cast<uint32_t>(rows) * 8u;  // the tile's (S, SW) pairs (BWD && ST)
     if ((bytes & 15u) == 0 && (!(BWD && ST) || (sbytes & 15u) == 0)) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&bars[s], bytes + ((BWD && ST) ? sbytes : 0u));
-        if constexpr (BWD && ST) bulk_g2s(aux, a.pix_stats + t * PPT, sbytes, &bars[s]);
+        if constexpr (BWD && ST) bulk_g2s(stat_s, a.pix_stats + t * PPT, sbytes, &bars[s]);
         if (BWD) {
           if (a.bwd_hint & 1)
             bulk_g2s_hint(dst, src, bytes, &bars[s], pol_first);
@@ -178,10 +212,14 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
       }
     } else {
-      for (int i = lane; i < rows * ROWF; i += 32)
-        slot_f[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+      for (int i = lane; i < rows * ROWF; i += 32) {
+        if constexpr (DIRECT)
+          reinterpret_cast<unsigned short*>(slot_f)[i] = reinterpret_cast<const unsigned short*>(src)[i];
+        else
+          slot_f[i] = PD ? bf16_bits_to_f32(reinterpret_cast<const unsigned short*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+      }
       if constexpr (BWD && ST) {
-        if (lane < rows) reinterpret_cast<float2*>(aux)[lane] = a.pix_stats[t * PPT + lane];
+        if (lane < rows) reinterpret_cast<float2*>(stat_s)[lane] = a.pix_stats[t * PPT + lane];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_expect_tx(&bars[s], 0);
@@ -281,9 +319,11 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     // (LATE_G: the first iteration's look-ahead reads the upstream gradient too, so it waits until after griddepcontrol.wait)
     if (it + 1 < t_cnt && !(LATE_G && it == 0)) fetch(t + t_dir, n_own, pix_own, n_cur, nfirst_cur, raw_cur, g_cur, st_cur);
 
-    float* slot = slots + s * TILE_F;
-    float* rowp = slot + pp * ROWF;
+    float* slot = slots + s * SLOT_F;
+    // (DIRECT: the row holds ROWF bfloat16 values; rowp is only ever handed to ld_row / st_row)
+    float* rowp = DIRECT ? reinterpret_cast<float*>(reinterpret_cast<unsigned short*>(slot) + pp * ROWF) : slot + pp * ROWF;
     float* auxp = aux + pp * M;
+    [[maybe_unused]] float* stat_cur = aux + (NSTAT > 1 ? s * STAT_F : 0);
     if (!(FUSED && BWD && it == 0)) mbar_wait(&bars[s], parity);
     if constexpr (FUSED && BWD && ST) {
       if (it == 0) {  // the resident tile was not loaded by this pass: fetch its (S, SW) pairs by hand
@@ -291,7 +331,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         __syncwarp();
       }
     }
-    if constexpr (PD != 0) {
+    if constexpr (PD == 1) {
       if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);  // (a ragged tile was widened by its loads)
     }
     if constexpr (BWD && NSLOT > 1) {
@@ -311,8 +351,8 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
 #pragma unroll
       for (int pr = 0; pr < NPAIR; ++pr) {
         const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
-        const float2 t = *reinterpret_cast<const float2*>(rowp + m0 + 2 * prr);
-        lmax = fmaxf(lmax, fmaxf(t.x, t.y));
+        const f2 t = ld_row<AL, DIRECT>(rowp, m0 + 2 * prr, false);
+        lmax = fmaxf(lmax, fmaxf(lo(t), hi(t)));
       }
     } else {
       lmax = rowp[m0];
@@ -325,7 +365,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     [[maybe_unused]] float st_rS = 0.f, st_rSW = 0.f, st_lt = 0.f, st_ll = 0.f;
     [[maybe_unused]] bool st_tiny = false;
     if constexpr (BWD && ST) {
-      const float2 stp = reinterpret_cast<const float2*>(aux)[pp];  // arrived with the tile
+      const float2 stp = reinterpret_cast<const float2*>(stat_cur)[pp];  // arrived with the tile
       (void)st;
       st_rS = rcpa(stp.x);
       st_rSW = rcpa(stp.y);
@@ -338,14 +378,14 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
       const int m = m0 + 2 * prr;
       const bool single = (MC % 2 == 1) && (prr == NPAIR - 1);
-      f2 lg = ld_pair<AL>(rowp, m, single);
+      f2 lg = ld_row<AL, DIRECT>(rowp, m, single);
       if (single) lg = pk(lo(lg), -INFINITY);  // the padding half gets zero weight
       f2 mu[3], sc[3], kp[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        mu[c] = ld_pair<AL>(rowp, (1 + 3 * c) * M + m, single);
-        sc[c] = ld_pair<AL>(rowp, (2 + 3 * c) * M + m, single);
-        kp[c] = ld_pair<AL>(rowp, (3 + 3 * c) * M + m, single);
+        mu[c] = ld_row<AL, DIRECT>(rowp, (1 + 3 * c) * M + m, single);
+        sc[c] = ld_row<AL, DIRECT>(rowp, (2 + 3 * c) * M + m, single);
+        kp[c] = ld_row<AL, DIRECT>(rowp, (3 + 3 * c) * M + m, single);
       }
       const float smin = fminf(fminf(fminf(lo(sc[0]), hi(sc[0])), fminf(lo(sc[1]), hi(sc[1]))), fminf(lo(sc[2]), hi(sc[2])));
       const bool narrow = __any_sync(kFull, smin < (AR ? a.ls_narrow : kLsNarrow));
@@ -367,9 +407,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
         }
         const f2 gr = r * g;
         if (active) {  // final gradients overwrite the component's parameters in place
-          st_pair<AL>(rowp, m, single, (r - pi) * g);
+          st_row<AL, DIRECT>(rowp, m, single, (r - pi) * g);
 #pragma unroll
-          for (int j = 0; j < 9; ++j) st_pair<AL>(rowp, (1 + j) * M + m, single, u[j] * gr);
+          for (int j = 0; j < 9; ++j) st_row<AL, DIRECT>(rowp, (1 + j) * M + m, single, u[j] * gr);
         }
       } else {
       sumW2 = sumW2 + W;
@@ -399,7 +439,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     const float* grow = param_row(a, i, ROWF);
 
     if constexpr (!BWD) {
-      if constexpr (PD != 0) fence_async_smem();  // the widening wrote the slot through the generic proxy
+      if constexpr (PD == 1) fence_async_smem();  // the widening wrote the slot through the generic proxy
       __syncwarp();
       {  // every lane has read its row: re-arm the slot for this warp's tile NSLOT iterations ahead
         if (it + NSLOT < t_cnt) issue(t + NSLOT * t_dir, s);
@@ -470,7 +510,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       const uint32_t bytes = static_cast<uint32_t>(rows) * ROWF * (PD ? 2u : 4u);
       char* dst = reinterpret_cast<char*>(a.dparams) + t * TILE_F * (PD ? 2 : 4);
       if ((bytes & 15u) == 0) {
-        if constexpr (PD != 0) {
+        if constexpr (PD == 1) {
           __syncwarp();
           narrow_bf16_inplace(slot, rows * ROWF, lane);
         }
@@ -486,7 +526,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
       } else {
         __syncwarp();
         for (int q = lane; q < rows * ROWF; q += 32) {
-          if (PD)
+          if constexpr (DIRECT)
+            reinterpret_cast<unsigned short*>(dst)[q] = reinterpret_cast<const unsigned short*>(slot)[q];
+          else if (PD)
             reinterpret_cast<unsigned short*>(dst)[q] = f32_to_bf16_bits(slot[q]);
           else
             reinterpret_cast<float*>(dst)[q] = slot[q];

@@ -150,11 +150,12 @@ def modl_backward(params: torch.Tensor, x: torch.Tensor, g_image: Optional[torch
         if plain:
             check(lib().vaemdl_modl_plain_bwd(ptr(p), ptr(xd), x_dtype, n_img, x_batch, H, W, C10 // 10, *_bins(plain), ptr(gi),
                                               ptr(gp), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_plain_bwd")
-        elif pix_stats is not None and not bf16:
-            # the per-pixel mixture sums of the forward call on the same parameters: one-pass gradient kernel
-            check(lib().vaemdl_modl_bwd_stats(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
-                                              ptr(gi), ptr(gp), ptr(pix_stats), ptr(dp), stream_ptr(p.device)),
-                  "vaemdl_modl_bwd_stats")
+        elif pix_stats is not None:
+            # the per-pixel mixture sums of the forward call on the same parameters: one-pass gradient kernel (bfloat16
+            # parameters: the tile then stays bfloat16 in shared memory, two slots per warp, gradient rounded once)
+            fn = lib().vaemdl_modl_bwd_stats_bf16 if bf16 else lib().vaemdl_modl_bwd_stats
+            check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
+                     ptr(gi), ptr(gp), ptr(pix_stats), ptr(dp), stream_ptr(p.device)), "vaemdl_modl_bwd_stats")
         else:
             fn = lib().vaemdl_modl_bwd_bf16 if bf16 else lib().vaemdl_modl_bwd
             check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, n_img, x_batch, H, W, C10 // 10,
@@ -197,13 +198,13 @@ def modl_iwae_forward(params: torch.Tensor, x: torch.Tensor, extra: Optional[tor
                                                ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo), ptr(g_ll), ptr(ws), ws_bytes,
                                                stream_ptr(dev)), "vaemdl_modl_plain_iwae_fwd")
         else:
-            if want_stats and not bf16:
+            if want_stats:
                 # leaves every pixel's (mixture sum, logit normaliser) for modl_backward(pix_stats=...): one-pass gradient
                 stats = torch.empty((S, B, H, W, 2), device=dev, dtype=torch.float32)
-                check(L.vaemdl_modl_iwae_fwd_stats(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch,
-                                                   H, W, M, ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo),
-                                                   ptr(g_ll), ptr(stats), ptr(ws), ws_bytes, stream_ptr(dev)),
-                      "vaemdl_modl_iwae_fwd_stats")
+                fn = L.vaemdl_modl_iwae_fwd_stats_bf16 if bf16 else L.vaemdl_modl_iwae_fwd_stats
+                check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch,
+                         H, W, M, ptr(ex), None, ptr(ll64), ptr(log_w), ptr(lme_b), ptr(elbo),
+                         ptr(g_ll), ptr(stats), ptr(ws), ws_bytes, stream_ptr(dev)), "vaemdl_modl_iwae_fwd_stats")
                 return ll64, log_w, lme_b, elbo, g_ll, stats
             fn = L.vaemdl_modl_iwae_fwd_bf16 if bf16 else L.vaemdl_modl_iwae_fwd
             check(fn(ptr(p), ptr(xd), x_dtype, x_range, edge_mode, S, B, int(b_total), x_batch, H, W, M,
@@ -220,8 +221,12 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     for the training shapes of models/model05.py, three launches otherwise.  Arguments as ``modl_iwae_forward``.
     Returns ``(lpxz float64 [S,B], log_w, lme_b [B], elbo [1], g_ll [S,B], dparams, launches)``."""
     if params.dtype == torch.bfloat16:  # bfloat16 parameters: forward + finish, then the gradient kernel (3 launches)
-        ll64, log_w, lme_b, elbo, g_ll = modl_iwae_forward(params, x, extra, b_total, x_range, edge_mode, plain)
-        return ll64, log_w, lme_b, elbo, g_ll, modl_backward(params, x, g_image=g_ll, x_range=x_range, edge_mode=edge_mode), 3
+        # n_mix 10 / 20 / 30: the forward kernel leaves the per-pixel sums and the gradient kernel keeps the tile in bfloat16
+        want = (not plain) and params.shape[-1] in (100, 200, 300)
+        out = modl_iwae_forward(params, x, extra, b_total, x_range, edge_mode, plain, want_stats=want)
+        ll64, log_w, lme_b, elbo, g_ll = out[:5]
+        dp = modl_backward(params, x, g_image=g_ll, x_range=x_range, edge_mode=edge_mode, pix_stats=out[5] if want else None)
+        return ll64, log_w, lme_b, elbo, g_ll, dp, 3
     p = dense_f32(params, "parameters")
     if p.dim() != 5:
         raise ValueError("parameters must be [S, B, H, W, 10*n_mix]")
@@ -736,7 +741,8 @@ class _FusedIwaeFn(torch.autograd.Function):
         if kind == "modl":
             # n_mix 5 / 30: the forward kernel leaves the per-pixel mixture sums for a one-pass gradient kernel (the
             # library ignores them for any other n_mix, so they are not even allocated then)
-            want = bool(ctx.needs_input_grad[5]) and p0.shape[-1] in (50, 300) and not meta["plain"]
+            stat_widths = (100, 200, 300) if p0.dtype == torch.bfloat16 else (50, 300)
+            want = bool(ctx.needs_input_grad[5]) and p0.shape[-1] in stat_widths and not meta["plain"]
             out = modl_iwae_forward(p0, x, extra, 0, meta["x_range"], meta["edge_mode"], meta["plain"], want_stats=want)
             ll64, log_w, lme_b, elbo, g_ll = out[:5]
             stats = out[5] if want else None
