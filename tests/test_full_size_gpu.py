@@ -190,6 +190,10 @@ def test_config1_one_launch_step_full_size(F, V, monkeypatch, S, B, M):
     x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
     extra = torch.randn(S, B, device=DEV, generator=gen) * 3
     monkeypatch.delenv("VAEMDL_FUSED", raising=False)
+    default = F.modl_iwae_step(params, x_u8, extra)
+    # n_mix 10: the cooperative kernel is the default; n_mix 5: three launches on two 6.4 KB slots per warp are faster
+    assert default[-1] == (1 if M == 10 else 3)
+    monkeypatch.setenv("VAEMDL_FUSED", "1")
     a = F.modl_iwae_step(params, x_u8, extra)
     assert a[-1] == 1
     monkeypatch.setenv("VAEMDL_FUSED", "0")
@@ -199,6 +203,7 @@ def test_config1_one_launch_step_full_size(F, V, monkeypatch, S, B, M):
         assert torch.equal(u, v)
     if M == 5:      # both routes hand the per-pixel mixture sums from the forward to the backward pass: same arithmetic
         assert torch.equal(a[5], b[5])
+        assert torch.equal(default[5], b[5]) and torch.equal(default[0], b[0])
     else:           # n_mix 10 as three launches keeps the two-pass gradient kernel: round-off apart
         assert relnorm(a[5], b[5]) <= 2e-6
     assert abs(a[3].item() - b[3].item()) <= 1e-6 * abs(b[3].item())

@@ -63,6 +63,16 @@ static void apply_l2_opt(ModlArgs& a, long long total_warps, long long tile_byte
   if (opt.keep_mb > 0 && a.keep_tiles < 1) a.keep_tiles = 1;
 }
 
+// n_mix 5, x-conditioned class, float32: a 32-row tile is 6.4 KB, so TWO slots per warp fit next to 16 warps (as for bfloat16
+// tiles of n_mix 10): the next tile lands while this one is processed.  Measured on B200 (tools/ab_m5.sh, profiles/r02n):
+// at 16 x 64 x 64 x 64 the one-pass gradient on two slots takes 287 us (pixel-pair kernel: 312 us, one slot: 307 us) while the
+// forward pass stays on the pixel-pair kernel (153 vs 177 us: the 32-row tile evaluates 6 component slots for 5 components);
+// at 5 x 128 x 32 x 32 three launches on two slots (93.5 us) beat the one-launch step (99.1 us).  VAEMDL_M5_SLOTS=1: one slot.
+static bool m5_two_slots() {
+  static const bool two = [] { const char* e = getenv("VAEMDL_M5_SLOTS"); return !(e && e[0] == '1'); }();
+  return two;
+}
+
 struct TilePlan {  // how the forward grid split the tile range: what the per-image reduction needs to know
   long long total_warps = 0, tw_base = 0, tw_rem = 0;
   int K = 0, PPT = 0;
@@ -152,6 +162,17 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   // warps per scheduler rather than by a second slot per warp
   const Shape sh = tune_shape(BWD, Shape{1, 16});
   if (AR == 0 && sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256, 0>(a, sh.warps, st, plan);  // tuning only
+  if constexpr (MC == 5 && LPP == 1 && AR == 0) {
+    // n_mix 5: two 6.4 KB slots per warp (m5_two_slots)
+    if (m5_two_slots()) {
+      if constexpr (BWD) {
+        if (a.pix_stats) return launch_tiled_shape<5, 1, true, 2, 512, 0, 0, true>(a, 16, st, plan);
+        return launch_tiled_shape<5, 1, true, 2, 512, 0>(a, 16, st, plan);
+      } else {
+        return launch_tiled_shape<5, 1, false, 2, 512, 0>(a, 16, st, plan);
+      }
+    }
+  }
   if constexpr (BWD) {
     if (a.pix_stats) return launch_tiled_shape<MC, LPP, true, 1, 512, AR, 0, true>(a, sh.warps, st, plan);  // one-pass gradient
   }
@@ -448,8 +469,10 @@ static bool stats_off() {
   const char* e = getenv("VAEMDL_STATS");
   return getenv("VAEMDL_NO_STATS") != nullptr || (e && e[0] == 'n');
 }
-static bool stats_supported(int M, long long n_px, bool bf16) {
-  if (stats_off() || use_pixel_pairs(M, n_px, bf16)) return false;
+static bool stats_supported(int M, long long n_px, bool bf16, int AR = 0) {
+  if (stats_off()) return false;
+  if (M == 5 && !bf16 && AR == 0 && m5_two_slots()) return true;  // pixel-pair forward writes them, two-slot tile backward reads them
+  if (use_pixel_pairs(M, n_px, bf16)) return false;
   if (bf16) return (M == 10 || M == 20 || M == 30) && getenv("VAEMDL_BF16_WIDEN") == nullptr;  // the direct bf16 backward pass needs them
   const char* e = getenv("VAEMDL_STATS");
   if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
@@ -461,8 +484,10 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   a.plain = AR;
   a.spread = spread_runs();
   a.pair_rot = pair_rot_on(a.M);
-  if (!stats_supported(a.M, a.n_px, a.bf16 != 0)) a.pix_stats = nullptr;
-  if (use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
+  if (!stats_supported(a.M, a.n_px, a.bf16 != 0, AR)) a.pix_stats = nullptr;
+  // n_mix 5 with the forward pass's sums at hand: the one-pass gradient on the two-slot 32-row tile, whatever the size
+  const bool m5_tile_bwd = BWD && AR == 0 && a.M == 5 && !a.bf16 && a.pix_stats && m5_two_slots();
+  if (!m5_tile_bwd && use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
     switch (a.M) {
       case 1: return launch_pp<1, BWD, AR>(a, st, plan);
       case 2: return launch_pp<2, BWD, AR>(a, st, plan);
@@ -681,7 +706,7 @@ static int fused_mode() {
   if (!e) return -1;
   return e[0] == '0' ? 0 : 1;
 }
-static bool fused_eligible(int S, long long n_px, int HW, int M) {
+static bool fused_eligible(int S, long long n_px, int HW, int M, int AR = 0) {
   const int mode = fused_mode();
   if (mode == 0 || S > 32) return false;
   if (use_pixel_pairs(M, n_px)) return false;
@@ -697,6 +722,7 @@ static bool fused_eligible(int S, long long n_px, int HW, int M) {
   }
   if (!coop) return false;
   if (mode == 1) return true;
+  if (M == 5 && AR == 0 && m5_two_slots()) return false;  // three launches on two slots per warp are faster (see m5_two_slots)
   const long long tiles = (n_px + ppt - 1) / ppt;
   return tiles <= kFusedMaxTilesPerWarp * device_info().sm_count * 16;
 }
@@ -723,9 +749,9 @@ static int modl_iwae_step_impl(const float* params, const void* x, int x_dtype, 
   // per-pixel mixture sums handed from the forward to the backward pass (one-pass gradient): behind the forward
   // workspace, when the caller sized the buffer with vaemdl_modl_step_workspace_bytes and the kernels support it
   const bool room = workspace_bytes >= need + static_cast<size_t>(n_px) * sizeof(float2);
-  const bool fused = room && !stats_off() && fused_eligible(S, n_px, HW, M);  // (implies n_mix in {5, 10, 20, 30})
+  const bool fused = room && !stats_off() && fused_eligible(S, n_px, HW, M, AR);  // (implies n_mix in {5, 10, 20, 30})
   float* stats = nullptr;
-  if (room && (fused || stats_supported(M, n_px, false))) stats = reinterpret_cast<float*>(ws + need);
+  if (room && (fused || stats_supported(M, n_px, false, AR))) stats = reinterpret_cast<float*>(ws + need);
   if (!fused) {
     if (launches) *launches = 3;
     rc = modl_iwae_fwd_impl<AR>(params, x, x_dtype, x_range, edge_mode, S, B, B_total, x_batch, H, W, M, extra, ll_image,

@@ -263,6 +263,10 @@ __global__ void __launch_bounds__(MAXT, 1) modl_pp_kernel(const ModlArgs a) {
         if (actA) a.lp_pixel[iA] = lpA;
         if (actB) a.lp_pixel[iB] = lpB;
       }
+      if (a.pix_stats) {  // (mixture sum, logit normaliser) per pixel-sample for a one-pass gradient kernel
+        if (actA) a.pix_stats[iA] = make_float2(lo(sumWP), lo(sumW));
+        if (actB) a.pix_stats[iB] = make_float2(hi(sumWP), hi(sumW));
+      }
       const float valA = actA ? lpA : 0.0f, valB = actB ? lpB : 0.0f;
       if (a.partial) {
         // a tile holds pixels of at most two images (HW >= 64 on this route): n_first and n_first + 1
