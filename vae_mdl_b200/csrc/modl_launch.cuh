@@ -161,7 +161,7 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   // 1 slot x 16 warps: measured best on B200 for every M (profiles/r01_tune_shapes.txt); latency is hidden by the 4
   // warps per scheduler rather than by a second slot per warp
   const Shape sh = tune_shape(BWD, Shape{1, 16});
-  if (AR == 0 && sh.slots == 2) return launch_tiled_shape<MC, LPP, BWD, 2, 256, 0>(a, sh.warps, st, plan);  // tuning only
+  // (2 slots x <= 8 warps was 20-30 % behind at every n_mix, profiles/r01_tune_shapes.txt: that instantiation is gone)
   if constexpr (MC == 5 && LPP == 1 && AR == 0) {
     // n_mix 5: two 6.4 KB slots per warp (m5_two_slots)
     if (m5_two_slots()) {
@@ -452,7 +452,7 @@ static int pair_rot_on(int M) {
     return !e ? -1 : (e[0] == '0' ? 0 : 1);
   }();
   if (forced >= 0) return forced;
-  return M == 30;
+  return M == 30 || M == 16 || M == 32;  // (16 / 32: rows of 160 / 320 words all start in bank 0 -- without it 32 % / 57 % backward)
 }
 
 static int spread_runs() {
@@ -473,7 +473,8 @@ static bool stats_supported(int M, long long n_px, bool bf16, int AR = 0) {
   if (stats_off()) return false;
   if (M == 5 && !bf16 && AR == 0 && m5_two_slots()) return true;  // pixel-pair forward writes them, two-slot tile backward reads them
   if (use_pixel_pairs(M, n_px, bf16)) return false;
-  if (bf16) return (M == 10 || M == 20 || M == 30) && getenv("VAEMDL_BF16_WIDEN") == nullptr;  // the direct bf16 backward pass needs them
+  if (bf16)  // the direct bf16 backward pass (aligned tile instantiations) needs them
+    return (M == 10 || M == 16 || M == 20 || M == 30 || M == 32 || M == 40) && getenv("VAEMDL_BF16_WIDEN") == nullptr;
   const char* e = getenv("VAEMDL_STATS");
   if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
   return M == 5 || M == 30;
@@ -505,10 +506,16 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
       return launch_tiled<5, 1, BWD, AR>(a, st, plan);
     case 10:
       return launch_tiled<10, 1, BWD, AR>(a, st, plan);
+    case 16:  // (r01: 67 % / 66 % of the HBM roofline on the run-time tiled kernel)
+      return launch_tiled<8, 2, BWD, AR>(a, st, plan);
     case 20:
       return launch_tiled<10, 2, BWD, AR>(a, st, plan);
     case 30:
       return launch_tiled<10, 3, BWD, AR>(a, st, plan);
+    case 32:  // (r01: 69 % / 70 %)
+      return launch_tiled<8, 4, BWD, AR>(a, st, plan);
+    case 40:  // (r01: 72 % / 68 %)
+      return launch_tiled<10, 4, BWD, AR>(a, st, plan);
     default: {
       static const bool force_generic = getenv("VAEMDL_GENERIC") != nullptr;  // A/B against the one-thread-per-pixel kernel
       if (!force_generic) return launch_rt<BWD, AR>(a, st, plan);
@@ -529,10 +536,14 @@ static int tile_ppt(int M, long long n_px, bool bf16 = false) {
     case 5:
     case 10:
       return 32;
+    case 16:
     case 20:
       return 16;
     case 30:
       return 10;
+    case 32:
+    case 40:
+      return 8;
     default:
       if (getenv("VAEMDL_GENERIC")) return 0;  // one-thread-per-pixel kernel: atomics
       return rt_plan(M, false, bf16).PPT;

@@ -26,6 +26,9 @@ struct Tile {
   // (modl_launch.cuh): the shared-memory pipe is not what limits these kernels.
   __device__ static __forceinline__ int pair_rot(int lane) {
     if constexpr (!ALIGNED) return 0;
+    // rows that are a multiple of 32 words long (n_mix 16, 32) all start in the same bank: 8- / 16-way conflicts in row order;
+    // pixel p starts at pair p, which leaves the two-way conflict the other tile shapes live with (or none, 4 lanes per pixel)
+    if constexpr (ROWF % 32 == 0) return (lane / LPP) % NPAIR;
     if constexpr (LPP == 1) return (lane >> 3) & 1;
     if constexpr (LPP == 2) return ((lane >> 3) & 1) * 2;
     if constexpr (LPP == 3) return (3 * (lane / 3)) % NPAIR;
