@@ -48,6 +48,8 @@ WORKLOADS = {
     "cfg1_m5": ("modl", 5, 128, 32, 32, 5),
     "cfg5_64_m5": ("modl", 16, 64, 64, 64, 5),
     "cfg5_64_m20": ("modl", 16, 32, 64, 64, 20),
+    "cfg1_m20": ("modl", 5, 64, 32, 32, 20),
+    "cfg1_m30": ("modl", 5, 64, 32, 32, 30),
 }
 DEFAULT_WORKLOAD = "cfg5_64_m10"
 L2_BYTES = 126 * 1024 * 1024

@@ -709,9 +709,11 @@ static int modl_iwae_fwd_impl(const float* params, const void* x, int x_dtype, i
 }  // namespace vaemdl
 
 namespace vaemdl {
-// VAEMDL_FUSED = "0": never, "1": whenever the shape is eligible, unset: eligible shapes with at most kFusedMaxTilesPerWarp
-// tiles per warp (where launch boundaries and pipeline ramps are a visible share of the step)
-constexpr long long kFusedMaxTilesPerWarp = 12;  // measured: 101.6 -> 96.6 us at 4.3 tiles per warp, a loss from ~25 on
+// VAEMDL_FUSED = "1": the one-launch cooperative step (modl_step_kernel) whenever the shape is eligible; otherwise three
+// launches.  Round 1 took the one-launch step for small training shapes (101.6 -> 96.6 us at BASELINE configs[0]).  Since the
+// gradient kernel forms its first tile's derivatives while the finish kernel runs (tile_body LATE_G) the three launches are
+// AHEAD at every shape measured (5 x 64 x 32 x 32: n_mix 10 92.5 vs 96.6 us, n_mix 20 154 vs 167 us, n_mix 30 235 vs 234 us;
+// n_mix 5 x batch 128 on two slots per warp 93.2 vs 99.1 us), so the cooperative kernel is now opt-in.
 static int fused_mode() {
   const char* e = getenv("VAEMDL_FUSED");
   if (!e) return -1;
@@ -732,10 +734,8 @@ static bool fused_eligible(int S, long long n_px, int HW, int M, int AR = 0) {
     coop = v;
   }
   if (!coop) return false;
-  if (mode == 1) return true;
-  if (M == 5 && AR == 0 && m5_two_slots()) return false;  // three launches on two slots per warp are faster (see m5_two_slots)
-  const long long tiles = (n_px + ppt - 1) / ppt;
-  return tiles <= kFusedMaxTilesPerWarp * device_info().sm_count * 16;
+  (void)AR;
+  return mode == 1;
 }
 
 // One IWAE step of the observation model: forward, per-image sums, log-mean-exp, elbo, softmax weights, parameter gradient.
