@@ -190,7 +190,7 @@ def test_one_launch_dl_step_equals_three_launch_step(built_lib, monkeypatch, S, 
         loc, ls = bd[..., :3].contiguous(), bd[..., 3:].contiguous()
     xd = x_u8.to(DEV) if u8 else (x_u8.float() / 255.0).to(DEV)
     ed = extra.float().to(DEV)
-    monkeypatch.delenv("VAEMDL_FUSED", raising=False)
+    monkeypatch.setenv("VAEMDL_FUSED", "1")
     a = F.dlogistic_iwae_step(loc, ls, xd, ed, 0.0, 1.0, 256.0)
     torch.cuda.synchronize()
     assert a[-1] == 1, "the one-launch kernel was not taken"

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(256, 3) dl_pair_kernel(const DlArgs a) {
   const long long gw = static_cast<long long>(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const int lane = threadIdx.x & 31;
   if (!BWD && a.zero_me && blockIdx.x == 0 && threadIdx.x == 0) *a.zero_me = 0u;
+  if constexpr (!BWD) pdl_trigger();  // the finish kernel's launch may overlap this kernel (it waits for it to complete)
   const long long t_begin = gw * a.tw_base + (gw < a.tw_rem ? gw : a.tw_rem);
   const long long t_end = t_begin + a.tw_base + (gw < a.tw_rem ? 1 : 0);
   if (t_begin >= t_end) return;
@@ -442,7 +443,12 @@ __global__ void __launch_bounds__(256, 3) dl_pair_kernel(const DlArgs a) {
       } else if (a.ll_atomic && active) {
         atomicAdd(a.ll_atomic + n, static_cast<double>(val));
       }
-    } else if (active) {
+    } else {
+      // The upstream gradient is only needed here, after the tile's derivatives have been formed: a gradient kernel
+      // launched programmatically behind the finish kernel loads and evaluates its first tile while that kernel still runs.
+      if (t == t_begin) pdl_wait();
+    }
+    if (BWD && active) {
       const float g = a.g_image ? a.g_image[n] : 0.0f;
       f2 ge[3] = {sp(g), sp(g), sp(g)};
       if (a.g_elem) {
@@ -744,6 +750,10 @@ static int dl_launch(DlArgs a, int cpt, int kind, cudaStream_t st, PartialGeom* 
   if (a.partial && !partials_fit(a.n_rows / a.rows_per_img, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
   if (geom) *geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, TR, a.rows_per_img};
   const unsigned grid = static_cast<unsigned>(blocks);
+  if (BWD && kind) {  // programmatic launch: the kernel's prologue and first tile overlap the finish kernel (see dl_pair_kernel)
+    void (*kern)(DlArgs) = kind == 1 ? dl_pair_kernel<BWD, true> : dl_pair_kernel<BWD, false>;
+    return cuda_rc(launch_pdl(kern, grid, 256u, 0, st, a));
+  }
   if (kind == 1)
     dl_pair_kernel<BWD, true><<<grid, 256, 0, st>>>(a);
   else if (kind == 2)
@@ -865,8 +875,10 @@ namespace vaemdl {
 constexpr int kStepMaxT = 12;
 // smallest number of parked tiles per warp T for which a grid of resident CTAs covers n_tiles; 0 = not eligible
 static int dl_step_plan(const DlArgs& a, int kind, int S, long long n_tiles, long long* blocks_out) {
-  const char* e = getenv("VAEMDL_FUSED");  // "0": always three launches
-  if (e && e[0] == '0') return 0;
+  // VAEMDL_FUSED=1: the one-launch cooperative step.  Default: three launches -- since the gradient kernel evaluates its
+  // first tile while the finish kernel runs they are ahead (BASELINE configs[1]: 25.1 vs 26.7 us, 23.0 vs 24.4 us as graphs).
+  const char* e = getenv("VAEMDL_FUSED");
+  if (!(e && e[0] == '1')) return 0;
   if (S > 32 || (kind != 1 && kind != 2) || a.rows_per_img < 64) return 0;
   static int coop = -1, occ[2][kStepMaxT + 1];
   static std::mutex mu;
