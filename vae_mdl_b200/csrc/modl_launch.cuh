@@ -445,7 +445,8 @@ static bool use_pixel_pairs(int M, long long n_px, bool bf16 = false) {
 // tools/ncu_smem.sh, profiles/r02e_*): it removes 65 % of the conflict wavefronts (31.0 M -> 20.2 M per backward launch at
 // n_mix 10) but the shared-memory pipe was not what limits these kernels: n_mix 30 gains 1.3 %, n_mix 20 is level, and the
 // n_mix 10 backward kernel LOSES 7 % back to back (280 -> 299 us; level under ncu's serialised replay) -- so it is on for
-// three lanes per pixel only.  VAEMDL_ROT = 0 / 1 forces it off / on for every tiled kernel (A/B).
+// three lanes per pixel and for rows of 160 / 320 words (n_mix 16 / 32, where every row starts in bank 0) only, and compiled
+// in only there (Tile::ROT).  VAEMDL_ROT = 0 switches it off (A/B).
 static int pair_rot_on(int M) {
   static const int forced = [] {
     const char* e = getenv("VAEMDL_ROT");

@@ -24,6 +24,10 @@ struct Tile {
   // iteration spread over the banks (wavefronts per pair iteration 20 -> 12 / 14 / 20 at M = 10 / 20 / 30; with five pairs
   // one iteration in five keeps a two-way conflict).  Whether that pays is decided per n_mix by pair_rot_on()
   // (modl_launch.cuh): the shared-memory pipe is not what limits these kernels.
+  // The rotation is compiled in only where it pays (measured, pair_rot_on() in modl_launch.cuh): rows that are a multiple of
+  // 32 words long (n_mix 16, 32) and three lanes per pixel (n_mix 30).  Elsewhere the pair index stays a compile-time
+  // sequence: carrying a run-time rotation through the rolled loops cost n_mix 10 about 4 % more instructions for nothing.
+  static constexpr bool ROT = ALIGNED && (ROWF % 32 == 0 || LPP == 3);
   __device__ static __forceinline__ int pair_rot(int lane) {
     if constexpr (!ALIGNED) return 0;
     // rows that are a multiple of 32 words long (n_mix 16, 32) all start in the same bank: 8- / 16-way conflicts in row order;
@@ -173,7 +177,7 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
   const int p = lane_used ? (lane / LPP) : 0;  // idle lanes (LPP=3: lanes 30,31) shadow pixel 0
   const int sub = lane % LPP;
   const int m0 = sub * MC;
-  const int rot = a.pair_rot ? T::pair_rot(lane) : 0;  // this lane's first component pair (bank-conflict rotation)
+  const int rot = (T::ROT && a.pair_rot) ? T::pair_rot(lane) : 0;  // this lane's first component pair (bank-conflict rotation)
 
   // this warp's run of CONSECUTIVE tiles (balanced split of the tile range over all warps of the grid): per-image
   // sums then accumulate in registers across tiles and leave the warp once per image instead of once per tile
