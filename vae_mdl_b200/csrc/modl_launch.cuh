@@ -216,8 +216,15 @@ static int launch_step(ModlArgs a, StepFinish f, long long n_img, cudaStream_t s
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
   if (!partials_fit(n_img, a.K)) return VAEMDL_EWORKSPACE;
   a.reverse = 1;
-  a.keep_tiles = 0;
-  a.bwd_hint = 0;
+  {  // VAEMDL_L2S="keep=<MB>,hint=<bits>" (A/B, tools/ab_l2s.sh): L2 policy inside the one-launch step -- forward loads of the
+     // last <MB> of every run evict_last, the rest evict_first; hint bit 0 / 1: evict_first on the backward pass's loads / stores.
+     // Measured: 94.1-97.7 us at BASELINE configs[0] whatever the setting, so the default is no hint at all.
+    static const int keep_mb = [] { const char* e = getenv("VAEMDL_L2S"); const char* q = e ? strstr(e, "keep=") : nullptr; return q ? atoi(q + 5) : 0; }();
+    static const int hint = [] { const char* e = getenv("VAEMDL_L2S"); const char* q = e ? strstr(e, "hint=") : nullptr; return q ? atoi(q + 5) : 0; }();
+    a.keep_tiles = keep_mb > 0 ? static_cast<int>((static_cast<long long>(keep_mb) << 20) / (total_warps * T::TILE_B)) : 0;
+    if (keep_mb > 0 && a.keep_tiles < 1) a.keep_tiles = 1;
+    a.bwd_hint = hint;
+  }
   f.geom = PartialGeom{a.partial, a.tw_base, a.tw_rem, a.K, T::PPT, a.HW};
   StepArgs sa{a, f};
   void* args[] = {&sa};
