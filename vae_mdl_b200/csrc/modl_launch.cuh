@@ -440,6 +440,37 @@ static int launch_rt_al(ModlArgs a, const RtPlan& rp, cudaStream_t st, TilePlan*
 // n_mix 1..9 run on the pixel-pair kernel.  n_mix = 5 also has a component-pair instantiation with 32-row tiles, which
 // is a little faster while the problem is so small that a warp only sees a handful of tiles (measured: 112 vs 117 us
 // per step at 5 x 128 x 32 x 32, 345 vs 314 us backward at 16 x 64 x 64 x 64).
+// Tile instantiations beyond n_mix 5 / 10 / 20 / 30 are compiled in their own translation units (modl_tiles_{a,b,c,d}.cu),
+// x-conditioned classes only (AR = 0); the un-conditioned class (utils/mdl_plain.py) runs those n_mix on the run-time tiled
+// kernel.  n_mix -> (components per lane) x (lanes per pixel):
+//   a:  8 -> 8x1, 12 -> 6x2, 16 -> 8x2, 24 -> 6x4        b: 32 -> 8x4, 40 -> 10x4, 64 -> 8x8
+//   c:  6 -> 6x1, 14 -> 14x1, 18 -> 6x3, 28 -> 14x2      d: 36 -> 12x3, 48 -> 12x4, 50 -> 10x5, 56 -> 14x4, 60 -> 12x5
+int launch_tiled_extra_a(bool bwd, const ModlArgs& a, cudaStream_t st, TilePlan* plan);
+int launch_tiled_extra_b(bool bwd, const ModlArgs& a, cudaStream_t st, TilePlan* plan);
+int launch_tiled_extra_c(bool bwd, const ModlArgs& a, cudaStream_t st, TilePlan* plan);
+int launch_tiled_extra_d(bool bwd, const ModlArgs& a, cudaStream_t st, TilePlan* plan);
+static int extra_tile_group(int M) {  // 1..4 = a..d, 0 = no extra tile instantiation
+  switch (M) {
+    case 8: case 12: case 16: case 24: return 1;
+    case 32: case 40: case 64: return 2;
+    case 6: case 14: case 18: case 28: return 3;
+    case 36: case 48: case 50: case 56: case 60: return 4;
+    default: return 0;
+  }
+}
+static int extra_tile_ppt(int M, int AR) {  // pixels per tile of the extra instantiation serving n_mix M (0: none)
+  if (AR != 0 || getenv("VAEMDL_NO_EXTRA_TILES")) return 0;
+  switch (M) {
+    case 6: case 8: case 14: return 32;       // one lane per pixel
+    case 12: case 16: case 28: return 16;     // two
+    case 18: case 36: return 10;              // three
+    case 24: case 32: case 40: case 48: case 56: return 8;  // four
+    case 50: case 60: return 6;               // five
+    case 64: return 4;                        // eight
+    default: return 0;
+  }
+}
+
 static bool use_pixel_pairs(int M, long long n_px, bool bf16 = false) {
   const char* env = getenv("VAEMDL_PP");  // "0" / "1" force the choice for n_mix = 5 (A/B measurements, tests)
   if (M < 1 || M > 9 || bf16) return false;  // (bfloat16 parameters: tile<5,1> for n_mix = 5, the run-time kernel otherwise)
@@ -448,19 +479,14 @@ static bool use_pixel_pairs(int M, long long n_px, bool bf16 = false) {
   return n_px >= 64ll * 148 * 16 * 6;
 }
 
-// Rotated component-pair order against shared-memory bank conflicts (Tile::pair_rot).  Measured on B200 (tools/ab_rot.sh,
-// tools/ncu_smem.sh, profiles/r02e_*): it removes 65 % of the conflict wavefronts (31.0 M -> 20.2 M per backward launch at
-// n_mix 10) but the shared-memory pipe was not what limits these kernels: n_mix 30 gains 1.3 %, n_mix 20 is level, and the
-// n_mix 10 backward kernel LOSES 7 % back to back (280 -> 299 us; level under ncu's serialised replay) -- so it is on for
-// three lanes per pixel and for rows of 160 / 320 words (n_mix 16 / 32, where every row starts in bank 0) only, and compiled
-// in only there (Tile::ROT).  VAEMDL_ROT = 0 switches it off (A/B).
-static int pair_rot_on(int M) {
-  static const int forced = [] {
+// Rotated component-pair order against shared-memory bank conflicts: which tile shapes carry it is decided at compile time
+// by the bank model in modl_tile.cuh (Tile::ROT_KIND).  VAEMDL_ROT=0 switches it off (A/B).
+static int pair_rot_on(int /*M*/) {
+  static const int on = [] {
     const char* e = getenv("VAEMDL_ROT");
-    return !e ? -1 : (e[0] == '0' ? 0 : 1);
+    return !(e && e[0] == '0');
   }();
-  if (forced >= 0) return forced;
-  return M == 30 || M == 16 || M == 32;  // (16 / 32: rows of 160 / 320 words all start in bank 0 -- without it 32 % / 57 % backward)
+  return on;
 }
 
 static int spread_runs() {
@@ -482,7 +508,8 @@ static bool stats_supported(int M, long long n_px, bool bf16, int AR = 0) {
   if (M == 5 && !bf16 && AR == 0 && m5_two_slots()) return true;  // pixel-pair forward writes them, two-slot tile backward reads them
   if (use_pixel_pairs(M, n_px, bf16)) return false;
   if (bf16)  // the direct bf16 backward pass (aligned tile instantiations) needs them
-    return (M == 10 || M == 16 || M == 20 || M == 30 || M == 32 || M == 40) && getenv("VAEMDL_BF16_WIDEN") == nullptr;
+    return (M == 10 || M == 20 || M == 30 || (AR == 0 && extra_tile_ppt(M, 0))) && getenv("VAEMDL_BF16_WIDEN") == nullptr;
+  if (AR == 0 && extra_tile_ppt(M, 0)) return false;  // (the extra float32 tiles keep the two-pass gradient)
   const char* e = getenv("VAEMDL_STATS");
   if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
   return M == 5 || M == 30;
@@ -496,6 +523,15 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   if (!stats_supported(a.M, a.n_px, a.bf16 != 0, AR)) a.pix_stats = nullptr;
   // n_mix 5 with the forward pass's sums at hand: the one-pass gradient on the two-slot 32-row tile, whatever the size
   const bool m5_tile_bwd = BWD && AR == 0 && a.M == 5 && !a.bf16 && a.pix_stats && m5_two_slots();
+  if (const int ppt = extra_tile_ppt(a.M, AR)) {
+    (void)ppt;
+    switch (extra_tile_group(a.M)) {
+      case 1: return launch_tiled_extra_a(BWD, a, st, plan);
+      case 2: return launch_tiled_extra_b(BWD, a, st, plan);
+      case 3: return launch_tiled_extra_c(BWD, a, st, plan);
+      default: return launch_tiled_extra_d(BWD, a, st, plan);
+    }
+  }
   if (!m5_tile_bwd && use_pixel_pairs(a.M, a.n_px, a.bf16 != 0)) {
     switch (a.M) {
       case 1: return launch_pp<1, BWD, AR>(a, st, plan);
@@ -514,16 +550,10 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
       return launch_tiled<5, 1, BWD, AR>(a, st, plan);
     case 10:
       return launch_tiled<10, 1, BWD, AR>(a, st, plan);
-    case 16:  // (r01: 67 % / 66 % of the HBM roofline on the run-time tiled kernel)
-      return launch_tiled<8, 2, BWD, AR>(a, st, plan);
     case 20:
       return launch_tiled<10, 2, BWD, AR>(a, st, plan);
     case 30:
       return launch_tiled<10, 3, BWD, AR>(a, st, plan);
-    case 32:  // (r01: 69 % / 70 %)
-      return launch_tiled<8, 4, BWD, AR>(a, st, plan);
-    case 40:  // (r01: 72 % / 68 %)
-      return launch_tiled<10, 4, BWD, AR>(a, st, plan);
     default: {
       static const bool force_generic = getenv("VAEMDL_GENERIC") != nullptr;  // A/B against the one-thread-per-pixel kernel
       if (!force_generic) return launch_rt<BWD, AR>(a, st, plan);
@@ -538,20 +568,17 @@ static int launch_modl(ModlArgs a, cudaStream_t st, TilePlan* plan = nullptr) {
   }
 }
 
-static int tile_ppt(int M, long long n_px, bool bf16 = false) {
+static int tile_ppt(int M, long long n_px, bool bf16 = false, int AR = 0) {
+  if (const int ppt = extra_tile_ppt(M, AR)) return ppt;
   if (use_pixel_pairs(M, n_px, bf16)) return 64;
   switch (M) {
     case 5:
     case 10:
       return 32;
-    case 16:
     case 20:
       return 16;
     case 30:
       return 10;
-    case 32:
-    case 40:
-      return 8;
     default:
       if (getenv("VAEMDL_GENERIC")) return 0;  // one-thread-per-pixel kernel: atomics
       return rt_plan(M, false, bf16).PPT;
@@ -624,7 +651,7 @@ static int modl_fwd_impl(const float* params, const void* x, int x_dtype, int x_
   a.bf16 = bf16;
   a.pix_stats = reinterpret_cast<float2*>(pix_stats);
   if ((rc = set_bins(a, bins, AR))) return rc;
-  const int ppt = tile_ppt(M, a.n_px, bf16 != 0);
+  const int ppt = tile_ppt(M, a.n_px, bf16 != 0, AR);
   const bool use_partials = want_ll && ppt > 0 && a.HW >= ppt;
   char* ws = static_cast<char*>(workspace);
   size_t tail_off = 0;

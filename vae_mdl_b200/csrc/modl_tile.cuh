@@ -1,9 +1,77 @@
 #pragma once
-// modl_tile.cuh -- the tiled kernel for n_mix = MC * LPP (5, 10, 20, 30) and the one-launch cooperative step built on it.
+// modl_tile.cuh -- the tiled kernel for n_mix = MC * LPP (5, 8, 10, 12, 16, 20, 24, 30, 32, 40, 64) and the one-launch cooperative
+// step built on it.
 // Part of the MoDL kernel family; see modl_kernels.cuh for the overview.
 #include "modl_core.cuh"
 
 namespace vaemdl {
+
+// ---- shared-memory bank model of the tiled kernel (compile time) ---------------------------------------------------------
+// A row is 10 M words, so rows of different lanes start in a few banks only (M = 16 / 32 / 64: ALL rows start in bank 0) and
+// the 64-bit accesses of a half-warp to "component pair pr of my row" collide.  A lane can walk its pairs in a rotated order,
+// the rotation taken from a small family of lane functions.  rot_wavefronts() counts the wavefronts of one pass over the pairs
+// (two half-warps per access, the degree of the worst bank each); best_rot_kind() picks the cheapest member -- but only when
+// row order costs at least 3x the conflict-free count: measured on B200 (tools/ab_rot.sh, tools/ncu_smem.sh), shapes at 2.0x
+// (n_mix 10 / 20 / 40) gain nothing from it (n_mix 10 even loses 7 % back to back although 65 % of the conflict wavefronts
+// go away: the shared-memory pipe is not their limit), at 2.5x (n_mix 30) the rotated order is level backward and 3 points
+// behind forward (the rotation arithmetic in the rolled loops), n_mix 16 / 32 (8x / 4x) go from 32-57 % to 84-87 % of the
+// HBM roofline.  Where the rotation is off the pair index stays a compile-time sequence.
+__host__ __device__ constexpr int rot_kind_value(int kind, int lane, int LPP, int NP) {
+  const int p = lane / LPP;
+  int r = 0;
+  switch (kind) {
+    case 1: r = (lane >> 3) & 1; break;
+    case 2: r = ((lane >> 3) & 1) * 2; break;
+    case 3: r = p; break;
+    case 4: r = lane >> 1; break;
+    case 5: r = lane >> 2; break;
+    case 6: r = lane >> 3; break;
+    case 7: r = 3 * p; break;
+    default: r = 0; break;
+  }
+  return r % NP;
+}
+constexpr int rot_wavefronts(int M, int MC, int LPP, int kind) {
+  const int PPT = 32 / LPP, NP = MC / 2, ROWF = 10 * M;
+  int tot = 0;
+  for (int pr = 0; pr < NP; ++pr) {
+    for (int half = 0; half < 2; ++half) {
+      int cnt[32] = {};
+      int addr[32][16] = {};
+      for (int lane = 16 * half; lane < 16 * half + 16; ++lane) {
+        int p = lane / LPP;
+        const int sub = lane % LPP;
+        if (p >= PPT) p = 0;
+        const int prr = (pr + rot_kind_value(kind, lane, LPP, NP)) % NP;
+        const int a = p * ROWF + sub * MC + 2 * prr;
+        for (int w = a; w < a + 2; ++w) {
+          const int b = w % 32;
+          bool seen = false;
+          for (int q = 0; q < cnt[b]; ++q) seen = seen || addr[b][q] == w;
+          if (!seen) addr[b][cnt[b]++] = w;
+        }
+      }
+      int mx = 0;
+      for (int b = 0; b < 32; ++b) mx = cnt[b] > mx ? cnt[b] : mx;
+      tot += mx;
+    }
+  }
+  return tot;
+}
+constexpr int best_rot_kind(int M, int MC, int LPP) {
+  if (MC % 2 != 0 || MC < 4) return 0;
+  const int ideal = 2 * (MC / 2);
+  int best = 0, bw = rot_wavefronts(M, MC, LPP, 0);
+  if (bw < 3 * ideal) return 0;  // row order is within 3x of conflict-free: leave it alone (see above)
+  for (int k = 1; k <= 7; ++k) {
+    const int w = rot_wavefronts(M, MC, LPP, k);
+    if (w < bw) {
+      bw = w;
+      best = k;
+    }
+  }
+  return best;
+}
 
 // ---- the tiled kernel -------------------------------------------------------------------------------------------------
 // M = MC * LPP mixtures; LPP lanes share a pixel, each owning MC consecutive components, processed two at a time.
@@ -18,26 +86,9 @@ struct Tile {
   static constexpr int NPAIR = (MC + 1) / 2;
   static constexpr bool ALIGNED = (M % 2 == 0) && (MC % 2 == 0);  // component pairs sit on 8-byte boundaries
   static_assert(TILE_B % 16 == 0, "bulk copies need 16-byte multiples");
-  // Shared-memory bank conflicts: a row is 10 M words, so the rows of lanes l and l + 8 (M = 10: 100 = 4 mod 32 words
-  // apart) start in the same bank and every 64-bit access of a half-warp takes two wavefronts instead of one.  A lane can
-  // walk its component pairs in a rotated order, the rotation chosen per lane group so that the pairs touched in one
-  // iteration spread over the banks (wavefronts per pair iteration 20 -> 12 / 14 / 20 at M = 10 / 20 / 30; with five pairs
-  // one iteration in five keeps a two-way conflict).  Whether that pays is decided per n_mix by pair_rot_on()
-  // (modl_launch.cuh): the shared-memory pipe is not what limits these kernels.
-  // The rotation is compiled in only where it pays (measured, pair_rot_on() in modl_launch.cuh): rows that are a multiple of
-  // 32 words long (n_mix 16, 32) and three lanes per pixel (n_mix 30).  Elsewhere the pair index stays a compile-time
-  // sequence: carrying a run-time rotation through the rolled loops cost n_mix 10 about 4 % more instructions for nothing.
-  static constexpr bool ROT = ALIGNED && (ROWF % 32 == 0 || LPP == 3);
-  __device__ static __forceinline__ int pair_rot(int lane) {
-    if constexpr (!ALIGNED) return 0;
-    // rows that are a multiple of 32 words long (n_mix 16, 32) all start in the same bank: 8- / 16-way conflicts in row order;
-    // pixel p starts at pair p, which leaves the two-way conflict the other tile shapes live with (or none, 4 lanes per pixel)
-    if constexpr (ROWF % 32 == 0) return (lane / LPP) % NPAIR;
-    if constexpr (LPP == 1) return (lane >> 3) & 1;
-    if constexpr (LPP == 2) return ((lane >> 3) & 1) * 2;
-    if constexpr (LPP == 3) return (3 * (lane / 3)) % NPAIR;
-    return 0;
-  }
+  static constexpr int ROT_KIND = ALIGNED ? best_rot_kind(M, MC, LPP) : 0;  // (bank model above)
+  static constexpr bool ROT = ROT_KIND != 0;
+  __device__ static __forceinline__ int pair_rot(int lane) { return rot_kind_value(ROT_KIND, lane, LPP, NPAIR); }
 };
 
 // a pair of consecutive floats at row[off], row[off+1]; `single`: only row[off] exists (odd MC), both halves get it

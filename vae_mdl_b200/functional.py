@@ -222,7 +222,7 @@ def modl_iwae_step(params: torch.Tensor, x: torch.Tensor, extra: Optional[torch.
     Returns ``(lpxz float64 [S,B], log_w, lme_b [B], elbo [1], g_ll [S,B], dparams, launches)``."""
     if params.dtype == torch.bfloat16:  # bfloat16 parameters: forward + finish, then the gradient kernel (3 launches)
         # n_mix 10 / 20 / 30: the forward kernel leaves the per-pixel sums and the gradient kernel keeps the tile in bfloat16
-        want = (not plain) and params.shape[-1] in (100, 160, 200, 300, 320, 400)
+        want = (not plain) and params.shape[-1] in (60, 80, 100, 120, 140, 160, 180, 200, 240, 280, 300, 320, 360, 400, 480, 500, 560, 600, 640)
         out = modl_iwae_forward(params, x, extra, b_total, x_range, edge_mode, plain, want_stats=want)
         ll64, log_w, lme_b, elbo, g_ll = out[:5]
         dp = modl_backward(params, x, g_image=g_ll, x_range=x_range, edge_mode=edge_mode, pix_stats=out[5] if want else None)
@@ -741,7 +741,7 @@ class _FusedIwaeFn(torch.autograd.Function):
         if kind == "modl":
             # n_mix 5 / 30: the forward kernel leaves the per-pixel mixture sums for a one-pass gradient kernel (the
             # library ignores them for any other n_mix, so they are not even allocated then)
-            stat_widths = (100, 160, 200, 300, 320, 400) if p0.dtype == torch.bfloat16 else (50, 300)
+            stat_widths = (60, 80, 100, 120, 140, 160, 180, 200, 240, 280, 300, 320, 360, 400, 480, 500, 560, 600, 640) if p0.dtype == torch.bfloat16 else (50, 300)
             want = bool(ctx.needs_input_grad[5]) and p0.shape[-1] in stat_widths and not meta["plain"]
             out = modl_iwae_forward(p0, x, extra, 0, meta["x_range"], meta["edge_mode"], meta["plain"], want_stats=want)
             ll64, log_w, lme_b, elbo, g_ll = out[:5]
