@@ -1,9 +1,11 @@
 """Per-source-line stall samples of one kernel: joins the SASS page of an .ncu-rep (`ncu --page source --csv`) with the
 line table of the cubin (`nvdisasm -g`).  Runs on the CPU box.
-    python tools/ncu_lines.py <report.ncu-rep> <object-with-kernel.o> <mangled-kernel-name> [top-N]"""
+    python tools/ncu_lines.py <report.ncu-rep> <object-with-kernel.o> <mangled-kernel-name> [top-N] [result-index]
+(result-index: which launch of a multi-kernel report, 0-based in report order; default 0)"""
 import csv, io, os, re, subprocess, sys, tempfile
 rep, obj, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+which = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -26,8 +28,19 @@ for l in dis:
         lines.append(cur)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr = next(r for r in rows if r and r[0] == "Address")
-data = [r for r in rows if r and r[0].startswith("0x")]
+# one section per profiled launch: "Kernel Name" line, header line ("Address", ...), then the instructions
+sections, cur_rows = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_rows = {"name": r[1] if len(r) > 1 else "", "hdr": None, "data": []}
+        sections.append(cur_rows)
+    elif cur_rows is not None and r and r[0] == "Address":
+        cur_rows["hdr"] = r
+    elif cur_rows is not None and r and r[0].startswith("0x"):
+        cur_rows["data"].append(r)
+sec = sections[which]
+print("kernel:", sec["name"][:120])
+hdr, data = sec["hdr"], sec["data"]
 assert len(data) == len(lines), (len(data), len(lines))
 col = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]

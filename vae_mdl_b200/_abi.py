@@ -14,7 +14,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvaemdl_b200.so")
+# (VAEMDL_LIB_PATH: A/B measurements of two builds inside one process launch; never set in normal use)
+LIB_PATH = os.environ.get("VAEMDL_LIB_PATH") or os.path.join(_HERE, "libvaemdl_b200.so")
 
 # enums (include/vaemdl.h)
 X_F32, X_U8 = 0, 1

@@ -122,6 +122,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
   if (a.partial && !partials_fit(a.n_px / a.HW, a.K)) return VAEMDL_EWORKSPACE;  // (before anything is enqueued)
+  a.small = a.n_px < (1ll << 31) - 64;  // image / pixel indices fit 32 bits
   apply_l2_opt(a, total_warps, T::TILE_B / (PD ? 2 : 1));
   if (PD == 2 && NSLOT > 1 && a.keep_tiles > 0 && a.keep_tiles < NSLOT) a.keep_tiles = NSLOT;
   if (plan) {
@@ -215,6 +216,7 @@ static int launch_step(ModlArgs a, StepFinish f, long long n_img, cudaStream_t s
   a.tw_rem = a.num_tiles % total_warps;
   a.K = partial_K(a.HW, T::PPT, a.tw_base);
   if (!partials_fit(n_img, a.K)) return VAEMDL_EWORKSPACE;
+  a.small = a.n_px < (1ll << 31) - 64;
   a.reverse = 1;
   {  // VAEMDL_L2S="keep=<MB>,hint=<bits>" (A/B, tools/ab_l2s.sh): L2 policy inside the one-launch step -- forward loads of the
      // last <MB> of every run evict_last, the rest evict_first; hint bit 0 / 1: evict_first on the backward pass's loads / stores.

@@ -142,7 +142,17 @@ struct PixRaw {
   unsigned v[3];
 };
 __device__ __forceinline__ PixRaw load_pixel_raw(const ModlArgs& a, long long n, int pix) {
-  const long long xb = a.x_batch == 1 ? 0 : (n < a.x_batch ? n : n % a.x_batch);
+  // image n is scored against x[n % x_batch].  The 64-bit remainder is a ~100-instruction subroutine executed per tile and
+  // lane (every importance sample but the first has n >= x_batch): 32-bit arithmetic whenever the problem allows it.
+  long long xb;
+  if (a.x_batch == 1)
+    xb = 0;
+  else if (n < a.x_batch)
+    xb = n;
+  else if (a.small)
+    xb = static_cast<long long>(static_cast<unsigned>(n) % static_cast<unsigned>(a.x_batch));
+  else
+    xb = n % a.x_batch;
   const long long xo = (xb * a.HW + pix) * 3;
   PixRaw r;
 #pragma unroll
