@@ -43,6 +43,8 @@ struct ModlArgs {
                               // read last are the ones still in L2)
   int keep_tiles;             // forward: the last keep_tiles tiles of a run are loaded with an L2 evict_last hint
   int bwd_hint;               // backward: L2 evict_first hint on the parameter loads (bit 0) / gradient stores (bit 1)
+  int tm_refill;              // tensor-memory gradient kernel: the component pair of the first pass before which the staging
+                              // slot is refilled with the warp's next tile (modl_tm.cuh)
   int plain;                  // 1: channel means chained on the component's own means (utils/mdl_plain.py:160-162),
                               // 0: on the observed x (utils/mdl.py:139-145); the fast kernels take this as template AR
   int HW;

@@ -4,6 +4,7 @@
 #include "modl_pp.cuh"
 #include "modl_rt.cuh"
 #include "modl_tile.cuh"
+#include "modl_tm.cuh"
 
 namespace vaemdl {
 
@@ -137,6 +138,67 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   return cuda_rc(cudaGetLastError());
 }
 
+// the two-pass gradient kernel on tensor memory (modl_tm.cuh): float32 parameters, one slot per warp, twelve warps per CTA.
+// Measured on B200 (tools/ab_tm.sh, profiles/r02y_*): headline gradient kernel 280 -> 271 us, n_mix 20 at the same size 613 -> 551 us,
+// BASELINE configs[0] 56 -> 48 us.  VAEMDL_TM=0 keeps the shared-memory kernel (A/B).
+static bool tm_enabled() {  // (re-read on every call: the tests compare both kernels inside one process)
+  const char* e = getenv("VAEMDL_TM");
+  return !(e && e[0] == '0');
+}
+template <int MC, int LPP, int AR>
+static int launch_tiled_tm(ModlArgs a, cudaStream_t st, TilePlan* plan) {
+  using T = Tile<MC, LPP>;
+  constexpr int MAXT = kTmWarps * 32;
+  a.num_tiles = (a.n_px + T::PPT - 1) / T::PPT;
+  const DeviceInfo& di = device_info();
+  const size_t per_warp = static_cast<size_t>(T::TILE_F) * 4 + 8;
+  int warps = kTmWarps;
+  while (warps > 1 && warps * per_warp + 16 > static_cast<size_t>(di.max_smem_optin)) --warps;
+  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  const size_t smem = warps * per_warp + 16;
+  auto kern = modl_tile_tm_kernel<MC, LPP, MAXT, AR>;
+  static std::mutex mu;
+  static int c_dev = -1;
+  static size_t c_smem = 0;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_dev != dev || smem > c_smem) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cuda_rc(e);
+      c_dev = dev;
+      c_smem = smem;
+    }
+  }
+  const long long need = (a.num_tiles + warps - 1) / warps;
+  long long grid = di.sm_count;  // persistent, ONE CTA per SM: the CTA owns all 512 TMEM columns
+  if (grid > need) grid = need;
+  if (grid * warps > kMaxGridWarps) grid = kMaxGridWarps / warps;
+  if (grid < 1) grid = 1;
+  const long long total_warps = grid * warps;
+  a.tw_base = a.num_tiles / total_warps;
+  a.tw_rem = a.num_tiles % total_warps;
+  a.K = partial_K(a.HW, T::PPT, a.tw_base);
+  a.small = a.n_px < (1ll << 31) - 64;
+  apply_l2_opt(a, total_warps, T::TILE_B);
+  {
+    // where in the first pass the staging slot is refilled: as late as possible -- before the LAST component pair -- measured
+    // best everywhere (VAEMDL_TM_REFILL=<pair> / NPAIR = after the pass: headline gradient kernel 309 / 305 / 302 / 289 / 271 / 285 us
+    // for 0 ... 5): the gradient tile the slot still holds drains slowly while the memory system is saturated with writes
+    static const int refill = [] { const char* e = getenv("VAEMDL_TM_REFILL"); return e ? atoi(e) : -1; }();
+    a.tm_refill = refill < 0 ? T::NPAIR - 1 : (refill < T::NPAIR ? refill : T::NPAIR);
+  }
+  if (plan) {
+    plan->total_warps = total_warps;
+    plan->tw_base = a.tw_base;
+    plan->tw_rem = a.tw_rem;
+    plan->K = a.K;
+    plan->PPT = T::PPT;
+  }
+  return cuda_rc(launch_pdl(kern, static_cast<unsigned>(grid), static_cast<unsigned>(warps * 32), smem, st, a));
+}
+
 template <int MC, int LPP, bool BWD, int AR>
 static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   if (a.bf16) {  // bfloat16 parameters: x-conditioned class only
@@ -176,6 +238,10 @@ static int launch_tiled(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   }
   if constexpr (BWD) {
     if (a.pix_stats) return launch_tiled_shape<MC, LPP, true, 1, 512, AR, 0, true>(a, sh.warps, st, plan);  // one-pass gradient
+    if constexpr (tm_supported<MC, LPP>()) {
+      // two-pass gradient with the tile in tensor memory
+      if (tm_enabled() && !getenv("VAEMDL_TUNE")) return launch_tiled_tm<MC, LPP, AR>(a, st, plan);
+    }
   }
   return launch_tiled_shape<MC, LPP, BWD, 1, 512, AR>(a, sh.warps, st, plan);
 }
