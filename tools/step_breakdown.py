@@ -5,7 +5,10 @@ import torch
 from bench import ModlStep, WORKLOADS
 dev = torch.device("cuda:0")
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg5_64_m10"
-_, S, B, H, W, M = WORKLOADS[name]
+if "," in name:  # "S,B,H,W,M"
+    S, B, H, W, M = (int(v) for v in name.split(","))
+else:
+    _, S, B, H, W, M = WORKLOADS[name]
 nbuf = max(2, -(-3 * 126 * 2**20 // (S * B * H * W * 40 * M)))
 st = ModlStep(S, B, H, W, M, dev, 1, B, n_buffers=nbuf)
 L = st.L

@@ -126,6 +126,13 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
   a.small = a.n_px < (1ll << 31) - 64;  // image / pixel indices fit 32 bits
   apply_l2_opt(a, total_warps, T::TILE_B / (PD ? 2 : 1));
   if (PD == 2 && NSLOT > 1 && a.keep_tiles > 0 && a.keep_tiles < NSLOT) a.keep_tiles = NSLOT;
+  if (BWD && NSLOT > 1) {
+    // two-slot gradient kernels: before which component pair of a tile the other slot is refilled (VAEMDL_REFILL2=<pair>, A/B).
+    // Measured (tools/ab_refill2.sh, profiles/r02z_refill2.txt): n_mix 5 gains 1 % (291 -> 288 us) and 2.4 % at 5 x 128 x 32 x 32 with
+    // pair 1 instead of 0; the bfloat16 tiles are indifferent.
+    static const int refill2 = [] { const char* e = getenv("VAEMDL_REFILL2"); return e ? atoi(e) : 1; }();
+    a.tm_refill = refill2 < T::NPAIR ? refill2 : T::NPAIR - 1;
+  }
   if (plan) {
     plan->total_warps = total_warps;
     plan->tw_base = a.tw_base;
@@ -580,7 +587,10 @@ static bool stats_supported(int M, long long n_px, bool bf16, int AR = 0) {
   if (AR == 0 && extra_tile_ppt(M, 0)) return false;  // (the extra float32 tiles keep the two-pass gradient)
   const char* e = getenv("VAEMDL_STATS");
   if (e && e[0] == 'a') return M == 5 || M == 10 || M == 20 || M == 30;
-  return M == 5 || M == 30;
+  // n_mix 30: below ~1.2 M pixel-samples the two-pass gradient on tensor memory is ahead of the one-pass kernel (5 x 64 x 32 x 32:
+  // step 229 vs 237 us, 5 x 128 x 32 x 32: 419 vs 440 us, 16 x 16 x 64 x 64: 670 vs 678 us; level from 1.5 M on; tools/ab_m30.sh)
+  if (M == 30) return tm_enabled() ? n_px >= 1200000 : true;
+  return M == 5;
 }
 
 template <bool BWD, int AR>

@@ -402,14 +402,18 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     if constexpr (PD == 1) {
       if (((rows * ROWF * 2) & 15) == 0) widen_bf16_inplace(slot, rows * ROWF, lane);  // (a ragged tile was widened by its loads)
     }
+    // Two slots (BWD): the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration; once
+    // its shared-memory reads are done that slot is refilled with this warp's next tile.  Those reads take microseconds while
+    // the memory system is saturated with writes, so the warp does not wait for them here but before component pair
+    // a.tm_refill of this tile (0: here, as in round 1) -- the later, the less it waits, as long as the tile still lands in time.
+    [[maybe_unused]] auto refill_other = [&]() {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      issue(t + t_dir, s ^ 1);
+    };
+    [[maybe_unused]] const bool refill = BWD && NSLOT > 1 && it + 1 < t_cnt;
     if constexpr (BWD && NSLOT > 1) {
-      // the other slot's gradient tile was handed to the TMA engine at the end of the previous iteration: once its
-      // shared-memory reads are done, refill that slot with this warp's next tile (lands while this tile computes)
-      if (it + 1 < t_cnt) {
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
-        issue(t + t_dir, s ^ 1);
-      }
+      if (refill && a.tm_refill <= 0) refill_other();
     }
 
     // W_m = exp(logit_m - max logit)
@@ -443,6 +447,9 @@ __device__ __forceinline__ void tile_body(const ModlArgs& a, unsigned char* smem
     f2 sumW2 = sp(0.0f), sumWP2 = sp(0.0f);
 #pragma unroll 1
     for (int pr = 0; pr < NPAIR; ++pr) {
+      if constexpr (BWD && NSLOT > 1) {
+        if (refill && pr > 0 && pr == a.tm_refill) refill_other();
+      }
       const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
       const int m = m0 + 2 * prr;
       const bool single = (MC % 2 == 1) && (prr == NPAIR - 1);
