@@ -982,7 +982,10 @@ def main():
     # roofline of the dominant kernel (backward: reads the 40M-byte row, writes the 40M-byte gradient row)
     bwd_bytes = n_px * 80 * M
     fwd_bytes = n_px * 40 * M
-    roofline = {"bound": "hbm", "kernel": "modl_tile_kernel<BWD> (vaemdl_modl_bwd)", "achieved": bwd_bytes / bwd_s / 1e9,
+    one_pass = M == 5 or (M == 30 and n_px >= 1200000)  # (what csrc/modl_launch.cuh::stats_supported chooses)
+    bwd_kernel = ("modl_tile_kernel<BWD, ST> (one-pass gradient from the forward pass's per-pixel sums)" if one_pass else
+                  "modl_tile_tm_kernel (vaemdl_modl_bwd: two-pass gradient, tile in tensor memory)")
+    roofline = {"bound": "hbm", "kernel": bwd_kernel, "achieved": bwd_bytes / bwd_s / 1e9,
                 "peak": peak, "peak_source": peak_how, "unit": "GB/s", "frac": bwd_bytes / bwd_s / 1e9 / peak,
                 "traffic": traffic_from_profiles(args.workload, "modl_bwd_dram_bytes_per_launch"),
                 "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel; not re-measured here)",

@@ -45,6 +45,13 @@ static int pick_warps(long long num_tiles, int sm_count, int max_warps) {
   return best;
 }
 
+// forward kernels (VAEMDL_FWD_WARPS=<n>: exactly n warps per CTA, A/B)
+static int pick_warps_fwd(long long num_tiles, int sm_count, int max_warps) {
+  static const int forced = [] { const char* e = getenv("VAEMDL_FWD_WARPS"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced < max_warps ? forced : max_warps;
+  return pick_warps(num_tiles, sm_count, max_warps);
+}
+
 struct L2Opt {  // VAEMDL_L2="rev=0|1,keep=<MB>,hint=0|1": L2 reuse between the forward and the backward kernel of a step
   int rev = 1, keep_mb = 48, hint = 0;  // measured on B200: profiles/r01_l2_reuse.txt
   L2Opt() {
@@ -89,7 +96,7 @@ static int launch_tiled_shape(ModlArgs a, int warps, cudaStream_t st, TilePlan* 
                            (ST ? (NSLOT > 1 ? NSLOT : 1) * 2 * T::PPT : 0)) * 4 + NSLOT * 8;
   if (warps > MAXT / 32) warps = MAXT / 32;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
-  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  warps = BWD ? pick_warps(a.num_tiles, di.sm_count, warps) : pick_warps_fwd(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
   if (smem > static_cast<size_t>(di.max_smem_optin)) return VAEMDL_EUNSUPPORTED;
   auto kern = modl_tile_kernel<MC, LPP, BWD, NSLOT, MAXT, AR, PD, ST>;
@@ -316,7 +323,7 @@ static int launch_pp(ModlArgs a, cudaStream_t st, TilePlan* plan) {
   const size_t per_warp = (static_cast<size_t>(T::TILE_F) + (BWD ? T::AUX_F : 0)) * 4 + 8;
   int warps = tune_shape(BWD, Shape{1, 16}).warps;
   while (warps > 1 && warps * per_warp > static_cast<size_t>(di.max_smem_optin)) --warps;
-  warps = pick_warps(a.num_tiles, di.sm_count, warps);
+  warps = BWD ? pick_warps(a.num_tiles, di.sm_count, warps) : pick_warps_fwd(a.num_tiles, di.sm_count, warps);
   const size_t smem = warps * per_warp;
   auto kern = modl_pp_kernel<M, BWD, 512, AR>;
   static std::mutex mu;
