@@ -17,10 +17,14 @@
 // Work split.  n_mix 10 / 20 / 30: M = MC * LPP, LPP lanes share a pixel, each owning MC components, two components
 // per packed register (modl_tile_kernel: 10x1, 10x2, 10x3).  n_mix 1..9: one lane owns two pixels, the same component
 // of both per packed register (modl_pp_kernel).  Any other M runs on modl_rt_kernel: the tiled pipeline with the split of
-// a pixel over lanes chosen at run time.  Small training shapes run forward, IWAE finish and backward as ONE cooperative
-// launch (modl_step_kernel).  bfloat16 parameters are widened / narrowed in place in the shared-memory slot.
+// a pixel over lanes chosen at run time.  The two-pass gradient of every tile shape with an even MC <= 14 keeps the tile it
+// works on in TENSOR MEMORY (modl_tile_tm_kernel, modl_tm.cuh: tcgen05.ld / tcgen05.st, one TMEM lane per thread = per pixel
+// row): the shared-memory slot is then only the TMA staging area, the next tile lands while this one goes through its first
+// pass, and the second pass swaps gradient out / next parameters in block by block.  The cooperative one-launch step
+// (modl_step_kernel) is opt-in.  bfloat16 parameters are widened / narrowed in place in the shared-memory slot, or stay bf16.
 // Template parameter AR selects what the green / blue means are chained on (pair_eval).
 //
-// Files: modl_core.cuh (arguments, helpers, pair_eval), modl_tile.cuh (tiled kernel + one-launch step), modl_pp.cuh
-// (pixel pairs), modl_rt.cuh (run-time tile, generic), modl_launch.cuh (launchers + host implementation).
+// Files: modl_core.cuh (arguments, helpers, pair_eval), modl_tile.cuh (tiled kernel + one-launch step), modl_tm.cuh (gradient
+// kernel on tensor memory), modl_pp.cuh (pixel pairs), modl_rt.cuh (run-time tile, generic), modl_launch.cuh (launchers + host
+// implementation).
 #include "modl_launch.cuh"
