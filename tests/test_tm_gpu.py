@@ -87,3 +87,4 @@ def test_tm_many_tiles_per_warp_and_guard_band(F, monkeypatch):
     torch.cuda.synchronize()
     assert rc == 0 and torch.equal(dp, ref)
     assert bool((guard[:4096] == 7.25).all()) and bool((guard[4096 + pd.numel():] == 7.25).all())
+

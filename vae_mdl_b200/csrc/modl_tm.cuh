@@ -376,4 +376,5 @@ __global__ void __launch_bounds__(MAXT, 1) modl_tile_tm_kernel(const ModlArgs a)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   tile_body_tm<MC, LPP, AR>(a, smem_raw);
 }
+
 }  // namespace vaemdl
