@@ -261,18 +261,20 @@ def test_soak_bitwise_reproducible_under_back_to_back_steps(F, monkeypatch, S, B
 
 
 @pytest.mark.parametrize("name,H,W,M", [("cfg5_64_m30", 64, 64, 30), ("cfg5_128_m10", 128, 128, 10),
-                                        ("cfg5_128_m30", 128, 128, 30)])
+                                        ("cfg5_128_m30", 128, 128, 30), ("tm_128_m32", 128, 128, 32)])
 def test_config5_other_sweep_points_full_size(F, V, name, H, W, M):
     """The other three points of BASELINE configs[4] at their full per-GPU size (16 importance samples x 32 images):
     whole-image oracle spot checks of the log-likelihood (1e-5) and of the gradient (1e-4) taken from both ends and the
     middle of the tensor.  cfg5_128_m30 is the one shape whose element offsets exceed 2^31 (8.39 M pixel-samples x 300
     floats = 2.5 G elements, 10 GB of parameters + 10 GB of gradients): its last image (15, 31) starts at element
-    2,511,667,200 -- the 64-bit indexing path of the tile kernel, the bulk copies and the partial-sum bookkeeping."""
+    2,511,667,200 -- the 64-bit indexing path of the tile kernel, the bulk copies and the partial-sum bookkeeping.  n_mix 30 takes
+    the one-pass gradient at this size; tm_128_m32 (n_mix 32, 2.68 G elements) is the same check for the two-pass gradient kernel on
+    tensor memory."""
     S, B = 16, 32
     gen = torch.Generator(device=DEV).manual_seed(700 + M + H)
     params = torch.randn(S, B, H, W, 10 * M, device=DEV, generator=gen)
     x_u8 = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=DEV, generator=gen)
-    if name == "cfg5_128_m30":
+    if name in ("cfg5_128_m30", "tm_128_m32"):
         assert (S * B - 1) * H * W * 10 * M > 2 ** 31
     # `extra` balances the importance weights of every image (random parameters would give one sample all the weight and
     # leave the other samples' gradients in the float32 denormals): every spot-checked image carries a real gradient
