@@ -10,7 +10,7 @@
 // 128 columns of 32 bits each: room for the 10 * MC floats a lane owns plus the W*P strip of the second pass.  So here
 //   * the shared-memory slot X is only the landing / staging area of the TMA engine,
 //   * the tile being worked on lives in tensor memory C (tcgen05.st / tcgen05.ld, shape 32x32b: thread i <-> TMEM lane i),
-//     laid out as one 24-column block per component pair: [W*P | logits | mu s k (R) | mu s k (G) | mu s k (B) | pad],
+//     laid out as one 24-column block per component pair: [W*P | logits | mu s k (R) | mu s k (G) | mu s k (B) | W],
 //     so a pair's twenty values arrive with three 8-column loads instead of ten 64-bit shared-memory loads,
 //   * pass 1 (unscaled derivatives, mixture sums) runs entirely on C while X receives the NEXT tile,
 //   * pass 2 swaps column block by column block: it takes the unscaled derivatives of tile k out of C, moves the parameters
@@ -42,13 +42,13 @@ struct Blk {
 __device__ __forceinline__ void tmem_ld24(uint32_t taddr, Blk& b) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%24+8];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%24+16];\n"
       "tcgen05.wait::ld.sync.aligned;\n"
       : "=r"(b.r[0]), "=r"(b.r[1]), "=r"(b.r[2]), "=r"(b.r[3]), "=r"(b.r[4]), "=r"(b.r[5]), "=r"(b.r[6]), "=r"(b.r[7]),
         "=r"(b.r[8]), "=r"(b.r[9]), "=r"(b.r[10]), "=r"(b.r[11]), "=r"(b.r[12]), "=r"(b.r[13]), "=r"(b.r[14]), "=r"(b.r[15]),
         "=r"(b.r[16]), "=r"(b.r[17]), "=r"(b.r[18]), "=r"(b.r[19]), "=r"(b.r[20]), "=r"(b.r[21]), "=r"(b.r[22]), "=r"(b.r[23])
-      : "r"(taddr), "r"(taddr + 8u), "r"(taddr + 16u)
+      : "r"(taddr)
       : "memory");
 }
 // The same in two statements, for a load issued one loop iteration ahead of its use: the wait names every register of the
@@ -56,12 +56,12 @@ __device__ __forceinline__ void tmem_ld24(uint32_t taddr, Blk& b) {
 __device__ __forceinline__ void tmem_ld24_issue(uint32_t taddr, Blk& b) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n"
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%24+8];\n"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%24+16];\n"
       : "=r"(b.r[0]), "=r"(b.r[1]), "=r"(b.r[2]), "=r"(b.r[3]), "=r"(b.r[4]), "=r"(b.r[5]), "=r"(b.r[6]), "=r"(b.r[7]),
         "=r"(b.r[8]), "=r"(b.r[9]), "=r"(b.r[10]), "=r"(b.r[11]), "=r"(b.r[12]), "=r"(b.r[13]), "=r"(b.r[14]), "=r"(b.r[15]),
         "=r"(b.r[16]), "=r"(b.r[17]), "=r"(b.r[18]), "=r"(b.r[19]), "=r"(b.r[20]), "=r"(b.r[21]), "=r"(b.r[22]), "=r"(b.r[23])
-      : "r"(taddr), "r"(taddr + 8u), "r"(taddr + 16u)
+      : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld24_wait(Blk& b) {
@@ -76,15 +76,20 @@ __device__ __forceinline__ void tmem_ld24_wait(Blk& b) {
 __device__ __forceinline__ void tmem_st24(uint32_t taddr, const Blk& b) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%24], {%0,%1,%2,%3,%4,%5,%6,%7};\n"
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%25], {%8,%9,%10,%11,%12,%13,%14,%15};\n"
-      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%26], {%16,%17,%18,%19,%20,%21,%22,%23};\n" ::"r"(b.r[0]),
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%24+8], {%8,%9,%10,%11,%12,%13,%14,%15};\n"
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%24+16], {%16,%17,%18,%19,%20,%21,%22,%23};\n" ::"r"(b.r[0]),
       "r"(b.r[1]), "r"(b.r[2]), "r"(b.r[3]), "r"(b.r[4]), "r"(b.r[5]), "r"(b.r[6]), "r"(b.r[7]), "r"(b.r[8]), "r"(b.r[9]),
       "r"(b.r[10]), "r"(b.r[11]), "r"(b.r[12]), "r"(b.r[13]), "r"(b.r[14]), "r"(b.r[15]), "r"(b.r[16]), "r"(b.r[17]),
-      "r"(b.r[18]), "r"(b.r[19]), "r"(b.r[20]), "r"(b.r[21]), "r"(b.r[22]), "r"(b.r[23]), "r"(taddr), "r"(taddr + 8u),
-      "r"(taddr + 16u)
+      "r"(b.r[18]), "r"(b.r[19]), "r"(b.r[20]), "r"(b.r[21]), "r"(b.r[22]), "r"(b.r[23]), "r"(taddr)
       : "memory");
 }
-// value pair q of a block (q = 0: W*P, 1: logits, 2 + j: parameter group 1 + j of the row)
+// a register whose value does not matter (columns of a block nobody reads): defined for the compiler, no instruction
+__device__ __forceinline__ uint32_t any_reg() {
+  uint32_t r;
+  asm("" : "=r"(r));
+  return r;
+}
+// value pair q of a block (q = 0: W*P, 1: logits, 2 + j: parameter group 1 + j of the row, 11: W = exp(logit - max logit))
 __device__ __forceinline__ f2 blk_get(const Blk& b, int q) { return pk(__uint_as_float(b.r[2 * q]), __uint_as_float(b.r[2 * q + 1])); }
 __device__ __forceinline__ void blk_set(Blk& b, int q, f2 v) {
   b.r[2 * q] = __float_as_uint(lo(v));
@@ -122,7 +127,9 @@ __device__ __forceinline__ void tile_body_tm(const ModlArgs& a, unsigned char* s
   __syncthreads();
   tmem_fence_after_sync();
   // thread i of a warp <-> TMEM lane 32 * (warp % 4) + i; warps that share a lane quarter take kTmColsPerWarp columns each
-  const uint32_t tm = *tmem_base_p + (static_cast<uint32_t>(32 * (warp & 3)) << 16) + static_cast<uint32_t>(kTmColsPerWarp * (warp >> 2));
+  // (taken through a lane-0 shuffle: the block address feeds the uniform datapath, and this tells the compiler that it is warp-uniform)
+  const uint32_t tm = __shfl_sync(kFull, *tmem_base_p + (static_cast<uint32_t>(32 * (warp & 3)) << 16) +
+                                             static_cast<uint32_t>(kTmColsPerWarp * (warp >> 2)), 0);
 
   const long long gw = run_index(a, warp, nwarps);
   const bool lane_used = (lane / LPP) < PPT;
@@ -197,7 +204,7 @@ __device__ __forceinline__ void tile_body_tm(const ModlArgs& a, unsigned char* s
       const int prr = (pr + rot >= NPAIR) ? pr + rot - NPAIR : pr + rot;
       const int m = m0 + 2 * prr;
       Blk b;
-      b.r[0] = b.r[1] = b.r[22] = b.r[23] = 0u;
+      b.r[0] = b.r[1] = b.r[22] = b.r[23] = any_reg();
 #pragma unroll
       for (int g = 0; g < 10; ++g) blk_set(b, 1 + g, ld_pair<true>(rowp, g * M + m, false));
       const f2 lg = blk_get(b, 1);
@@ -279,7 +286,7 @@ __device__ __forceinline__ void tile_body_tm(const ModlArgs& a, unsigned char* s
         sumW2 = sumW2 + W;
         sumWP2 = fma2(W, P, sumWP2);
         Blk o;
-        o.r[22] = o.r[23] = 0u;
+        blk_set(o, 11, W);  // (the second pass takes W from here instead of forming it again)
         blk_set(o, 0, W * P);
         blk_set(o, 1, lg);
 #pragma unroll
@@ -321,15 +328,14 @@ __device__ __forceinline__ void tile_body_tm(const ModlArgs& a, unsigned char* s
         tmem_ld24(tm + 24u * pr, b);
         if (has_next) {
           Blk nb;
-          nb.r[0] = nb.r[1] = nb.r[22] = nb.r[23] = 0u;
+          nb.r[0] = nb.r[1] = nb.r[22] = nb.r[23] = any_reg();
 #pragma unroll
           for (int q = 0; q < 10; ++q) blk_set(nb, 1 + q, ld_pair<true>(rowp_next, q * M + m, false));
           const f2 nlg = blk_get(nb, 1);
           lmax_next = fmaxf(lmax_next, fmaxf(lo(nlg), hi(nlg)));
           tmem_st24(tm + 24u * pr, nb);
         }
-        const f2 lg = blk_get(b, 1);
-        const f2 W = ex2_2((lg - sp(lmax)) * kLog2e);
+        const f2 W = blk_get(b, 11);
         const f2 wp = blk_get(b, 0);
         f2 r = wp * rS;   // posterior responsibility of the component
         f2 pi = W * rSW;  // softmax(logits)
