@@ -81,8 +81,11 @@ class ClockSampler:
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
             # the first query of each kind can stall in the driver for tens of milliseconds (seen once at N = 2: one sample in an
             # 80 ms region, the launches of that rank held up with it): make it here, before the timed region starts
-            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            (getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.h)
+            try:
+                pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+                (getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.h)
+            except Exception:
+                pass
         except Exception:
             self.nv = None
 
