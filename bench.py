@@ -178,6 +178,23 @@ def barrier(world):
         dist.barrier()
 
 
+_GATE = None
+
+
+def start_gate(world, dev):
+    """After the host-side barrier + synchronize: a tiny all-reduce enqueued on the timing stream, so that every rank's timed
+    region begins at the same moment ON THE DEVICE.  Without it the ranks leave the host barrier a few hundred microseconds to
+    milliseconds apart (Python, NVML), and with an exchange inside the step the early ranks' timed regions then contain the
+    wait for the late ones -- 15-40 % of a 20-step region at 4-8 GPUs.  The begin event is recorded right behind the gate."""
+    global _GATE
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    if _GATE is None or _GATE.device != dev:
+        _GATE = torch.zeros(1, device=dev)
+    dist.all_reduce(_GATE)  # (the current stream waits for it; the host does not)
+
+
 def max_over_ranks(value, world, dev):
     if world == 1:
         return value
@@ -347,9 +364,11 @@ def run_sustained(step: ModlStep, seconds, ms_per_step, world, dev, sampler_inde
     run's time per step, so every rank enqueues the same number of steps."""
     n = max(10, int(math.ceil(seconds * 1e3 / ms_per_step * 1.08)))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(sampler_index, period_s=0.01)
     barrier(world)
     torch.cuda.synchronize(dev)
-    with ClockSampler(sampler_index, period_s=0.01) as clk:
+    with sampler as clk:
+        start_gate(world, dev)
         e0.record(step.stream)
         for _ in range(n):
             step.next_input()
@@ -378,9 +397,11 @@ def run_device_resident(step: ModlStep, steps, warmup, world, dev, sampler_index
     probes = [k for k in range(steps) if k % PROBE_EVERY == 0]
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(3)] for k in probes}
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(sampler_index)  # (NVML set-up before the barrier: it takes a different time on every rank)
     barrier(world)
     torch.cuda.synchronize(dev)
-    with ClockSampler(sampler_index) as clk:
+    with sampler as clk:
+        start_gate(world, dev)
         t0 = time.perf_counter()
         e_begin.record(step.stream)
         for k in range(steps):
@@ -547,6 +568,7 @@ def run_small_shape(name, world, dev, peak, steps=60, warm=6):
     torch.cuda.synchronize(dev)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start_gate(world, dev)
     e0.record(st.stream)
     for _ in range(steps):
         st.step()
@@ -640,6 +662,7 @@ def run_sample_split(S_total, B_per_gpu, H, W, M, steps, warm, world, rank, dev,
     torch.cuda.synchronize(dev)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start_gate(world, dev)
     e0.record(stream)
     for _ in range(steps):
         step()
