@@ -6,8 +6,9 @@
 // warp computes, none of its bytes are in flight, and while its gradient tile drains and the next tile lands, it waits (15 % of
 // the warp samples of the headline backward kernel sit on the mbarrier / bulk-group waits).  Blackwell's 256 KB of tensor
 // memory per SM are idle on this path (no contraction anywhere), and their geometry is exactly a warp's working set: a warp
-// may address 32 TMEM lanes (its quarter) -- one lane per thread, i.e. per pixel row of the tile -- and with 16 warps per CTA
-// 128 columns of 32 bits each: room for the 10 * MC floats a lane owns plus the W*P strip of the second pass.  So here
+// may address 32 TMEM lanes (its quarter) -- one lane per thread, i.e. per pixel row of the tile -- and, with twelve warps per
+// CTA (three per quarter), 168 of the 512 columns of 32 bits: room for the 10 * MC floats a lane owns plus the W*P and W pairs
+// the second pass takes over from the first.  So here
 //   * the shared-memory slot X is only the landing / staging area of the TMA engine,
 //   * the tile being worked on lives in tensor memory C (tcgen05.st / tcgen05.ld, shape 32x32b: thread i <-> TMEM lane i),
 //     laid out as one 24-column block per component pair: [W*P | logits | mu s k (R) | mu s k (G) | mu s k (B) | W],
@@ -15,7 +16,9 @@
 //   * pass 1 (unscaled derivatives, mixture sums) runs entirely on C while X receives the NEXT tile,
 //   * pass 2 swaps column block by column block: it takes the unscaled derivatives of tile k out of C, moves the parameters
 //     of tile k+1 from X into the block of C it just emptied, and puts the final gradient of tile k into the positions of X
-//     it just read; then X goes to global memory as one bulk store and is refilled during pass 1 of tile k+1.
+//     it just read; then X goes to global memory as one bulk store and is refilled late in pass 1 of tile k+1 (before its
+//     last component pair: the store drains slowly while the memory system is saturated with writes, and a warp that asks
+//     earlier blocks on it -- measured 309 ... 271 us for "before pair 0 ... 4").
 // The arithmetic and its order are those of tile_body<.., BWD, 1, ..>: the gradients are bit-identical to that kernel's.
 #include "modl_tile.cuh"
 
