@@ -200,8 +200,10 @@ static int launch_tiled_tm(ModlArgs a, cudaStream_t st, TilePlan* plan) {
     // where in the first pass the staging slot is refilled: as late as possible -- before the LAST component pair -- measured
     // best everywhere (VAEMDL_TM_REFILL=<pair> / NPAIR = after the pass: headline gradient kernel 309 / 305 / 302 / 289 / 271 / 285 us
     // for 0 ... 5): the gradient tile the slot still holds drains slowly while the memory system is saturated with writes
+    // (a problem of a few tiles per warp does not saturate the write path: there one pair earlier is 1-3 % ahead, tools/ab_tm.sh)
     static const int refill = [] { const char* e = getenv("VAEMDL_TM_REFILL"); return e ? atoi(e) : -1; }();
-    a.tm_refill = refill < 0 ? T::NPAIR - 1 : (refill < T::NPAIR ? refill : T::NPAIR);
+    const bool few_tiles = a.num_tiles < total_warps * 12 && T::NPAIR >= 3;
+    a.tm_refill = refill < 0 ? T::NPAIR - (few_tiles ? 2 : 1) : (refill < T::NPAIR ? refill : T::NPAIR);
   }
   if (plan) {
     plan->total_warps = total_warps;
