@@ -159,3 +159,32 @@ def test_u8_to_unit_recipe_is_exact_for_every_byte():
         assert q1 == want, k
         bare += int(q0 != want)
     assert bare > 0
+
+
+def _bench_timing_worker(rank, world, port, out_dir):
+    """bench.py's multi-rank timing plumbing on a gloo group: host barrier, the device-side start gate (a tiny all-reduce on the
+    timing stream; a plain all-reduce here), max over ranks."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        dev = torch.device("cpu")
+        bench.barrier(world)
+        bench.start_gate(world, dev)
+        bench.start_gate(world, dev)          # (the gate tensor is reused)
+        bench.start_gate(1, dev)              # no-op on one rank
+        worst = bench.max_over_ranks(10.0 + rank, world, dev)
+        torch.save(torch.tensor([worst]), os.path.join(out_dir, f"t{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_start_gate_and_max_over_ranks_world_size_2_gloo(tmp_path):
+    port = _free_port()
+    tmp.spawn(_bench_timing_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(os.path.join(tmp_path, "t0.pt"))
+    b = torch.load(os.path.join(tmp_path, "t1.pt"))
+    assert a.item() == 11.0 and b.item() == 11.0      # every rank reports the slowest rank's time
